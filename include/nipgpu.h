@@ -1,0 +1,210 @@
+/* nipgpu.h — C ABI of the B200 (sm_100a) backend for NIP's join-tree hot path.
+ *
+ * The reference (manuelschmidt/nip) has no plugin/FFI seam: its boundary is the
+ * public C API of src/nip.h.  This header is what a `nip.h` implementation binds
+ * to in order to run that API on the GPU:  plain pointers and sizes, no
+ * reference types, no torch types.  Every entry point names the reference
+ * function(s) it replaces.  The host-side glue that walks a `nip_model` and
+ * calls these functions is nip_b200/host/nip_gpu_backend.c.
+ *
+ * Conventions
+ *   - all functions return 0 on success or a NIPGPU_E* code; the message of the
+ *     last failure on the calling thread is available from nipgpu_last_error();
+ *   - all tables are IEEE double, flat, dimension 0 fastest
+ *     (src/nippotential.c:58-68), indices are 32-bit like the reference's `int`;
+ *   - variables are numbered 0..n_vars-1 in `model->variables[]` order
+ *     (= ascending variable id = .net declaration order, src/nipvariable.c:72);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call
+ *     fails with NIPGPU_ENODEVICE.
+ */
+#ifndef NIPGPU_H
+#define NIPGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIPGPU_OK          0
+#define NIPGPU_EINVAL      1   /* malformed description / argument            */
+#define NIPGPU_ENODEVICE   2   /* no CUDA device / wrong architecture         */
+#define NIPGPU_ECUDA       3   /* a CUDA runtime call failed                  */
+#define NIPGPU_ENOMEM      4
+#define NIPGPU_EUNSUPPORTED 5  /* model outside what the device path handles  */
+#define NIPGPU_EBADLUCK    8   /* = NIP_ERROR_BAD_LUCK (src/nip.c:1827-1854)  */
+
+/* interface_status bits, identical to src/nipvariable.h:30-34 */
+#define NIPGPU_IF_INCOMING      1
+#define NIPGPU_IF_OUTGOING      2
+#define NIPGPU_IF_OLD_OUTGOING  4
+
+/* engine selection for nipgpu_model_create (0 = let the compiler choose) */
+#define NIPGPU_ENGINE_AUTO   0
+#define NIPGPU_ENGINE_JTREE  1  /* generic join-tree schedule (any model)     */
+#define NIPGPU_ENGINE_CHAIN  2  /* interface-clique + leaves, DMMA contraction*/
+
+/* Flat description of one parsed time-slice model.  It is a by-value snapshot
+ * of what parse_model() leaves in nip_model_struct (src/nip.h:71-112) and in
+ * the nip_clique / nip_sepset / nip_variable structs reachable from it
+ * (src/nipjointree.h:43-63, src/nipvariable.h:51-78).  The library copies
+ * everything it needs; the caller keeps ownership of the arrays. */
+typedef struct nipgpu_model_desc {
+  /* ---- variables ---- */
+  int32_t n_vars;
+  const int32_t* var_card;        /* [n_vars] cardinality                        */
+  const int32_t* var_flags;       /* [n_vars] NIPGPU_IF_* bits                   */
+  const int32_t* var_parent_off;  /* [n_vars+1] offsets into var_parents         */
+  const int32_t* var_parents;     /* parents in variable->parents[] order        */
+  const int32_t* var_family;      /* [n_vars] family clique (nip_find_family)    */
+  const int32_t* var_prior_off;   /* [n_vars+1] offsets into var_prior           */
+  const double*  var_prior;       /* priors of parentless variables, 0 length
+                                     for variables that have parents            */
+  /* ---- cliques ---- */
+  int32_t n_cliques;
+  const int32_t* clique_var_off;  /* [n_cliques+1]                               */
+  const int32_t* clique_vars;     /* variables of each clique, dim 0 first       */
+  const int64_t* clique_tab_off;  /* [n_cliques+1] offsets into clique_tables    */
+  const double*  clique_tables;   /* original_p of every clique, concatenated    */
+  /* ---- sepsets ---- */
+  int32_t n_sepsets;
+  const int32_t* sepset_cliques;  /* [n_sepsets][2] first/second neighbour       */
+  const int32_t* sepset_var_off;  /* [n_sepsets+1]                               */
+  const int32_t* sepset_vars;     /* variables of each sepset, dim 0 first       */
+  const int32_t* clique_adj_off;  /* [n_cliques+1] offsets into clique_adj       */
+  const int32_t* clique_adj;      /* sepset ids in clique->sepsets list order    */
+  /* ---- time-slice interface (src/nip.h:88-99) ---- */
+  int32_t n_interface;            /* outgoing_interface_size                     */
+  const int32_t* outgoing;        /* [n_interface] I_t      (alpha/gamma dims)   */
+  const int32_t* prev_outgoing;   /* [n_interface] I_{t-1}, same index order     */
+  int32_t in_clique;              /* -1 when n_interface == 0                    */
+  int32_t out_clique;
+} nipgpu_model_desc;
+
+typedef struct nipgpu_model nipgpu_model;   /* compiled model, device resident  */
+typedef struct nipgpu_batch nipgpu_batch;   /* a set of time series in HBM      */
+
+const char* nipgpu_last_error(void);
+/* 0 when a CUDA device of compute capability 10.x is usable */
+int nipgpu_device_check(int device);
+
+/* Compile a model: index maps / projections, message schedule, device upload
+ * of original_p and priors.  Replaces the per-call nip_mapper()+malloc of
+ * nip_message_pass (src/nipjointree.c:676-709) and the per-entry
+ * nip_inverse_mapping loops (src/nippotential.c:251-264). */
+int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine,
+                        nipgpu_model** out);
+void nipgpu_model_destroy(nipgpu_model* m);
+/* which engine the compiler picked (NIPGPU_ENGINE_*) */
+int nipgpu_model_engine(const nipgpu_model* m);
+
+/* Replace all clique tables / priors (same layout as in the description), e.g.
+ * after the host changed original_p.  Replaces nothing in the reference: it is
+ * the H2D half of keeping `clique->original_p` authoritative on the host. */
+int nipgpu_model_set_parameters(nipgpu_model* m, const double* clique_tables,
+                                const double* var_prior);
+/* D2H: current device parameters → host arrays (after EM), so write_model()
+ * (src/nip.c:298-482) sees the trained CPTs. */
+int nipgpu_model_get_parameters(nipgpu_model* m, double* clique_tables,
+                                double* var_prior);
+
+/* Upload a set of time series (time_series_struct, src/nip.h:117-131).
+ *   n_series    number of series
+ *   lengths     [n_series] slices per series (ragged sets allowed)
+ *   n_obs       number of observed columns (ts->num_of_observed)
+ *   obs_vars    [n_obs] model variable of each column (ts->observed[])
+ *   data        concatenated rows, series after series: sum(lengths) x n_obs
+ *               state indices, < 0 = missing (src/nip.c:649, :994)
+ * Replaces the per-slice insert_ts_step() evidence entry (src/nip.c:982-1001):
+ * observations stay packed in HBM for the whole job. */
+int nipgpu_batch_create(nipgpu_model* m, int32_t n_series, const int32_t* lengths,
+                        int32_t n_obs, const int32_t* obs_vars, const int32_t* data,
+                        nipgpu_batch** out);
+void nipgpu_batch_destroy(nipgpu_batch* b);
+
+/* Batched forward_inference / forward_backward_inference
+ * (src/nip.c:1103-1315, 1320-1581) for every series of the batch.
+ *   use_evidence [n_vars] non-zero = variable is marked (NIP_MARK_ON): only
+ *                these columns enter evidence (src/nip.c:993); NULL = all
+ *   query_vars   [n_query] variables of interest
+ *   forward_only non-zero = filtering (forward_inference)
+ *   post         host, sum(lengths) rows x (sum of card(query_vars)) doubles:
+ *                row r of series s, variables in query order, or NULL
+ *   loglik       host [n_series] total log-likelihood per series as the
+ *                reference accumulates it (sum_t log m2 - log m1), or NULL
+ * Host buffers; H2D of nothing (batch is resident), D2H of post/loglik. */
+int nipgpu_infer(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence,
+                 int32_t n_query, const int32_t* query_vars, int forward_only,
+                 double* post, double* loglik);
+
+/* Same computation, results left in HBM (for callers that chain device work
+ * and for kernel-only timing).  *post_dev / *loglik_dev receive device
+ * pointers owned by the batch, valid until the next call on that batch. */
+int nipgpu_infer_device(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence,
+                        int32_t n_query, const int32_t* query_vars, int forward_only,
+                        int want_loglik, double** post_dev, double** loglik_dev);
+
+/* One E-step over the batch with the current device parameters
+ * (e_step for every series, src/nip.c:1708-2007): expected family counts are
+ * accumulated in HBM, starting from the reference's 1.0 pseudo-count
+ * (src/nip.c:2171-2172) when `add_pseudocount` is non-zero.
+ *   counts   host or NULL: per-variable family tables, child first then
+ *            parents[] order (src/nip.c:2108-2128), concatenated in variable
+ *            order; use nipgpu_model_counts_size() for the length
+ *   loglik   sum over series
+ *   status   0, or NIPGPU_EBADLUCK if any slice had m1<=0, m2<=0 or a running
+ *            log-likelihood > 0 (src/nip.c:1827-1854) */
+int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence,
+                    int add_pseudocount, double* counts, double* loglik, int* status);
+int64_t nipgpu_model_counts_size(const nipgpu_model* m);
+/* [n_vars+1] offsets of each variable's family table inside `counts` */
+int nipgpu_model_counts_offsets(const nipgpu_model* m, int64_t* off);
+
+/* Device pointer to the count accumulator (+2 trailing doubles: loglik, status)
+ * so a multi-GPU caller can all-reduce it in place (one ncclAllReduce per EM
+ * iteration) before the M-step. */
+int nipgpu_em_counts_device(nipgpu_model* m, double** counts_dev, int64_t* n_doubles);
+
+/* M-step on the device from the accumulator (m_step, src/nip.c:2010-2071):
+ * normalise_cpd, reset cliques to 1, multiply CPTs into family cliques,
+ * priors <- normalised counts of parentless variables.  When `counts` is not
+ * NULL it is uploaded first (used for the random initial parameters of
+ * em_learn, src/nip.c:2135-2154). */
+int nipgpu_em_mstep(nipgpu_model* m, const double* counts);
+
+/* niplikelihood inner loop (util/niplikelihood.c:111-135) for every slice of
+ * every series, slices evaluated independently (no inter-slice message):
+ *   m1 = mass with the evidence of variables flagged in `evidence_off`
+ *   m2 = mass with, in addition, the evidence of those in `evidence_on`
+ * out: host, sum(lengths) x 2 doubles (m1, m2). */
+int nipgpu_likelihood(nipgpu_model* m, nipgpu_batch* b, const uint8_t* evidence_off,
+                      const uint8_t* evidence_on, double* out);
+
+/* ---- single-slice, stateful API (B = 1) --------------------------------
+ * Device counterparts of reset_model / use_priors / nip_enter_evidence /
+ * make_consistent / model_prob_mass / get_probability (src/nip.c:61-119,
+ * 1600-1617, 2254-2298; src/nipjointree.c:859-943) for callers that drive
+ * slices by hand (util/nipjoint.c, test/hmmtest.c). */
+int nipgpu_slice_reset(nipgpu_model* m);
+int nipgpu_slice_use_priors(nipgpu_model* m, int has_history);
+int nipgpu_slice_enter_evidence(nipgpu_model* m, int32_t var, const double* likelihood);
+int nipgpu_slice_make_consistent(nipgpu_model* m);
+int nipgpu_slice_mass(nipgpu_model* m, double* mass);
+int nipgpu_slice_marginal(nipgpu_model* m, int32_t var, double* out /*[card]*/);
+/* D2H copy of a clique's current belief table (clique->p) */
+int nipgpu_slice_get_clique(nipgpu_model* m, int32_t clique, double* out);
+
+/* ---- instrumentation -------------------------------------------------- */
+/* number of kernels this library launched since the counter was last reset */
+int64_t nipgpu_launch_count(int reset);
+/* milliseconds the GPU spent in the dominant kernel(s) of the last
+ * nipgpu_infer / nipgpu_em_estep call, measured with CUDA events on the library's
+ * stream; n receives the number of launches summed. */
+int nipgpu_last_kernel_ms(nipgpu_model* m, double* ms, int32_t* n);
+/* the CUDA stream (cudaStream_t) all work of this model is enqueued on */
+void* nipgpu_model_stream(nipgpu_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIPGPU_H */
