@@ -1,0 +1,686 @@
+// api.cu — implementation of the C ABI declared in include/nipgpu.h.
+#include "api.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace nipgpu {
+
+static thread_local std::string g_error;
+int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+
+namespace {
+
+template <class T>
+int dev_upload(T** dst, const T* src, size_t n, cudaStream_t st) {
+  NIPGPU_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) NIPGPU_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return NIPGPU_OK;
+}
+
+template <class T>
+int dev_upload(T** dst, const std::vector<T>& v, cudaStream_t st) {
+  return dev_upload(dst, v.data(), v.size(), st);
+}
+
+int fail(int code, const std::string& msg) {
+  set_error(msg);
+  return code;
+}
+
+// ---- launch geometry of the generic engine ------------------------------
+int choose_launch(nipgpu_model* m) {
+  const HostModel& hm = m->hm;
+  int biggest = 1;
+  for (int c = 0; c < hm.nc; c++) biggest = std::max(biggest, hm.csize[c]);
+  JtLaunch& l = m->launch;
+  l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
+  const size_t bytes = jt_work_doubles(m->prog) * sizeof(double);
+  if (bytes <= 200 * 1024) {
+    l.smem_bytes = bytes;
+    l.gwork = nullptr;
+    const int by_smem = (int)std::max<size_t>(1, (220 * 1024) / (bytes + 1024));
+    const int by_threads = 2048 / l.threads;
+    l.grid = m->sm_count * std::max(1, std::min({by_smem, by_threads, 16}));
+  } else {
+    l.smem_bytes = 0;
+    size_t ctas = (size_t)m->sm_count * 2;
+    const size_t budget = (size_t)32 << 30;  // keep the workspace under 32 GB
+    while (ctas > 1 && ctas * bytes > budget) ctas /= 2;
+    if (m->gwork_doubles < ctas * jt_work_doubles(m->prog)) {
+      cudaFree(m->d_gwork);
+      m->gwork_doubles = ctas * jt_work_doubles(m->prog);
+      NIPGPU_CUDA(cudaMalloc((void**)&m->d_gwork, m->gwork_doubles * sizeof(double)));
+    }
+    l.gwork = m->d_gwork;
+    l.grid = (int)ctas;
+  }
+  return NIPGPU_OK;
+}
+
+// base0/base1, calibration vectors and the chain-engine tables from d_orig / d_prior
+int refresh_derived(nipgpu_model* m) {
+  const HostModel& hm = m->hm;
+  cudaStream_t st = m->stream;
+  const size_t tab_bytes = (size_t)m->prog.tab_total * sizeof(double);
+  NIPGPU_CUDA(cudaMemcpyAsync(m->d_base1, m->d_orig, tab_bytes, cudaMemcpyDeviceToDevice, st));
+  const int np = (int)hm.prior_vars.size();
+  if (int e = prior_flags(m->d_prior, m->d_prior_off, m->d_prior_vars, np, m->d_prior_flags, st)) return e;
+  auto apply = [&](double* base, int k) {
+    const int v = hm.prior_vars[k], c = hm.family[v];
+    int stride = 1;
+    for (int j = 0; j < hm.var_pos(c, v); j++) stride *= hm.card[hm.clique_vars(c)[j]];
+    return apply_vector(base + m->tab_off[c], hm.csize[c], stride, hm.card[v],
+                        m->d_prior + hm.prior_off[v], m->d_prior_flags + k, st);
+  };
+  for (int k = 0; k < np; k++)  // priors kept when the slice has history (src/nip.c:100)
+    if (!(hm.flags[hm.prior_vars[k]] & NIPGPU_IF_OLD_OUTGOING))
+      if (int e = apply(m->d_base1, k)) return e;
+  NIPGPU_CUDA(cudaMemcpyAsync(m->d_base0, m->d_base1, tab_bytes, cudaMemcpyDeviceToDevice, st));
+  for (int k = 0; k < np; k++)
+    if (hm.flags[hm.prior_vars[k]] & NIPGPU_IF_OLD_OUTGOING)
+      if (int e = apply(m->d_base0, k)) return e;
+  JtLaunch one = m->launch;
+  if (one.gwork == nullptr && one.smem_bytes == 0) return fail(NIPGPU_EINVAL, "launch not configured");
+  if (int e = jt_calibrate(m->prog, one, m->d_R1, m->d_m10, st)) return e;
+  if (m->chain.ok)
+    if (int e = chain_refresh(hm, m->chain, m->d_base0, m->d_base1, m->tab_off, m->d_ipool, st)) return e;
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  m->slice_consistent = false;
+  return NIPGPU_OK;
+}
+
+int ensure_post(nipgpu_batch* b, size_t doubles) {
+  if (b->post_cap >= doubles) return NIPGPU_OK;
+  cudaFree(b->d_post);
+  b->d_post = nullptr;
+  b->post_cap = 0;
+  NIPGPU_CUDA(cudaMalloc((void**)&b->d_post, std::max<size_t>(doubles, 1) * sizeof(double)));
+  b->post_cap = doubles;
+  return NIPGPU_OK;
+}
+
+DBatch dev_batch(const nipgpu_batch* b, const int* obs_proj) {
+  DBatch d;
+  d.n_series = b->n_series; d.n_obs = b->n_obs; d.len = b->d_len; d.row_off = b->d_row_off;
+  d.obs = b->d_obs; d.obs_proj = obs_proj;
+  return d;
+}
+
+// evidence columns -> projection ids (or -1) in slot `which` of the batch scratch
+int upload_obs_proj(nipgpu_model* m, nipgpu_batch* b, const uint8_t* mask, bool null_means_all,
+                    int which, const int** out) {
+  std::vector<int> p(std::max(b->n_obs, 1), -1);
+  for (int k = 0; k < b->n_obs; k++) {
+    const int v = b->obs_vars[k];
+    const bool on = mask ? mask[v] != 0 : null_means_all;
+    p[k] = on ? m->hm.proj_var[v] : -1;
+  }
+  int* dst = b->d_obs_proj + (size_t)which * std::max(b->n_obs, 1);
+  NIPGPU_CUDA(cudaMemcpyAsync(dst, p.data(), p.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));  // `p` dies here
+  *out = dst;
+  return NIPGPU_OK;
+}
+
+int upload_query(nipgpu_model* m, nipgpu_batch* b, int nq, const int32_t* q, DQuery* out) {
+  const HostModel& hm = m->hm;
+  std::vector<int> proj(std::max(nq, 1), 0), off(std::max(nq, 1), 0);
+  int row = 0;
+  for (int i = 0; i < nq; i++) {
+    if (q[i] < 0 || q[i] >= hm.nv) return fail(NIPGPU_EINVAL, "query variable out of range");
+    proj[i] = hm.proj_var[q[i]];
+    off[i] = row;
+    row += hm.card[q[i]];
+  }
+  if (b->q_cap < (size_t)std::max(nq, 1)) {
+    cudaFree(b->d_qproj); cudaFree(b->d_qoff);
+    b->q_cap = std::max(nq, 1);
+    NIPGPU_CUDA(cudaMalloc((void**)&b->d_qproj, b->q_cap * sizeof(int)));
+    NIPGPU_CUDA(cudaMalloc((void**)&b->d_qoff, b->q_cap * sizeof(int)));
+  }
+  NIPGPU_CUDA(cudaMemcpyAsync(b->d_qproj, proj.data(), proj.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  NIPGPU_CUDA(cudaMemcpyAsync(b->d_qoff, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  out->n_query = nq; out->row = row; out->proj = b->d_qproj; out->off = b->d_qoff;
+  return NIPGPU_OK;
+}
+
+int ensure_alpha(nipgpu_model* m, nipgpu_batch* b) {
+  if (b->d_alpha) return NIPGPU_OK;
+  NIPGPU_CUDA(cudaMalloc((void**)&b->d_alpha,
+                         std::max<size_t>((size_t)b->rows * m->hm.S, 1) * sizeof(double)));
+  return NIPGPU_OK;
+}
+
+int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int nq,
+               const int32_t* query, int forward_only, int want_ll, bool want_post) {
+  if (!m || !b || b->m != m) return fail(NIPGPU_EINVAL, "model/batch mismatch");
+  const HostModel& hm = m->hm;
+  DQuery Q{};
+  if (int e = upload_query(m, b, nq, query, &Q)) return e;
+  if (want_post)
+    if (int e = ensure_post(b, (size_t)b->rows * std::max(Q.row, 1))) return e;
+  double* post = want_post && nq > 0 ? b->d_post : nullptr;
+  m->last_kernel_ms = 0;
+  m->last_kernel_n = 0;
+
+  // ---- engine 2 when the model, the evidence columns and the query allow it ----
+  ChainPlan plan;
+  const bool query_is_interface = nq == 0 || (nq == 1 && hm.nif == 1 && query[0] == hm.outg[0]);
+  if (m->engine == NIPGPU_ENGINE_CHAIN && m->chain.ok && query_is_interface &&
+      chain_plan(hm, m->chain, b->n_obs, b->obs_vars.data(), use_evidence, plan)) {
+    if (int e = chain_batch_prepare(m->chain, b->chain, b->n_series, b->len.data(), b->rows, b->t_max, m->stream)) return e;
+    ChainInferArgs a;
+    a.n_series = b->n_series; a.n_obs = b->n_obs; a.t_max = b->t_max; a.rows = b->rows;
+    a.d_obs = b->d_obs; a.d_row_off = b->d_row_off; a.want_ll = want_ll; a.forward_only = forward_only;
+    a.d_post = post; a.post_stride = Q.row; a.post_off = 0;
+    a.d_ll = b->d_ll; a.d_status = b->d_status;
+    if (int e = chain_infer(hm, m->chain, b->chain, plan, a, m->stream, m->ev0, m->ev1)) return e;
+    NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    if (b->n_series > 0 && cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) {
+      m->last_kernel_ms = ms;
+      m->last_kernel_n = forward_only ? 1 : 2;
+    }
+    return NIPGPU_OK;
+  }
+
+  // ---- generic join-tree engine ----
+  const int* obs_proj = nullptr;
+  if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;
+  if (int e = ensure_alpha(m, b)) return e;
+  const DBatch B = dev_batch(b, obs_proj);
+  JtLaunch l = m->launch;
+  l.grid = std::max(1, std::min(l.grid, b->n_series));
+  NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
+  if (int e = jt_forward(m->prog, B, Q, l, want_ll, forward_only, b->d_alpha, forward_only ? post : nullptr,
+                         b->d_ll, b->d_status, m->stream)) return e;
+  if (!forward_only)
+    if (int e = jt_backward(m->prog, B, Q, l, b->d_alpha, post, nullptr, 0, m->stream)) return e;
+  NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) {
+    m->last_kernel_ms = ms;
+    m->last_kernel_n = forward_only ? 1 : 2;
+  }
+  return NIPGPU_OK;
+}
+
+}  // namespace
+}  // namespace nipgpu
+
+using namespace nipgpu;
+
+extern "C" {
+
+const char* nipgpu_last_error(void) { return g_error.c_str(); }
+
+int nipgpu_device_check(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(NIPGPU_ENODEVICE, "no CUDA device");
+  if (device < 0 || device >= n) return fail(NIPGPU_ENODEVICE, "device index out of range");
+  cudaDeviceProp p;
+  NIPGPU_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return fail(NIPGPU_ENODEVICE, std::string("device is not sm_100-class (Blackwell B200): ") + p.name);
+  return NIPGPU_OK;
+}
+
+int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, nipgpu_model** out) {
+  if (!out) return fail(NIPGPU_EINVAL, "null out pointer");
+  *out = nullptr;
+  if (int e = nipgpu_device_check(device)) return e;
+  NIPGPU_CUDA(cudaSetDevice(device));
+  nipgpu_model* m = new nipgpu_model();
+  m->device = device;
+  const std::string err = m->hm.load(desc);
+  if (!err.empty()) { delete m; return fail(NIPGPU_EINVAL, "model description: " + err); }
+  HostModel& hm = m->hm;
+  for (int c = 0; c < hm.nc; c++)
+    if (hm.clique_dim(c) > kMaxDims) { delete m; return fail(NIPGPU_EUNSUPPORTED, "clique with too many variables"); }
+  const std::string why = chain_build(hm, m->chain);
+  if (engine == NIPGPU_ENGINE_CHAIN && !m->chain.ok) { delete m; return fail(NIPGPU_EUNSUPPORTED, "chain engine: " + why); }
+  m->engine = engine == NIPGPU_ENGINE_JTREE ? NIPGPU_ENGINE_JTREE
+                                            : (m->chain.ok ? NIPGPU_ENGINE_CHAIN : NIPGPU_ENGINE_JTREE);
+  cudaDeviceProp prop;
+  NIPGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+  m->sm_count = prop.multiProcessorCount;
+  NIPGPU_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  NIPGPU_CUDA(cudaEventCreate(&m->ev0));
+  NIPGPU_CUDA(cudaEventCreate(&m->ev1));
+  cudaStream_t st = m->stream;
+
+  // ---- table offsets (int: the reference indexes tables with int too) ----
+  if (hm.toff[hm.nc] > INT32_MAX) { nipgpu_model_destroy(m); return fail(NIPGPU_EUNSUPPORTED, "tables exceed 2^31 entries"); }
+  m->tab_off.resize(hm.nc + 1);
+  for (int c = 0; c <= hm.nc; c++) m->tab_off[c] = (int)hm.toff[c];
+
+  // ---- projections -> one int pool ----
+  std::vector<int> pool;
+  std::vector<DProj> dp(hm.projs.size());
+  for (size_t i = 0; i < hm.projs.size(); i++) {
+    Proj& p = hm.projs[i];
+    p.base_pos = (int)pool.size();
+    pool.insert(pool.end(), p.base.begin(), p.base.end());
+    p.off_pos = (int)pool.size();
+    pool.insert(pool.end(), p.off.begin(), p.off.end());
+    dp[i].tab = m->tab_off[p.clique]; dp[i].m = p.m; dp[i].R = p.R; dp[i].lanes = p.lanes;
+    dp[i].base = p.base_pos; dp[i].off = p.off_pos;
+  }
+  auto to_dmsg = [&](const std::vector<Msg>& v) {
+    std::vector<DMsg> r(v.size());
+    for (size_t i = 0; i < v.size(); i++) r[i] = DMsg{v[i].proj_src, v[i].proj_dst, v[i].slot, v[i].size};
+    return r;
+  };
+  int e = 0;
+  std::vector<long long> coff(hm.coff.begin(), hm.coff.end());
+  if ((e = dev_upload(&m->d_ipool, pool, st)) || (e = dev_upload(&m->d_projs, dp, st)) ||
+      (e = dev_upload(&m->d_collect, to_dmsg(hm.collect), st)) ||
+      (e = dev_upload(&m->d_distribute, to_dmsg(hm.distribute), st)) ||
+      (e = dev_upload(&m->d_path, to_dmsg(hm.path_to_out), st)) ||
+      (e = dev_upload(&m->d_proj_var, hm.proj_var, st)) || (e = dev_upload(&m->d_proj_fam, hm.proj_fam, st)) ||
+      (e = dev_upload(&m->d_var_flags, hm.flags, st)) || (e = dev_upload(&m->d_coff, coff, st)) ||
+      (e = dev_upload(&m->d_prior_off, hm.prior_off, st)) || (e = dev_upload(&m->d_prior_vars, hm.prior_vars, st)) ||
+      (e = dev_upload(&m->d_orig, hm.tables, st)) || (e = dev_upload(&m->d_prior, hm.prior, st))) {
+    nipgpu_model_destroy(m);
+    return e;
+  }
+  NIPGPU_CUDA(cudaStreamSynchronize(st));  // the temporaries above die here
+  const size_t T = (size_t)m->tab_off[hm.nc];
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_prior_flags, std::max<size_t>(hm.prior_vars.size(), 1) * sizeof(int)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_base0, T * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_base1, T * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_R1, (size_t)hm.S * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_m10, sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_counts, (size_t)(hm.coff[hm.nv] + 2) * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_slice_start, T * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_slice_tab, T * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&m->d_slice_msg, (size_t)std::max(hm.msg_total, 1) * sizeof(double)));
+
+  DProgram& P = m->prog;
+  P.tab_total = (int)T; P.msg_total = hm.msg_total; P.msg_max = hm.msg_max;
+  P.scratch = std::max({hm.fam_max, hm.card_max, hm.S, 1});
+  P.n_collect = (int)hm.collect.size(); P.n_distribute = (int)hm.distribute.size();
+  P.n_path = (int)hm.path_to_out.size();
+  P.nif = hm.nif; P.S = hm.S; P.proj_in = hm.proj_in; P.proj_out = hm.proj_out;
+  P.root_tab = m->tab_off[0]; P.root_size = hm.csize[0]; P.nv = hm.nv;
+  P.projs = m->d_projs; P.ipool = m->d_ipool; P.collect = m->d_collect; P.distribute = m->d_distribute;
+  P.path = m->d_path; P.base0 = m->d_base0; P.base1 = m->d_base1; P.R1 = m->d_R1; P.m1_0 = m->d_m10;
+  P.proj_var = m->d_proj_var; P.proj_fam = m->d_proj_fam; P.coff = m->d_coff; P.var_flags = m->d_var_flags;
+
+  if ((e = choose_launch(m)) || (e = chain_upload_structure(hm, m->chain, st)) || (e = refresh_derived(m))) {
+    nipgpu_model_destroy(m);
+    return e;
+  }
+  m->lik.resize(hm.nv);
+  for (int v = 0; v < hm.nv; v++) m->lik[v].assign(hm.card[v], 1.0);
+  m->prior_entered.assign(hm.nv, 0);
+  *out = m;
+  return NIPGPU_OK;
+}
+
+void nipgpu_model_destroy(nipgpu_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaFree(m->d_ipool); cudaFree(m->d_projs); cudaFree(m->d_collect); cudaFree(m->d_distribute);
+  cudaFree(m->d_path); cudaFree(m->d_proj_var); cudaFree(m->d_proj_fam); cudaFree(m->d_var_flags);
+  cudaFree(m->d_coff); cudaFree(m->d_prior_off); cudaFree(m->d_prior_vars); cudaFree(m->d_prior_flags);
+  cudaFree(m->d_orig); cudaFree(m->d_prior); cudaFree(m->d_base0); cudaFree(m->d_base1);
+  cudaFree(m->d_R1); cudaFree(m->d_m10); cudaFree(m->d_counts); cudaFree(m->d_acc); cudaFree(m->d_gwork);
+  cudaFree(m->d_slice_start); cudaFree(m->d_slice_tab); cudaFree(m->d_slice_msg);
+  chain_free(m->chain);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int nipgpu_model_engine(const nipgpu_model* m) { return m ? m->engine : 0; }
+void* nipgpu_model_stream(nipgpu_model* m) { return m ? (void*)m->stream : nullptr; }
+
+int nipgpu_model_set_parameters(nipgpu_model* m, const double* tables, const double* prior) {
+  if (!m || !tables) return fail(NIPGPU_EINVAL, "null argument");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  NIPGPU_CUDA(cudaMemcpyAsync(m->d_orig, tables, (size_t)m->prog.tab_total * sizeof(double),
+                              cudaMemcpyHostToDevice, m->stream));
+  if (prior && m->hm.prior_off[m->hm.nv] > 0)
+    NIPGPU_CUDA(cudaMemcpyAsync(m->d_prior, prior, (size_t)m->hm.prior_off[m->hm.nv] * sizeof(double),
+                                cudaMemcpyHostToDevice, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  return refresh_derived(m);
+}
+
+int nipgpu_model_get_parameters(nipgpu_model* m, double* tables, double* prior) {
+  if (!m) return fail(NIPGPU_EINVAL, "null argument");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  if (tables)
+    NIPGPU_CUDA(cudaMemcpyAsync(tables, m->d_orig, (size_t)m->prog.tab_total * sizeof(double),
+                                cudaMemcpyDeviceToHost, m->stream));
+  if (prior && m->hm.prior_off[m->hm.nv] > 0)
+    NIPGPU_CUDA(cudaMemcpyAsync(prior, m->d_prior, (size_t)m->hm.prior_off[m->hm.nv] * sizeof(double),
+                                cudaMemcpyDeviceToHost, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  return NIPGPU_OK;
+}
+
+int nipgpu_batch_create(nipgpu_model* m, int32_t n_series, const int32_t* lengths, int32_t n_obs,
+                        const int32_t* obs_vars, const int32_t* data, nipgpu_batch** out) {
+  if (!m || !out || n_series < 0 || n_obs < 0) return fail(NIPGPU_EINVAL, "bad batch arguments");
+  *out = nullptr;
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  nipgpu_batch* b = new nipgpu_batch();
+  b->m = m; b->n_series = n_series; b->n_obs = n_obs;
+  b->len.assign(lengths, lengths + n_series);
+  b->obs_vars.assign(obs_vars, obs_vars + n_obs);
+  for (int k = 0; k < n_obs; k++)
+    if (obs_vars[k] < 0 || obs_vars[k] >= m->hm.nv) { delete b; return fail(NIPGPU_EINVAL, "observed variable out of range"); }
+  b->row_off.resize(n_series + 1);
+  b->rows = 0; b->t_max = 0;
+  for (int s = 0; s < n_series; s++) {
+    if (lengths[s] < 0) { delete b; return fail(NIPGPU_EINVAL, "negative series length"); }
+    b->row_off[s] = b->rows;
+    b->rows += lengths[s];
+    b->t_max = std::max(b->t_max, lengths[s]);
+  }
+  b->row_off[n_series] = b->rows;
+  // range check of the observations (the reference would index out of bounds)
+  for (long long r = 0; r < b->rows; r++)
+    for (int k = 0; k < n_obs; k++)
+      if (data[r * n_obs + k] >= m->hm.card[obs_vars[k]]) { delete b; return fail(NIPGPU_EINVAL, "observation index >= cardinality"); }
+  cudaStream_t st = m->stream;
+  int e = 0;
+  if ((e = dev_upload(&b->d_len, b->len, st)) || (e = dev_upload(&b->d_row_off, b->row_off, st)) ||
+      (e = dev_upload(&b->d_obs, data, (size_t)b->rows * n_obs, st))) {
+    nipgpu_batch_destroy(b);
+    return e;
+  }
+  NIPGPU_CUDA(cudaMalloc((void**)&b->d_obs_proj, 3 * (size_t)std::max(n_obs, 1) * sizeof(int)));
+  NIPGPU_CUDA(cudaMalloc((void**)&b->d_ll, (size_t)std::max(n_series, 1) * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&b->d_status, (size_t)std::max(n_series, 1) * sizeof(int)));
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  *out = b;
+  return NIPGPU_OK;
+}
+
+void nipgpu_batch_destroy(nipgpu_batch* b) {
+  if (!b) return;
+  if (b->m) { cudaSetDevice(b->m->device); cudaStreamSynchronize(b->m->stream); }
+  cudaFree(b->d_len); cudaFree(b->d_row_off); cudaFree(b->d_obs); cudaFree(b->d_obs_proj);
+  cudaFree(b->d_qproj); cudaFree(b->d_qoff); cudaFree(b->d_alpha); cudaFree(b->d_post);
+  cudaFree(b->d_ll); cudaFree(b->d_like); cudaFree(b->d_status);
+  chain_batch_free(b->chain);
+  delete b;
+}
+
+int nipgpu_infer_device(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int32_t n_query,
+                        const int32_t* query_vars, int forward_only, int want_loglik,
+                        double** post_dev, double** loglik_dev) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  if (int e = infer_impl(m, b, use_evidence, n_query, query_vars, forward_only, want_loglik, true)) return e;
+  if (post_dev) *post_dev = b->d_post;
+  if (loglik_dev) *loglik_dev = b->d_ll;
+  return NIPGPU_OK;
+}
+
+int nipgpu_infer(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int32_t n_query,
+                 const int32_t* query_vars, int forward_only, double* post, double* loglik) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  if (int e = infer_impl(m, b, use_evidence, n_query, query_vars, forward_only, loglik != nullptr, post != nullptr)) return e;
+  if (post && n_query > 0) {
+    size_t row = 0;
+    for (int i = 0; i < n_query; i++) row += m->hm.card[query_vars[i]];
+    NIPGPU_CUDA(cudaMemcpyAsync(post, b->d_post, (size_t)b->rows * row * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  }
+  if (loglik)
+    NIPGPU_CUDA(cudaMemcpyAsync(loglik, b->d_ll, (size_t)b->n_series * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  return NIPGPU_OK;
+}
+
+int64_t nipgpu_model_counts_size(const nipgpu_model* m) { return m ? m->hm.coff[m->hm.nv] : 0; }
+
+int nipgpu_model_counts_offsets(const nipgpu_model* m, int64_t* off) {
+  if (!m || !off) return fail(NIPGPU_EINVAL, "null argument");
+  for (int v = 0; v <= m->hm.nv; v++) off[v] = m->hm.coff[v];
+  return NIPGPU_OK;
+}
+
+int nipgpu_em_counts_device(nipgpu_model* m, double** counts_dev, int64_t* n_doubles) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  if (counts_dev) *counts_dev = m->d_counts;
+  if (n_doubles) *n_doubles = m->hm.coff[m->hm.nv] + 2;
+  return NIPGPU_OK;
+}
+
+int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int add_pseudocount,
+                    double* counts, double* loglik, int* status) {
+  if (!m || !b || b->m != m) return fail(NIPGPU_EINVAL, "model/batch mismatch");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  const HostModel& hm = m->hm;
+  const long long n = hm.coff[hm.nv];
+  const int* obs_proj = nullptr;
+  if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;
+  if (int e = ensure_alpha(m, b)) return e;
+  const DBatch B = dev_batch(b, obs_proj);
+  JtLaunch l = m->launch;
+  l.grid = std::max(1, std::min(l.grid, std::max(b->n_series, 1)));
+  if (m->acc_groups < (size_t)l.grid) {
+    cudaFree(m->d_acc);
+    m->acc_groups = l.grid;
+    NIPGPU_CUDA(cudaMalloc((void**)&m->d_acc, m->acc_groups * (size_t)n * sizeof(double)));
+  }
+  NIPGPU_CUDA(cudaMemsetAsync(m->d_acc, 0, (size_t)l.grid * n * sizeof(double), m->stream));
+  DQuery Q{};
+  NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
+  if (int e = jt_forward(m->prog, B, Q, l, 1, 0, b->d_alpha, nullptr, b->d_ll, b->d_status, m->stream)) return e;
+  if (int e = jt_backward(m->prog, B, Q, l, b->d_alpha, nullptr, m->d_acc, n, m->stream)) return e;
+  NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+  if (int e = finish_estep(m->d_acc, l.grid, n, n, add_pseudocount ? 1.0 : 0.0, b->d_ll, b->d_status,
+                           b->n_series, m->d_counts, m->stream)) return e;
+  double tail[2] = {0, 0};
+  NIPGPU_CUDA(cudaMemcpyAsync(tail, m->d_counts + n, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (counts)
+    NIPGPU_CUDA(cudaMemcpyAsync(counts, m->d_counts, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 2; }
+  if (loglik) *loglik = tail[0];
+  if (status) *status = tail[1] != 0 ? NIPGPU_EBADLUCK : 0;
+  return NIPGPU_OK;
+}
+
+int nipgpu_em_mstep(nipgpu_model* m, const double* counts) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  const HostModel& hm = m->hm;
+  cudaStream_t st = m->stream;
+  const long long n = hm.coff[hm.nv];
+  if (counts) {
+    NIPGPU_CUDA(cudaMemcpyAsync(m->d_counts, counts, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    NIPGPU_CUDA(cudaStreamSynchronize(st));
+  }
+  // 1. normalise_cpd over the child dimension (src/nip.c:2032-2038)
+  for (int v = 0; v < hm.nv; v++)
+    if (int e = normalise_cpd(m->d_counts + hm.coff[v], hm.coff[v + 1] - hm.coff[v], hm.card[v], st)) return e;
+  // 2. total_reset: every original_p <- 1 (src/nip.c:76-85)
+  if (int e = fill(m->d_orig, m->prog.tab_total, 1.0, st)) return e;
+  // 3. CPTs into family cliques, priors of parentless variables (src/nip.c:2044-2067)
+  for (int v = 0; v < hm.nv; v++) {
+    if (hm.nparents(v) > 0) {
+      const int c = hm.family[v];
+      FamMap fm;
+      fm.n = 1 + hm.nparents(v);
+      int fstride = 1;
+      for (int k = 0; k < fm.n; k++) {
+        const int var = k == 0 ? v : hm.parents[hm.poff[v] + k - 1];
+        int cs = 1;
+        for (int j = 0; j < hm.var_pos(c, var); j++) cs *= hm.card[hm.clique_vars(c)[j]];
+        fm.cstride[k] = cs; fm.card[k] = hm.card[var]; fm.fstride[k] = fstride;
+        fstride *= hm.card[var];
+      }
+      if (int e = init_potential(m->d_orig + m->tab_off[c], hm.csize[c], m->d_counts + hm.coff[v], fm, st)) return e;
+    } else {
+      NIPGPU_CUDA(cudaMemcpyAsync(m->d_prior + hm.prior_off[v], m->d_counts + hm.coff[v],
+                                  (size_t)hm.card[v] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return refresh_derived(m);
+}
+
+int nipgpu_likelihood(nipgpu_model* m, nipgpu_batch* b, const uint8_t* evidence_off,
+                      const uint8_t* evidence_on, double* out) {
+  if (!m || !b || b->m != m || !out) return fail(NIPGPU_EINVAL, "bad arguments");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  const int *p_off = nullptr, *p_on = nullptr;
+  if (int e = upload_obs_proj(m, b, evidence_off, false, 1, &p_off)) return e;
+  if (int e = upload_obs_proj(m, b, evidence_on, false, 2, &p_on)) return e;
+  if (!b->d_like) NIPGPU_CUDA(cudaMalloc((void**)&b->d_like, std::max<size_t>((size_t)b->rows * 2, 1) * sizeof(double)));
+  const DBatch B = dev_batch(b, nullptr);
+  JtLaunch l = m->launch;
+  l.grid = std::max(1, std::min(l.grid, std::max(b->n_series, 1)));
+  NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
+  if (int e = jt_likelihood(m->prog, B, p_off, p_on, l, b->d_like, m->stream)) return e;
+  NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+  NIPGPU_CUDA(cudaMemcpyAsync(out, b->d_like, (size_t)b->rows * 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 1; }
+  return NIPGPU_OK;
+}
+
+// ---- single-slice stateful API ------------------------------------------
+int nipgpu_slice_reset(nipgpu_model* m) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  for (auto& l : m->lik) std::fill(l.begin(), l.end(), 1.0);
+  std::fill(m->prior_entered.begin(), m->prior_entered.end(), 0);
+  m->slice_consistent = false;
+  return NIPGPU_OK;
+}
+
+int nipgpu_slice_use_priors(nipgpu_model* m, int has_history) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  for (int v : m->hm.prior_vars)
+    if (!m->prior_entered[v] && (!has_history || !(m->hm.flags[v] & NIPGPU_IF_OLD_OUTGOING)))
+      m->prior_entered[v] = 1;
+  m->slice_consistent = false;
+  return NIPGPU_OK;
+}
+
+int nipgpu_slice_enter_evidence(nipgpu_model* m, int32_t var, const double* likelihood) {
+  if (!m || var < 0 || var >= m->hm.nv || !likelihood) return fail(NIPGPU_EINVAL, "bad arguments");
+  // nip_enter_evidence replaces the old likelihood by the new one (old is divided out,
+  // or everything is retracted and re-entered): the net effect is "current = new".
+  m->lik[var].assign(likelihood, likelihood + m->hm.card[var]);
+  m->slice_consistent = false;
+  return NIPGPU_OK;
+}
+
+int nipgpu_slice_make_consistent(nipgpu_model* m) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  const HostModel& hm = m->hm;
+  cudaStream_t st = m->stream;
+  NIPGPU_CUDA(cudaMemcpyAsync(m->d_slice_start, m->d_orig, (size_t)m->prog.tab_total * sizeof(double),
+                              cudaMemcpyDeviceToDevice, st));
+  auto stride_of = [&](int c, int v) {
+    int s = 1;
+    for (int j = 0; j < hm.var_pos(c, v); j++) s *= hm.card[hm.clique_vars(c)[j]];
+    return s;
+  };
+  for (size_t k = 0; k < hm.prior_vars.size(); k++) {
+    const int v = hm.prior_vars[k], c = hm.family[v];
+    if (!m->prior_entered[v]) continue;
+    if (int e = apply_vector(m->d_slice_start + m->tab_off[c], hm.csize[c], stride_of(c, v), hm.card[v],
+                             m->d_prior + hm.prior_off[v], m->d_prior_flags + k, st)) return e;
+  }
+  double* d_vec = nullptr;
+  NIPGPU_CUDA(cudaMalloc((void**)&d_vec, (size_t)hm.card_max * sizeof(double)));
+  for (int v = 0; v < hm.nv; v++) {
+    bool all_one = true;
+    for (double x : m->lik[v]) all_one = all_one && x == 1.0;
+    if (all_one) continue;
+    const int c = hm.family[v];
+    NIPGPU_CUDA(cudaMemcpyAsync(d_vec, m->lik[v].data(), (size_t)hm.card[v] * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int e = apply_vector(m->d_slice_start + m->tab_off[c], hm.csize[c], stride_of(c, v), hm.card[v], d_vec, nullptr, st)) { cudaFree(d_vec); return e; }
+    NIPGPU_CUDA(cudaStreamSynchronize(st));
+  }
+  cudaFree(d_vec);
+  if (int e = jt_slice(m->prog, m->launch, m->d_slice_start, m->d_slice_tab, m->d_slice_msg, st)) return e;
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  m->slice_consistent = true;
+  return NIPGPU_OK;
+}
+
+int nipgpu_slice_get_clique(nipgpu_model* m, int32_t clique, double* out) {
+  if (!m || clique < 0 || clique >= m->hm.nc || !out) return fail(NIPGPU_EINVAL, "bad arguments");
+  if (!m->slice_consistent) return fail(NIPGPU_EINVAL, "call nipgpu_slice_make_consistent first");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  NIPGPU_CUDA(cudaMemcpy(out, m->d_slice_tab + m->tab_off[clique], (size_t)m->hm.csize[clique] * sizeof(double), cudaMemcpyDeviceToHost));
+  return NIPGPU_OK;
+}
+
+int nipgpu_slice_mass(nipgpu_model* m, double* mass) {
+  if (!m || !mass) return fail(NIPGPU_EINVAL, "bad arguments");
+  if (!m->slice_consistent) return fail(NIPGPU_EINVAL, "call nipgpu_slice_make_consistent first");
+  // nip_probability_mass: sum of cliques - sum of sepsets (src/nipjointree.c:1156-1188)
+  const HostModel& hm = m->hm;
+  std::vector<double> tab(m->prog.tab_total), msg(std::max(hm.msg_total, 1));
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  NIPGPU_CUDA(cudaMemcpy(tab.data(), m->d_slice_tab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (hm.msg_total)
+    NIPGPU_CUDA(cudaMemcpy(msg.data(), m->d_slice_msg, (size_t)hm.msg_total * sizeof(double), cudaMemcpyDeviceToHost));
+  double r = 0;
+  for (int c = 0; c < hm.nc; c++) {
+    double x = 0;
+    for (int i = 0; i < hm.csize[c]; i++) x += tab[m->tab_off[c] + i];
+    r += x;
+  }
+  for (int s = 0; s < hm.ns; s++) {
+    double x = 0;
+    for (int i = 0; i < hm.ssize[s]; i++) x += msg[hm.sep_slot[s] + i];
+    r -= x;
+  }
+  *mass = r;
+  return NIPGPU_OK;
+}
+
+int nipgpu_slice_marginal(nipgpu_model* m, int32_t var, double* out) {
+  if (!m || var < 0 || var >= m->hm.nv || !out) return fail(NIPGPU_EINVAL, "bad arguments");
+  if (!m->slice_consistent) return fail(NIPGPU_EINVAL, "call nipgpu_slice_make_consistent first");
+  const HostModel& hm = m->hm;
+  const int c = hm.family[var];
+  std::vector<double> tab(hm.csize[c]);
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  NIPGPU_CUDA(cudaMemcpy(tab.data(), m->d_slice_tab + m->tab_off[c], tab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  int stride = 1;
+  for (int j = 0; j < hm.var_pos(c, var); j++) stride *= hm.card[hm.clique_vars(c)[j]];
+  double sum = 0;
+  for (int i = 0; i < hm.card[var]; i++) out[i] = 0;
+  for (int i = 0; i < hm.csize[c]; i++) out[(i / stride) % hm.card[var]] += tab[i];
+  for (int i = 0; i < hm.card[var]; i++) sum += out[i];
+  if (sum != 0)
+    for (int i = 0; i < hm.card[var]; i++) out[i] /= sum;
+  return NIPGPU_OK;
+}
+
+int64_t nipgpu_launch_count(int reset) {
+  const int64_t n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+int nipgpu_last_kernel_ms(nipgpu_model* m, double* ms, int32_t* n) {
+  if (!m) return fail(NIPGPU_EINVAL, "null model");
+  if (ms) *ms = m->last_kernel_ms;
+  if (n) *n = m->last_kernel_n;
+  return NIPGPU_OK;
+}
+
+}  // extern "C"

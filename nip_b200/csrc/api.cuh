@@ -1,0 +1,68 @@
+// api.cuh — the opaque objects behind include/nipgpu.h.
+#pragma once
+
+#include <vector>
+
+#include "chain.cuh"
+#include "common.cuh"
+#include "jtree.cuh"
+#include "model.h"
+#include "params.cuh"
+
+struct nipgpu_model {
+  nipgpu::HostModel hm;
+  int device = 0;
+  int engine = NIPGPU_ENGINE_JTREE;  // preferred engine
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_kernel_ms = 0;
+  int last_kernel_n = 0;
+
+  // ---- structure (immutable) ----
+  int* d_ipool = nullptr;
+  nipgpu::DProj* d_projs = nullptr;
+  nipgpu::DMsg *d_collect = nullptr, *d_distribute = nullptr, *d_path = nullptr;
+  int *d_proj_var = nullptr, *d_proj_fam = nullptr, *d_var_flags = nullptr;
+  long long* d_coff = nullptr;
+  int *d_prior_off = nullptr, *d_prior_vars = nullptr, *d_prior_flags = nullptr;
+  std::vector<int> tab_off;  // per clique offset inside the table area (int)
+
+  // ---- parameters and what is derived from them (HBM resident) ----
+  double *d_orig = nullptr, *d_prior = nullptr;
+  double *d_base0 = nullptr, *d_base1 = nullptr, *d_R1 = nullptr, *d_m10 = nullptr;
+  double* d_counts = nullptr;  // family counts + {loglik, status}
+  double* d_acc = nullptr;     // per-CTA accumulators
+  size_t acc_groups = 0;
+  double* d_gwork = nullptr;   // HBM workspace when tables do not fit shared memory
+  size_t gwork_doubles = 0;
+
+  nipgpu::DProgram prog{};
+  nipgpu::JtLaunch launch{};
+
+  nipgpu::ChainModel chain;  // engine 2 (valid when hm.chain_ok)
+
+  // ---- single-slice state (stateful API) ----
+  std::vector<std::vector<double>> lik;  // host mirror of variable->likelihood
+  std::vector<char> prior_entered;
+  double *d_slice_start = nullptr, *d_slice_tab = nullptr, *d_slice_msg = nullptr;
+  bool slice_consistent = false;
+};
+
+struct nipgpu_batch {
+  nipgpu_model* m = nullptr;
+  int n_series = 0, n_obs = 0, t_max = 0;
+  long long rows = 0;
+  std::vector<int> len, obs_vars;
+  std::vector<long long> row_off;
+  int* d_len = nullptr;
+  long long* d_row_off = nullptr;
+  int* d_obs = nullptr;
+  int* d_obs_proj = nullptr;  // 3 x n_obs scratch (evidence / off / on sets)
+  int *d_qproj = nullptr, *d_qoff = nullptr;
+  size_t q_cap = 0;
+  double *d_alpha = nullptr, *d_post = nullptr, *d_ll = nullptr, *d_like = nullptr;
+  size_t post_cap = 0;
+  int* d_status = nullptr;
+  nipgpu::ChainBatch chain;
+};

@@ -1,0 +1,698 @@
+// chain.cu — engine 2, see chain.cuh.  FP64 tensor-core (DMMA) forward /
+// backward recursions for interface-clique + leaf models.
+//
+// Fragment convention (mma.sync.aligned.m8n8k4 .f64, lane L, g = L/4, q = L%4):
+//   A (8x4, row)  : lane holds A[g][q]
+//   B (4x8, col)  : lane holds B[q][g]
+//   C/D (8x8)     : lane holds C[g][2q], C[g][2q+1]
+// A warp keeps a [8 sequences] x [SP states] vector as NT = SP/8 accumulator
+// tiles, i.e. lane (g,q) owns states 8n+2q+e (n < NT, e < 2) of sequence g.
+// The K loop of the next contraction enumerates the states in exactly that
+// ownership order (k-step (n,e), k-slot q  <->  state 8n+2q+e), so the previous
+// result is already the A operand: no shuffle, no shared-memory round trip.
+// The transition table is pre-arranged once per parameter change in "fragment
+// order" so that every B operand is one conflict-free 8-byte load per lane.
+#include "chain.cuh"
+
+#include <algorithm>
+#include <cfloat>
+
+namespace nipgpu {
+
+namespace {
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// sum over the 4 lanes that share one sequence; only those lanes need to be converged
+__device__ __forceinline__ double quad_sum(double v) {
+  const unsigned mask = 0xFu << ((threadIdx.x & 31) & 28);
+  v += __shfl_xor_sync(mask, v, 1);
+  v += __shfl_xor_sync(mask, v, 2);
+  return v;
+}
+
+// position of A(k-state, n-state) inside a fragment-ordered SPxSP table
+__host__ __device__ inline int frag_index(int kstate, int nstate, int NT) {
+  const int j = kstate >> 3, q = (kstate & 7) >> 1, e = kstate & 1;
+  const int nt = nstate >> 3, g = nstate & 7;
+  return (((j * 2 + e) * NT + nt) << 5) + (g << 2) + q;
+}
+
+struct ChainDev {
+  int S, SP, n_active;
+  const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *lam_static, *lam;
+  long long lam_off[8];  // per active leaf
+};
+
+struct ChainBatchDev {
+  int n_series, t_max;
+  const int* order;
+  const int* len_sorted;
+  const long long* cum;
+  const int* cfg;
+  const long long* row_off;
+};
+
+// ---------------------------------------------------------------- refresh ---
+__global__ void k_chain_mats(const double* base0, const double* base1, const int* ent_of, int S,
+                             int NT, double* Bf1, double* Bb1, double* Bb0) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= S * S) return;
+  const int im = x / S, ip = x - im * S, ent = ent_of[x];
+  const double a1 = base1[ent], a0 = base0[ent];
+  Bf1[frag_index(im, ip, NT)] = a1;  // forward:  k = previous state, n = current state
+  Bb1[frag_index(ip, im, NT)] = a1;  // backward: k = current state,  n = previous state
+  Bb0[frag_index(ip, im, NT)] = a0;
+}
+
+__global__ void k_chain_phi0(const double* base0, const int* ent_of, int S, double* phi0) {
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= S) return;
+  double s = 0;
+  for (int im = 0; im < S; im++) s += base0[ent_of[im * S + ip]];
+  phi0[ip] = s;
+}
+
+// meta: [n_free, card[0..n_free), stride[0..n_free)] — Lambda[cfg][ip] = sum over the leaf's
+// free-variable combinations compatible with cfg of leaf_table[base[s(ip)] + off[r]]
+__global__ void k_chain_lambda(const double* leaf_tab, const int* base, const int* off, int R,
+                               const int* ip_to_s, const int* meta, int n_cfg, int S, int SP,
+                               double* lam) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n_cfg * S) return;
+  const int cfg = x / S, ip = x - cfg * S;
+  const int nf = meta[0];
+  const int* card = meta + 1;
+  const int* stride = meta + 1 + nf;
+  const int b = base[ip_to_s[ip]];
+  double s = 0;
+  for (int r = 0; r < R; r++) {
+    int rem = r, ok = 1;
+    for (int k = 0; k < nf; k++) {
+      const int digit = rem % card[k];
+      rem /= card[k];
+      const int code = (cfg / stride[k]) % (card[k] + 1);
+      if (code != card[k] && code != digit) ok = 0;
+    }
+    if (ok) s += leaf_tab[b + off[r]];
+  }
+  lam[(long long)cfg * SP + ip] = s;
+}
+
+// out[ip] = prod over the listed leaves of Lambda_l[miss_l][ip]
+__global__ void k_chain_lam_prod(const double* lam, const long long* row_off, int n, int S, int SP,
+                                 double* out) {
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= SP) return;
+  double p = ip < S ? 1.0 : 0.0;
+  for (int l = 0; l < n && ip < S; l++) p *= lam[row_off[l] + ip];
+  out[ip] = p;
+}
+
+// time-major evidence configuration per (slice, sequence, active leaf)
+__global__ void k_chain_cfg(ChainBatchDev B, const int* obs, int n_obs, const int* col_slot,
+                            const int* col_stride, const int* col_card, const int* miss_cfg,
+                            int n_active, int* cfg) {
+  const int bp = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (bp >= B.n_series || t >= B.len_sorted[bp]) return;
+  const long long sm_row = B.row_off[B.order[bp]] + t;
+  const long long tm_row = B.cum[t] + bp;
+  for (int a = 0; a < n_active; a++) {
+    int c = miss_cfg[a];
+    for (int k = 0; k < n_obs; k++) {
+      const int o = obs[sm_row * n_obs + k];
+      if (col_slot[k] == a && o >= 0) c += (o - col_card[k]) * col_stride[k];
+    }
+    cfg[tm_row * n_active + a] = c;
+  }
+}
+
+// ---------------------------------------------------------------- forward ---
+// lam[n][e] = lambda(state 8n+2q+e) = static part x the active leaves' evidence rows
+template <int NT>
+__device__ __forceinline__ void load_lambda(const ChainDev& C, const int* cfg_row, int q,
+                                            double (&lam)[NT][2]) {
+  const double2* ls = reinterpret_cast<const double2*>(C.lam_static);
+#pragma unroll
+  for (int n = 0; n < NT; n++) {
+    const double2 v = ls[4 * n + q];
+    lam[n][0] = v.x;
+    lam[n][1] = v.y;
+  }
+  for (int a = 0; a < C.n_active; a++) {
+    const double2* p =
+        reinterpret_cast<const double2*>(C.lam + C.lam_off[a] + (long long)cfg_row[a] * C.SP);
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+      const double2 v = p[4 * n + q];
+      lam[n][0] *= v.x;
+      lam[n][1] *= v.y;
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev B, int want_ll,
+                                                       double* __restrict__ alpha, double* post,
+                                                       int post_stride, int post_off,
+                                                       double* ll_out, int* status_out) {
+  constexpr int SP = 8 * NT;
+  extern __shared__ double sB[];
+  for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) sB[i] = C.Bf1[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int bp = warp * 8 + g;
+  const bool valid = bp < B.n_series;
+  const int T = valid ? B.len_sorted[bp] : 0;
+  const int Tw = __shfl_sync(0xffffffffu, T, 0);  // sorted by length: row 0 is the longest
+  const long long prow0 = valid ? B.row_off[B.order[bp]] : 0;
+  const double2* lam0 = reinterpret_cast<const double2*>(C.lam0);
+  double own[NT][2], acc[NT][2], lam[NT][2];
+#pragma unroll
+  for (int n = 0; n < NT; n++) own[n][0] = own[n][1] = 0.0;
+  double ll = 0;
+  int bad = 0;
+  for (int t = 0; t < Tw; t++) {
+    const bool active = t < T;
+    if (t == 0) {
+      const double2* p0 = reinterpret_cast<const double2*>(C.phi0);
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        const double2 v = p0[4 * n + q];
+        acc[n][0] = v.x;
+        acc[n][1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NT; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const double a = own[j][e];
+          const double* brow = sB + (((j * 2 + e) * NT) << 5) + lane;
+#pragma unroll
+          for (int n = 0; n < NT; n++) dmma(acc[n][0], acc[n][1], a, brow[n << 5]);
+        }
+    }
+    if (active) {
+      const long long row = B.cum[t] + bp;
+      load_lambda<NT>(C, B.cfg + row * C.n_active, q, lam);
+      double m1 = 0, m2 = 0;
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        if (want_ll) {
+          const double2 l0 = lam0[4 * n + q];
+          m1 += acc[n][0] * l0.x + acc[n][1] * l0.y;
+        }
+        acc[n][0] *= lam[n][0];
+        acc[n][1] *= lam[n][1];
+        m2 += acc[n][0] + acc[n][1];
+      }
+      m2 = quad_sum(m2);
+      if (want_ll) m1 = quad_sum(m1);
+      const bool nz = m2 != 0;
+      double2* arow = reinterpret_cast<double2*>(alpha + row * SP);
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        own[n][0] = nz ? acc[n][0] / m2 : acc[n][0];
+        own[n][1] = nz ? acc[n][1] / m2 : acc[n][1];
+        arow[4 * n + q] = make_double2(own[n][0], own[n][1]);
+      }
+      if (post) {  // filtering: the forward marginal of I_t is alpha_t itself
+        double* prow = post + (prow0 + t) * post_stride + post_off;
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+          const int c = 8 * n + 2 * q;
+          if (c < C.S) prow[c] = own[n][0];
+          if (c + 1 < C.S) prow[c + 1] = own[n][1];
+        }
+      }
+      if (want_ll) {  // src/nip.c:1458-1474, BAD_LUCK test :1827-1831
+        if (m1 > 0 && m2 > 0) ll += log(m2) - log(m1);
+        if (m2 == 0) ll = -DBL_MAX;
+        if (m1 <= 0 || m2 <= 0 || ll > 0) bad = 1;
+      }
+    }
+  }
+  if (valid && q == 0) {
+    if (ll_out) ll_out[B.order[bp]] = ll;
+    if (status_out) status_out[B.order[bp]] = bad;
+  }
+}
+
+// --------------------------------------------------------------- backward ---
+template <int NT, bool B0_IN_SMEM>
+__global__ void __launch_bounds__(128) k_chain_backward(ChainDev C, ChainBatchDev B,
+                                                        const double* __restrict__ alpha,
+                                                        double* post, int post_stride,
+                                                        int post_off) {
+  constexpr int SP = 8 * NT;
+  extern __shared__ double sB[];
+  for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) {
+    sB[i] = C.Bb1[i];
+    if (B0_IN_SMEM) sB[SP * SP + i] = C.Bb0[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int bp = warp * 8 + g;
+  const bool valid = bp < B.n_series;
+  const int T = valid ? B.len_sorted[bp] : 0;
+  const int Tw = __shfl_sync(0xffffffffu, T, 0);
+  const long long prow0 = valid ? B.row_off[B.order[bp]] : 0;
+  double acur[NT][2], gnext[NT][2], r[NT][2], u[NT][2];
+#pragma unroll
+  for (int n = 0; n < NT; n++) acur[n][0] = acur[n][1] = gnext[n][0] = gnext[n][1] = 0.0;
+  for (int t = Tw - 1; t >= 0; t--) {
+    const bool active = t < T;
+    const bool last = t == T - 1;
+    const long long row = active ? B.cum[t] + bp : 0;
+    if (active) {
+      if (last) {  // first slice processed for this sequence: alpha_{T-1} comes from HBM
+        const double2* arow = reinterpret_cast<const double2*>(alpha + row * SP);
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+          const double2 v = arow[4 * n + q];
+          acur[n][0] = v.x;
+          acur[n][1] = v.y;
+        }
+      }
+      load_lambda<NT>(C, B.cfg + row * C.n_active, q, r);
+      // r = lambda * gamma_{t+1} / alpha_t (0 where alpha_t == 0); posterior of I_t = alpha_t * ratio
+      double ps = 0;
+#pragma unroll
+      for (int n = 0; n < NT; n++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const double a = acur[n][e];
+          const double rho = last ? 1.0 : (a != 0 ? gnext[n][e] / a : 0.0);
+          r[n][e] *= rho;
+          u[n][e] = a * rho;  // un-normalised smoothed marginal, parked in u for the moment
+          ps += u[n][e];
+        }
+      ps = quad_sum(ps);
+      if (post) {
+        double* prow = post + (prow0 + t) * post_stride + post_off;
+        const bool nz = ps != 0;
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+          const int c = 8 * n + 2 * q;
+          if (c < C.S) prow[c] = nz ? u[n][0] / ps : u[n][0];
+          if (c + 1 < C.S) prow[c + 1] = nz ? u[n][1] / ps : u[n][1];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < NT; n++) r[n][0] = r[n][1] = 0.0;
+    }
+    {
+      // u = r . A^T  (k = current state, n = previous state); slice 0 uses the prior-weighted table
+      const double* tab = (t == 0) ? (B0_IN_SMEM ? sB + SP * SP : C.Bb0) : sB;
+#pragma unroll
+      for (int n = 0; n < NT; n++) u[n][0] = u[n][1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NT; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const double a = r[j][e];
+          const double* brow = tab + (((j * 2 + e) * NT) << 5) + lane;
+#pragma unroll
+          for (int n = 0; n < NT; n++) dmma(u[n][0], u[n][1], a, brow[n << 5]);
+        }
+    }
+    if (active && t > 0) {
+      // gamma_t = normalise(alpha_{t-1} * u); alpha_{t-1} becomes the next slice's alpha_t
+      const double2* arow = reinterpret_cast<const double2*>(alpha + (B.cum[t - 1] + bp) * SP);
+      double z = 0;
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        const double2 v = arow[4 * n + q];
+        acur[n][0] = v.x;
+        acur[n][1] = v.y;
+        gnext[n][0] = v.x * u[n][0];
+        gnext[n][1] = v.y * u[n][1];
+        z += gnext[n][0] + gnext[n][1];
+      }
+      z = quad_sum(z);
+      if (z != 0) {
+#pragma unroll
+        for (int n = 0; n < NT; n++) {
+          gnext[n][0] /= z;
+          gnext[n][1] /= z;
+        }
+      }
+    }
+  }
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    NIPGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return NIPGPU_OK;
+}
+
+template <int NT>
+int launch_forward(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
+                   cudaStream_t st) {
+  const size_t smem = sizeof(double) * 64 * NT * NT;
+  if (int e = set_smem(k_chain_forward<NT>, smem)) return e;
+  const int grid = (B.n_series + 31) / 32;
+  k_chain_forward<NT><<<grid, 128, smem, st>>>(C, B, a.want_ll, alpha,
+                                                a.forward_only ? a.d_post : nullptr, a.post_stride,
+                                                a.post_off, a.d_ll, a.d_status);
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
+template <int NT>
+int launch_backward(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a,
+                    const double* alpha, cudaStream_t st) {
+  const int grid = (B.n_series + 31) / 32;
+  const size_t one = sizeof(double) * 64 * NT * NT;
+  if (2 * one <= 96 * 1024) {
+    if (int e = set_smem(k_chain_backward<NT, true>, 2 * one)) return e;
+    k_chain_backward<NT, true><<<grid, 128, 2 * one, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                           a.post_off);
+  } else {
+    if (int e = set_smem(k_chain_backward<NT, false>, one)) return e;
+    k_chain_backward<NT, false><<<grid, 128, one, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                        a.post_off);
+  }
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
+template <class T>
+int upload(T** dst, const std::vector<T>& src, cudaStream_t st) {
+  const size_t n = std::max<size_t>(src.size(), 1);
+  NIPGPU_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+  if (!src.empty())
+    NIPGPU_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return NIPGPU_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host ---
+std::string chain_build(HostModel& hm, ChainModel& cm) {
+  cm.ok = false;
+  if (!hm.chain_ok) return hm.chain_why;
+  const int S = hm.S;
+  int SP = 8;
+  while (SP < S) SP *= 2;
+  if (SP > 64) return "interface larger than 64 states: warp-resident DMMA path not applicable";
+  cm.S = S; cm.SP = SP; cm.NT = SP / 8; cm.c0 = hm.in_clique;
+  const int c0 = cm.c0, nd = hm.clique_dim(c0);
+  // entry -> (previous-slice interface state, current interface state)
+  std::vector<int> istride_prev(hm.nv, 0), istride_cur(hm.nv, 0);
+  int st = 1;
+  for (int k = 0; k < hm.nif; k++) {
+    istride_prev[hm.prev[k]] = st;
+    istride_cur[hm.outg[k]] = st;
+    st *= hm.card[hm.outg[k]];
+  }
+  cm.ent_of.assign((size_t)S * S, 0);
+  for (int ent = 0; ent < hm.csize[c0]; ent++) {
+    int rem = ent, im = 0, ip = 0;
+    for (int k = 0; k < nd; k++) {
+      const int v = hm.clique_vars(c0)[k], digit = rem % hm.card[v];
+      rem /= hm.card[v];
+      bool is_prev = false;
+      for (int x = 0; x < hm.nif; x++)
+        if (hm.prev[x] == v) is_prev = true;
+      if (is_prev) im += digit * istride_prev[v];
+      else ip += digit * istride_cur[v];
+    }
+    cm.ent_of[(size_t)im * S + ip] = ent;
+  }
+  cm.var_leaf.assign(hm.nv, -1);
+  cm.var_slot.assign(hm.nv, -1);
+  cm.leaves.clear();
+  long long lam_total = 0;
+  for (size_t li = 0; li < hm.leaves.size(); li++) {
+    ChainLeafHost L;
+    L.clique = hm.leaves[li];
+    const int s = hm.leaf_sepset[li];
+    std::vector<int> sv(hm.sepset_vars(s), hm.sepset_vars(s) + hm.sepset_dim(s));
+    long long ncfg = 1;
+    for (int k = 0; k < hm.clique_dim(L.clique); k++) {
+      const int v = hm.clique_vars(L.clique)[k];
+      if (std::find(sv.begin(), sv.end(), v) != sv.end()) continue;
+      L.free_vars.push_back(v);
+      L.cfg_stride.push_back((int)ncfg);
+      ncfg *= hm.card[v] + 1;
+      if (ncfg * SP > (1LL << 27)) return "leaf clique with too many evidence configurations";
+    }
+    L.n_cfg = (int)ncfg;
+    L.miss_cfg = 0;
+    for (size_t k = 0; k < L.free_vars.size(); k++) L.miss_cfg += hm.card[L.free_vars[k]] * L.cfg_stride[k];
+    L.proj = hm.add_proj(L.clique, sv);
+    L.ip_to_s.assign(S, 0);
+    for (int ip = 0; ip < S; ip++) {
+      int sidx = 0, sst = 1;
+      for (int v : sv) {
+        const int digit = (ip / istride_cur[v]) % hm.card[v];
+        sidx += digit * sst;
+        sst *= hm.card[v];
+      }
+      L.ip_to_s[ip] = sidx;
+    }
+    L.lam_off = lam_total;
+    lam_total += (long long)L.n_cfg * SP;
+    for (size_t k = 0; k < L.free_vars.size(); k++) {
+      cm.var_leaf[L.free_vars[k]] = (int)cm.leaves.size();
+      cm.var_slot[L.free_vars[k]] = (int)k;
+    }
+    cm.leaves.push_back(L);
+  }
+  cm.n_real = (int)cm.leaves.size();
+  for (int k = 0; k < hm.nif; k++) {  // evidence on an I_t variable itself: indicator "leaf"
+    ChainLeafHost L;
+    L.var = hm.outg[k];
+    L.free_vars = {L.var};
+    L.cfg_stride = {1};
+    L.n_cfg = hm.card[L.var] + 1;
+    L.miss_cfg = hm.card[L.var];
+    L.ip_to_s.assign(S, 0);
+    for (int ip = 0; ip < S; ip++) L.ip_to_s[ip] = (ip / istride_cur[L.var]) % hm.card[L.var];
+    L.lam_off = lam_total;
+    lam_total += (long long)L.n_cfg * SP;
+    cm.var_leaf[L.var] = (int)cm.leaves.size();
+    cm.var_slot[L.var] = 0;
+    cm.leaves.push_back(L);
+  }
+  cm.lam_total = lam_total;
+  cm.ok = true;
+  return "";
+}
+
+int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st) {
+  if (!cm.ok) return NIPGPU_OK;
+  const size_t sp2 = (size_t)cm.SP * cm.SP;
+  if (int e = upload(&cm.d_ent_of, cm.ent_of, st)) return e;
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_Bf1, sp2 * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_Bb1, sp2 * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_Bb0, sp2 * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_phi0, cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_lam0, cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_lam, std::max<long long>(cm.lam_total, 1) * sizeof(double)));
+  NIPGPU_CUDA(cudaMemsetAsync(cm.d_lam, 0, std::max<long long>(cm.lam_total, 1) * sizeof(double), st));
+  // pseudo leaves never change: Lambda[o][ip] = [state(ip) == o], Lambda[card][ip] = 1
+  for (size_t l = cm.n_real; l < cm.leaves.size(); l++) {
+    const ChainLeafHost& L = cm.leaves[l];
+    std::vector<double> tab((size_t)L.n_cfg * cm.SP, 0.0);
+    for (int c = 0; c < L.n_cfg; c++)
+      for (int ip = 0; ip < cm.S; ip++)
+        tab[(size_t)c * cm.SP + ip] = (c == L.miss_cfg || L.ip_to_s[ip] == c) ? 1.0 : 0.0;
+    NIPGPU_CUDA(cudaMemcpyAsync(cm.d_lam + L.lam_off, tab.data(), tab.size() * sizeof(double),
+                                cudaMemcpyHostToDevice, st));
+    NIPGPU_CUDA(cudaStreamSynchronize(st));
+  }
+  (void)hm;
+  return NIPGPU_OK;
+}
+
+int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, const double* d_base1,
+                  const std::vector<int>& tab_off, const int* d_ipool,
+                  cudaStream_t st) {
+  if (!cm.ok) return NIPGPU_OK;
+  const size_t sp2 = (size_t)cm.SP * cm.SP;
+  NIPGPU_CUDA(cudaMemsetAsync(cm.d_Bf1, 0, sp2 * sizeof(double), st));
+  NIPGPU_CUDA(cudaMemsetAsync(cm.d_Bb1, 0, sp2 * sizeof(double), st));
+  NIPGPU_CUDA(cudaMemsetAsync(cm.d_Bb0, 0, sp2 * sizeof(double), st));
+  NIPGPU_CUDA(cudaMemsetAsync(cm.d_phi0, 0, cm.SP * sizeof(double), st));
+  const int S = cm.S;
+  k_chain_mats<<<(S * S + 255) / 256, 256, 0, st>>>(d_base0 + tab_off[cm.c0], d_base1 + tab_off[cm.c0],
+                                                    cm.d_ent_of, S, cm.NT, cm.d_Bf1, cm.d_Bb1, cm.d_Bb0);
+  NIPGPU_LAUNCHED();
+  k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base0 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_phi0);
+  NIPGPU_LAUNCHED();
+  std::vector<long long> miss_rows;
+  for (int l = 0; l < cm.n_real; l++) {
+    const ChainLeafHost& L = cm.leaves[l];
+    const Proj& p = hm.projs[L.proj];
+    std::vector<int> meta{(int)L.free_vars.size()};
+    for (int v : L.free_vars) meta.push_back(hm.card[v]);
+    for (int s : L.cfg_stride) meta.push_back(s);
+    meta.insert(meta.end(), L.ip_to_s.begin(), L.ip_to_s.end());
+    int* d_meta = nullptr;
+    NIPGPU_CUDA(cudaMalloc((void**)&d_meta, meta.size() * sizeof(int)));
+    NIPGPU_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int n = L.n_cfg * S;
+    k_chain_lambda<<<(n + 127) / 128, 128, 0, st>>>(
+        d_base1 + tab_off[L.clique], d_ipool + p.base_pos, d_ipool + p.off_pos, p.R,
+        d_meta + 1 + 2 * (int)L.free_vars.size(), d_meta, L.n_cfg, S, cm.SP, cm.d_lam + L.lam_off);
+    NIPGPU_LAUNCHED();
+    NIPGPU_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_meta);
+    miss_rows.push_back(L.lam_off + (long long)L.miss_cfg * cm.SP);
+  }
+  long long* d_rows = nullptr;
+  if (int e = upload(&d_rows, miss_rows, st)) return e;
+  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, d_rows, (int)miss_rows.size(), S,
+                                                        cm.SP, cm.d_lam0);
+  NIPGPU_LAUNCHED();
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_rows);
+  return NIPGPU_OK;
+}
+
+void chain_free(ChainModel& cm) {
+  cudaFree(cm.d_ent_of); cudaFree(cm.d_Bf1); cudaFree(cm.d_Bb1); cudaFree(cm.d_Bb0);
+  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta);
+  cm = ChainModel();
+}
+
+bool chain_plan(const HostModel& hm, const ChainModel& cm, int n_obs, const int* obs_vars,
+                const uint8_t* use_evidence, ChainPlan& plan) {
+  plan = ChainPlan();
+  if (!cm.ok) return false;
+  plan.col_leaf_slot.assign(n_obs, -1);
+  plan.col_stride.assign(n_obs, 0);
+  plan.col_card.assign(n_obs, 0);
+  for (int k = 0; k < n_obs; k++) {
+    const int v = obs_vars[k];
+    if (use_evidence && !use_evidence[v]) continue;
+    const int l = cm.var_leaf[v];
+    if (l < 0) return false;  // evidence on a previous-slice variable: generic engine
+    int a = (int)(std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) - plan.active_leaf.begin());
+    if (a == (int)plan.active_leaf.size()) plan.active_leaf.push_back(l);
+    plan.col_leaf_slot[k] = a;
+    plan.col_stride[k] = cm.leaves[l].cfg_stride[cm.var_slot[v]];
+    plan.col_card[k] = hm.card[v];
+  }
+  plan.n_active = (int)plan.active_leaf.size();
+  return plan.n_active <= 8;
+}
+
+int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, const int* len,
+                        long long rows, int t_max, cudaStream_t st) {
+  if (cb.ready) return NIPGPU_OK;
+  cb.order.resize(n_series);
+  for (int i = 0; i < n_series; i++) cb.order[i] = i;
+  std::stable_sort(cb.order.begin(), cb.order.end(), [&](int a, int b) { return len[a] > len[b]; });
+  cb.len_sorted.resize(n_series);
+  for (int i = 0; i < n_series; i++) cb.len_sorted[i] = len[cb.order[i]];
+  cb.cum.assign((size_t)t_max + 1, 0);
+  {
+    int act = n_series;
+    for (int t = 0; t < t_max; t++) {
+      while (act > 0 && cb.len_sorted[act - 1] <= t) act--;
+      cb.cum[t + 1] = cb.cum[t] + act;
+    }
+  }
+  if (int e = upload(&cb.d_order, cb.order, st)) return e;
+  if (int e = upload(&cb.d_len_sorted, cb.len_sorted, st)) return e;
+  if (int e = upload(&cb.d_cum, cb.cum, st)) return e;
+  NIPGPU_CUDA(cudaMalloc((void**)&cb.d_alpha, std::max<long long>(rows, 1) * cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cb.d_lam_static, cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  cb.ready = true;
+  return NIPGPU_OK;
+}
+
+void chain_batch_free(ChainBatch& cb) {
+  cudaFree(cb.d_order); cudaFree(cb.d_len_sorted); cudaFree(cb.d_cum); cudaFree(cb.d_cfg);
+  cudaFree(cb.d_alpha); cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_active_off);
+  cb = ChainBatch();
+}
+
+int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
+                const ChainInferArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+  (void)hm;
+  const int na = plan.n_active;
+  // ---- per-call evidence configuration (time-major) ----
+  const size_t need = (size_t)std::max<long long>(a.rows, 1) * std::max(na, 1);
+  if (cb.cfg_cap < need) {
+    cudaFree(cb.d_cfg);
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_cfg, need * sizeof(int)));
+    cb.cfg_cap = need;
+  }
+  std::vector<int> cols;  // slot | stride | card | miss_cfg
+  cols.insert(cols.end(), plan.col_leaf_slot.begin(), plan.col_leaf_slot.end());
+  cols.insert(cols.end(), plan.col_stride.begin(), plan.col_stride.end());
+  cols.insert(cols.end(), plan.col_card.begin(), plan.col_card.end());
+  for (int l : plan.active_leaf) cols.push_back(cm.leaves[l].miss_cfg);
+  cudaFree(cb.d_cols);
+  cb.d_cols = nullptr;
+  if (int e = upload(&cb.d_cols, cols, st)) return e;
+  std::vector<long long> inactive_rows;
+  for (int l = 0; l < cm.n_real; l++)
+    if (std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) == plan.active_leaf.end())
+      inactive_rows.push_back(cm.leaves[l].lam_off + (long long)cm.leaves[l].miss_cfg * cm.SP);
+  cudaFree(cb.d_active_off);
+  cb.d_active_off = nullptr;
+  if (int e = upload(&cb.d_active_off, inactive_rows, st)) return e;
+  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, cb.d_active_off,
+                                                        (int)inactive_rows.size(), cm.S, cm.SP,
+                                                        cb.d_lam_static);
+  NIPGPU_LAUNCHED();
+
+  ChainBatchDev B;
+  B.n_series = a.n_series; B.t_max = a.t_max; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
+  B.cum = cb.d_cum; B.cfg = cb.d_cfg; B.row_off = a.d_row_off;
+  if (na > 0 && a.rows > 0) {
+    dim3 grid((a.n_series + 127) / 128, a.t_max);
+    k_chain_cfg<<<grid, 128, 0, st>>>(B, a.d_obs, a.n_obs, cb.d_cols, cb.d_cols + a.n_obs,
+                                      cb.d_cols + 2 * a.n_obs, cb.d_cols + 3 * a.n_obs, na, cb.d_cfg);
+    NIPGPU_LAUNCHED();
+  }
+  ChainDev C;
+  C.S = cm.S; C.SP = cm.SP; C.n_active = na;
+  C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
+  C.lam_static = cb.d_lam_static; C.lam = cm.d_lam;
+  for (int i = 0; i < 8; i++) C.lam_off[i] = i < na ? cm.leaves[plan.active_leaf[i]].lam_off : 0;
+
+  if (a.n_series == 0) return NIPGPU_OK;
+  if (ev0) NIPGPU_CUDA(cudaEventRecord(ev0, st));
+  int e = NIPGPU_OK;
+  switch (cm.NT) {
+    case 1: e = launch_forward<1>(C, B, a, cb.d_alpha, st); break;
+    case 2: e = launch_forward<2>(C, B, a, cb.d_alpha, st); break;
+    case 4: e = launch_forward<4>(C, B, a, cb.d_alpha, st); break;
+    case 8: e = launch_forward<8>(C, B, a, cb.d_alpha, st); break;
+    default: set_error("chain: unsupported interface size"); return NIPGPU_EUNSUPPORTED;
+  }
+  if (e) return e;
+  if (!a.forward_only) {
+    switch (cm.NT) {
+      case 1: e = launch_backward<1>(C, B, a, cb.d_alpha, st); break;
+      case 2: e = launch_backward<2>(C, B, a, cb.d_alpha, st); break;
+      case 4: e = launch_backward<4>(C, B, a, cb.d_alpha, st); break;
+      case 8: e = launch_backward<8>(C, B, a, cb.d_alpha, st); break;
+    }
+    if (e) return e;
+  }
+  if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
+  return NIPGPU_OK;
+}
+
+}  // namespace nipgpu

@@ -1,0 +1,107 @@
+// chain.cuh — engine 2 (NIPGPU_ENGINE_CHAIN): models whose slice is one
+// interface clique {I_{t-1}, I_t} with leaf cliques hanging off I_t (HMM-style
+// DBNs: configs C1/C2/C5 of SURVEY §8, and C4 up to |I| = 128).
+//
+// For such a model the slice-to-slice messages of
+// start/finish_timeslice_message_pass (src/nip.c:1031-1098) are
+//     alpha_t = normalise( (alpha_{t-1} . A) * lambda_t )
+//     gamma_t = normalise( alpha_{t-1} * (A . (lambda_t * gamma_{t+1} / alpha_t)) )
+// with A the interface clique table and lambda_t the product of the leaf tables
+// restricted to the slice's evidence.  Batched over sequences the contraction
+// is a dense FP64 GEMM and runs on the tensor cores (DMMA, mma.sync m8n8k4):
+// one warp owns 8 sequences for their whole length, keeps alpha/gamma in
+// registers in the MMA accumulator layout, and never synchronises with any
+// other warp.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+#include "model.h"
+
+namespace nipgpu {
+
+struct ChainLeafHost {
+  int clique = -1;             // real leaf clique, or -1 for an interface-variable pseudo leaf
+  int var = -1;                // pseudo leaf: the I_t variable it carries evidence for
+  std::vector<int> free_vars;  // non-sepset variables of the leaf, clique order
+  std::vector<int> cfg_stride; // per free var: stride of its code inside the config index
+  int n_cfg = 1;               // prod(card + 1); code == card means "no evidence"
+  int miss_cfg = 0;            // config index with every code == card
+  int proj = -1;               // projection leaf -> its sepset (base/off)
+  std::vector<int> ip_to_s;    // [S] interface state -> sepset entry
+  long long lam_off = 0;       // offset of Lambda_l[n_cfg][SP] inside d_lam
+};
+
+struct ChainModel {
+  bool ok = false;
+  int S = 0, SP = 0, NT = 0;   // interface size, padded size (8*NT)
+  int c0 = -1;
+  std::vector<ChainLeafHost> leaves;  // real leaves first, then pseudo leaves
+  int n_real = 0;
+  std::vector<int> var_leaf, var_slot;  // per variable: leaf carrying its evidence / digit slot, or -1
+  std::vector<int> ent_of;     // [S*S] (i_prev * S + i_cur) -> entry of the interface clique
+  // device
+  int* d_ent_of = nullptr;
+  double *d_Bf1 = nullptr, *d_Bb1 = nullptr, *d_Bb0 = nullptr;  // fragment-ordered SPxSP
+  double *d_phi0 = nullptr, *d_lam0 = nullptr;                  // [SP]
+  double* d_lam = nullptr;     // all Lambda tables
+  long long lam_total = 0;
+  int* d_leaf_meta = nullptr;  // flattened per-leaf metadata for the refresh kernel
+};
+
+struct ChainBatch {
+  bool ready = false;
+  std::vector<int> order;          // sorted position -> series (length descending)
+  std::vector<int> len_sorted;
+  std::vector<long long> cum;      // [t_max+1] rows before slice t in time-major order
+  int* d_order = nullptr;
+  int* d_len_sorted = nullptr;
+  long long* d_cum = nullptr;
+  int* d_cfg = nullptr;            // [rows][n_active] time-major
+  size_t cfg_cap = 0;
+  double* d_alpha = nullptr;       // [rows][SP] time-major
+  double* d_lam_static = nullptr;  // [SP] product of the inactive real leaves' no-evidence rows
+  int* d_cols = nullptr;           // per-call column metadata
+  long long* d_active_off = nullptr;
+};
+
+// per-call evidence plan: which leaves see evidence through which data columns
+struct ChainPlan {
+  int n_active = 0;
+  std::vector<int> active_leaf;       // leaf ids
+  std::vector<int> col_leaf_slot;     // [n_obs] index into active_leaf or -1
+  std::vector<int> col_stride;        // [n_obs] cfg stride of the column's digit
+  std::vector<int> col_card;          // [n_obs]
+};
+
+std::string chain_build(HostModel& hm, ChainModel& cm);
+int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st);
+// recompute Bf1/Bb1/Bb0/phi0/lam0/Lambda from the base tables (after any parameter change)
+int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, const double* d_base1,
+                  const std::vector<int>& tab_off, const int* d_ipool,
+                  cudaStream_t st);
+void chain_free(ChainModel& cm);
+
+struct ChainInferArgs {
+  int n_series, n_obs, t_max;
+  long long rows;
+  const int* d_obs;            // series-major [rows][n_obs]
+  const long long* d_row_off;  // series-major first row per series
+  int want_ll, forward_only;
+  double* d_post;              // series-major rows, `post_stride` doubles each, or nullptr
+  int post_stride, post_off;
+  double* d_ll;                // [n_series] or nullptr
+  int* d_status;               // [n_series] or nullptr
+};
+
+// returns false when the plan cannot be served by the chain engine
+bool chain_plan(const HostModel& hm, const ChainModel& cm, int n_obs, const int* obs_vars,
+                const uint8_t* use_evidence, ChainPlan& plan);
+int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, const int* len,
+                        long long rows, int t_max, cudaStream_t st);
+int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
+                const ChainInferArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
+void chain_batch_free(ChainBatch& cb);
+
+}  // namespace nipgpu

@@ -1,0 +1,82 @@
+// jtree.cuh — generic join-tree engine (NIPGPU_ENGINE_JTREE): device program
+// layout and launchers.  One CTA owns one sequence at a time and walks the
+// compiled collect/distribute schedule for every slice with the sequence's
+// clique tables staged in shared memory (or in a per-CTA HBM workspace when
+// they do not fit).
+#pragma once
+
+#include "common.cuh"
+
+namespace nipgpu {
+
+struct DProj {
+  int tab;    // offset of the clique's table inside the work area
+  int m, R, lanes;
+  int base, off;  // positions in the int pool
+};
+
+struct DMsg {
+  int proj_src, proj_dst, slot, size;
+};
+
+// Everything a slice kernel needs about the model; passed by value.
+struct DProgram {
+  int tab_total, msg_total, msg_max, scratch;
+  int n_collect, n_distribute, n_path;
+  int nif, S, proj_in, proj_out;
+  int root_tab, root_size;
+  int nv;
+  const DProj* projs;
+  const int* ipool;
+  const DMsg* collect;
+  const DMsg* distribute;
+  const DMsg* path;
+  const double* base0;  // original_p x every prior          (slices without history)
+  const double* base1;  // original_p x priors of non-I_{t-1} variables (with history)
+  const double* R1;     // [S] mass of base1 per interface state  (m1 = alpha . R1)
+  const double* m1_0;   // [1] mass of base0                      (m1 at t = 0)
+  const int* proj_var;  // [nv] family clique -> {v}
+  const int* proj_fam;  // [nv] family clique -> (v, parents...)
+  const long long* coff;  // [nv+1] family count offsets
+  const int* var_flags;   // [nv]
+};
+
+struct DBatch {
+  int n_series, n_obs;
+  const int* len;          // [n_series]
+  const long long* row_off;  // [n_series] first row of each series
+  const int* obs;          // [rows][n_obs]
+  const int* obs_proj;     // [n_obs] projection used to enter the column's evidence, -1 = ignored
+};
+
+struct DQuery {
+  int n_query, row;        // row = doubles per output row
+  const int* proj;         // [n_query]
+  const int* off;          // [n_query] offset inside the row
+};
+
+// work-area size in doubles for one CTA
+inline size_t jt_work_doubles(const DProgram& p) {
+  return (size_t)p.tab_total + p.msg_total + p.msg_max + 3 * (size_t)p.S + p.scratch + 40;
+}
+
+struct JtLaunch {
+  int threads, grid;
+  size_t smem_bytes;     // 0 when the work area lives in HBM
+  double* gwork;         // per-CTA workspace (grid x work doubles) or nullptr
+};
+
+int jt_forward(const DProgram& p, const DBatch& b, const DQuery& q, const JtLaunch& l,
+               int want_ll, int emit_filtered, double* alpha, double* post, double* ll,
+               int* status, cudaStream_t st);
+int jt_backward(const DProgram& p, const DBatch& b, const DQuery& q, const JtLaunch& l,
+                const double* alpha, double* post, double* acc /*per-CTA counts or null*/,
+                long long acc_stride, cudaStream_t st);
+int jt_likelihood(const DProgram& p, const DBatch& b, const int* proj_off, const int* proj_on,
+                  const JtLaunch& l, double* out, cudaStream_t st);
+int jt_calibrate(const DProgram& p, const JtLaunch& l, double* R1, double* m1_0, cudaStream_t st);
+// single-slice propagation for the stateful API: tables <- base x lik, collect, distribute
+int jt_slice(const DProgram& p, const JtLaunch& l, const double* start_tables, double* out_tables,
+             double* out_msgs, cudaStream_t st);
+
+}  // namespace nipgpu

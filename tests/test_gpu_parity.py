@@ -1,0 +1,176 @@
+"""GPU parity suite (run with -m gpu on a B200): the CUDA path, called through the
+C ABI (include/nipgpu.h), against
+  * the golden fixtures generated from the reference itself, and
+  * the C oracle on seeded synthetic inputs.
+Tolerance: 1e-9 RELATIVE on posterior marginals, log-likelihoods, expected counts
+and re-estimated CPTs (BASELINE.json north star); exact zeros must stay exact
+zeros (atol = 0) and -DBL_MAX must be reproduced exactly.
+"""
+import numpy as np
+import pytest
+
+from cases import (ALL_CASES, EM_CASES, LIKELIHOOD_CASES, SLICE_CASES, Case, assert_close, unhex)
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [1, 0]  # NIPGPU_ENGINE_JTREE, NIPGPU_ENGINE_AUTO (chain engine when the model allows)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_inference_golden(gpu_lib, name, engine):
+    c = Case(name)
+    m = gpu_lib.Model(c.fm, engine=engine)
+    b = m.batch(c.obs_vars, c.series)
+    for kind, fwd in (("smooth", False), ("filter", True)):
+        posts, lls = c.expected(kind)
+        post, ll = b.infer(c.query, forward_only=fwd)
+        for i, got in enumerate(b.split(post)):
+            assert_close(got, posts[i], "%s %s series %d posterior (engine %d)" % (name, kind, i, m.engine))
+        assert_close(ll, lls, "%s %s loglik" % (name, kind))
+        # interface-variable-only query: the path the chain engine serves directly
+        if c.fm.n_interface == 1:
+            v = int(c.fm.outgoing[0])
+            k = c.query.index(v) if v in c.query else None
+            if k is not None:
+                off = int(sum(c.fm.var_card[q] for q in c.query[:k]))
+                card = int(c.fm.var_card[v])
+                post1, ll1 = b.infer([v], forward_only=fwd)
+                for i, got in enumerate(b.split(post1)):
+                    assert_close(got, posts[i][:, off:off + card], "%s %s interface posterior" % (name, kind))
+                assert_close(ll1, lls, "%s %s loglik (interface query)" % (name, kind))
+    b.close()
+    m.close()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_unmarked_columns_are_ignored(gpu_lib, oracle_lib, engine):
+    """NIP_MARK semantics (src/nip.c:993): only marked variables enter evidence"""
+    c = Case("hmm12_two_leaves")
+    om = oracle_lib.model(c.fm)
+    m = gpu_lib.Model(c.fm, engine=engine)
+    b = m.batch(c.obs_vars, c.series)
+    for keep in ([1, 0], [0, 1], [0, 0]):
+        mask = np.zeros(c.fm.n_vars, dtype=np.uint8)
+        for k, on in zip(c.obs_vars, keep):
+            mask[k] = on
+        post, ll = b.infer([2], use_evidence=mask)
+        for i, got in enumerate(b.split(post)):
+            want, llw = om.infer(c.obs_vars, c.series[i], [2], use_evidence=mask)
+            assert_close(got, want, "masked posterior %r" % (keep,))
+            assert_close(ll[i], llw, "masked loglik %r" % (keep,), atol=1e-12)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("S,M,B,T", [(64, 32, 48, 40), (7, 3, 100, 17), (33, 5, 19, 9)])
+def test_hmm_vs_oracle(gpu_lib, oracle_lib, engine, S, M, B, T):
+    """seeded synthetic HMMs of the benchmark family, ragged lengths, missing data"""
+    from nip_b200.synth import HmmSpec
+    h = HmmSpec(S, M, seed=S + M)
+    fm = h.flat()
+    data = h.sample(B, T, seed=3, missing=0.1)
+    rng = np.random.default_rng(5)
+    series = [data[i, :int(rng.integers(1, T + 1))] for i in range(B)]
+    om = oracle_lib.model(fm)
+    m = gpu_lib.Model(fm, engine=engine)
+    b = m.batch(h.obs_vars, series)
+    post, ll = b.infer(h.hidden_query)
+    fpost, fll = b.infer(h.hidden_query, forward_only=True)
+    for i, (got, fgot) in enumerate(zip(b.split(post), b.split(fpost))):
+        want, llw = om.infer(h.obs_vars, series[i], h.hidden_query)
+        assert_close(got, want, "HMM-%d series %d smoothed" % (S, i))
+        assert_close(ll[i], llw, "HMM-%d series %d loglik" % (S, i))
+        want, llw = om.infer(h.obs_vars, series[i], h.hidden_query, forward_only=True)
+        assert_close(fgot, want, "HMM-%d series %d filtered" % (S, i))
+        assert_close(fll[i], llw, "HMM-%d series %d loglik (filter)" % (S, i))
+
+
+def test_empty_and_single_slice(gpu_lib):
+    c = Case("hmm5")
+    m = gpu_lib.Model(c.fm)
+    b = m.batch(c.obs_vars, [np.zeros((0, 1), dtype=np.int32), c.series[6]])   # T = 0 and T = 1
+    post, ll = b.infer(c.query)
+    assert ll[0] == 0.0
+    posts, lls = c.expected("smooth")
+    assert_close(post, posts[6], "single-slice series")
+    assert_close(ll[1], lls[6], "single-slice loglik")
+    b0 = m.batch(c.obs_vars, [])
+    post, ll = b0.infer(c.query)
+    assert post.shape[0] == 0 and ll.shape[0] == 0
+
+
+@pytest.mark.parametrize("name", EM_CASES)
+def test_em_golden(gpu_lib, name):
+    """each EM iteration from the reference's own inputs: M-step tables/priors, then
+    E-step expected counts and log-likelihood"""
+    c = Case(name)
+    m = gpu_lib.Model(c.fm)
+    b = m.batch(c.obs_vars, c.series)
+    counts_in = unhex(c.j["em"]["init"])
+    for k, it in enumerate(c.j["em"]["iters"]):
+        m.mstep(counts_in)
+        tables, prior = m.parameters()
+        assert_close(tables, unhex(it["tables"]), "%s iter %d re-estimated clique tables" % (name, k))
+        assert_close(prior, unhex(it["prior"]), "%s iter %d priors" % (name, k))
+        counts, ll, st = b.estep()
+        assert (st != 0) == (it["status"] != 0)
+        if it["status"] == 0:
+            assert_close(counts, unhex(it["counts"]), "%s iter %d expected counts" % (name, k))
+            assert_close(ll, float.fromhex(it["ll"]), "%s iter %d loglik" % (name, k))
+        counts_in = unhex(it["counts"])
+
+
+def test_em_pseudocount_once_and_device_mstep(gpu_lib):
+    """counts without the 1.0 pseudo-count + 1 == counts with it; an M-step straight
+    from the device accumulator equals an M-step from the same counts uploaded"""
+    c = Case("hmm5")
+    m = gpu_lib.Model(c.fm)
+    b = m.batch(c.obs_vars, c.series)
+    with_p, ll1, _ = b.estep(add_pseudocount=True)
+    without, ll0, _ = b.estep(add_pseudocount=False)
+    assert_close(without + 1.0, with_p, "pseudo-count")
+    assert ll0 == ll1
+    b.estep(add_pseudocount=True, want_counts=False)
+    m.mstep(None)
+    t_dev, p_dev = m.parameters()
+    m.mstep(with_p)
+    t_up, p_up = m.parameters()
+    assert np.array_equal(t_dev, t_up) and np.array_equal(p_dev, p_up)
+
+
+@pytest.mark.parametrize("name", LIKELIHOOD_CASES)
+def test_likelihood_golden(gpu_lib, name):
+    c = Case(name)
+    m = gpu_lib.Model(c.fm)
+    b = m.batch(c.obs_vars, c.series)
+    on = np.zeros(c.fm.n_vars, dtype=np.uint8)
+    on[c.j["likelihood"]["marked"]] = 1
+    out = b.likelihood(1 - on, on)
+    for i, got in enumerate(b.split(out)):
+        assert_close(got.reshape(-1), unhex(c.j["likelihood"]["out"][i]), "%s likelihood series %d" % (name, i))
+
+
+@pytest.mark.parametrize("name", SLICE_CASES)
+def test_slice_api_golden(gpu_lib, name):
+    c = Case(name)
+    m = gpu_lib.Model(c.fm)
+    for step in c.j["slice"]:
+        m.slice_reset()
+        m.slice_use_priors(step["has_history"])
+        for var, lik in step["evidence"]:
+            m.slice_enter_evidence(var, unhex(lik))
+        m.slice_make_consistent()
+        assert_close(m.slice_mass(), float.fromhex(step["mass"]), "mass")
+        for v in range(c.fm.n_vars):
+            assert_close(m.slice_marginal(v), unhex(step["marginals"][v]), "marginal of %d" % v)
+        for k in range(c.fm.n_cliques):
+            assert_close(m.slice_clique(k), unhex(step["cliques"][k]), "clique %d" % k)
+
+
+def test_launches_are_counted(gpu_lib):
+    c = Case("hmm5")
+    m = gpu_lib.Model(c.fm)
+    b = m.batch(c.obs_vars, c.series)
+    gpu_lib.launch_count(reset=True)
+    b.infer(c.query)
+    assert gpu_lib.launch_count() >= 2
