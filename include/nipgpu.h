@@ -201,6 +201,11 @@ int64_t nipgpu_launch_count(int reset);
  * nipgpu_infer / nipgpu_em_estep call, measured with CUDA events on the library's
  * stream; n receives the number of launches summed. */
 int nipgpu_last_kernel_ms(nipgpu_model* m, double* ms, int32_t* n);
+/* Measures, with CUDA events, what this device sustains on the two resources the
+ * hot path is bound by (MEASURED_PEAKS.json has no FP64 figure): a dependent-free
+ * stream of DMMA m8n8k4 instructions, the same with scalar DFMA, and a plain
+ * device-to-device copy.  Used by bench.py as roofline denominators. */
+int nipgpu_probe_peaks(int device, double* dmma_tflops, double* dfma_tflops, double* copy_gbs);
 /* the CUDA stream (cudaStream_t) all work of this model is enqueued on */
 void* nipgpu_model_stream(nipgpu_model* m);
 

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "nipgpu_em_counts_device", "nipgpu_em_mstep", "nipgpu_likelihood", "nipgpu_slice_reset",
     "nipgpu_slice_use_priors", "nipgpu_slice_enter_evidence", "nipgpu_slice_make_consistent",
     "nipgpu_slice_mass", "nipgpu_slice_marginal", "nipgpu_slice_get_clique",
-    "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_model_stream",
+    "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_model_stream", "nipgpu_probe_peaks",
 ]
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -82,6 +82,7 @@ def load_library(path=LIB_PATH):
     L.nipgpu_launch_count.restype = C.c_int64
     L.nipgpu_launch_count.argtypes = [_i]
     L.nipgpu_last_kernel_ms.argtypes = [_vp, C.POINTER(_d), C.POINTER(C.c_int32)]
+    L.nipgpu_probe_peaks.argtypes = [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]
     L.nipgpu_model_stream.restype = _vp
     L.nipgpu_model_stream.argtypes = [_vp]
     _lib = L
@@ -103,6 +104,13 @@ def _mask(a, n):
     a = np.ascontiguousarray(a, dtype=np.uint8)
     assert a.shape == (n,)
     return a
+
+
+def probe_peaks(device=0):
+    """(DMMA TFLOP/s, DFMA TFLOP/s, copy GB/s) measured live on `device`"""
+    a, b, c = _d(), _d(), _d()
+    _check(load_library().nipgpu_probe_peaks(int(device), C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
 
 
 def launch_count(reset=False):

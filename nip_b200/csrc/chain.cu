@@ -43,18 +43,21 @@ __host__ __device__ inline int frag_index(int kstate, int nstate, int NT) {
 }
 
 struct ChainDev {
-  int S, SP, n_active;
-  const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *lam_static, *lam;
-  long long lam_off[8];  // per active leaf
+  int S, SP, c_miss;   // c_miss: combined evidence index meaning "no evidence in this slice"
+  const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *lam_comb;
 };
 
 struct ChainBatchDev {
-  int n_series, t_max;
-  const int* order;
+  int n_series;
+  const int* order;        // sorted position -> series
   const int* len_sorted;
-  const long long* cum;
-  const int* cfg;
+  const int* cfg;          // [rows] combined evidence index, API row order
   const long long* row_off;
+};
+
+struct ChainComb {
+  int mult[8], n_cfg[8];
+  long long lam_off[8];
 };
 
 // ---------------------------------------------------------------- refresh ---
@@ -113,57 +116,53 @@ __global__ void k_chain_lam_prod(const double* lam, const long long* row_off, in
   out[ip] = p;
 }
 
-// time-major evidence configuration per (slice, sequence, active leaf)
-__global__ void k_chain_cfg(ChainBatchDev B, const int* obs, int n_obs, const int* col_slot,
-                            const int* col_stride, const int* col_card, const int* miss_cfg,
-                            int n_active, int* cfg) {
-  const int bp = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y;
-  if (bp >= B.n_series || t >= B.len_sorted[bp]) return;
-  const long long sm_row = B.row_off[B.order[bp]] + t;
-  const long long tm_row = B.cum[t] + bp;
-  for (int a = 0; a < n_active; a++) {
-    int c = miss_cfg[a];
-    for (int k = 0; k < n_obs; k++) {
-      const int o = obs[sm_row * n_obs + k];
-      if (col_slot[k] == a && o >= 0) c += (o - col_card[k]) * col_stride[k];
-    }
-    cfg[tm_row * n_active + a] = c;
+// Combined evidence table of one call: Lc[c][ip] = lam_static[ip] * prod_a Lambda_a[digit_a(c)][ip]
+// with c = sum_a cfg_a * mult_a.  One gather per (sequence, slice) in the hot kernels.
+__global__ void k_chain_combine(const double* lam, const double* lam_static, int n_active,
+                                ChainComb K, int n_comb, int S, int SP, double* Lc) {
+  const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (x >= (long long)n_comb * SP) return;
+  const int c = (int)(x / SP), ip = (int)(x - (long long)c * SP);
+  double p = ip < S ? lam_static[ip] : 0.0;
+  for (int a = 0; a < n_active && ip < S; a++) {
+    const int digit = (c / K.mult[a]) % K.n_cfg[a];
+    p *= lam[K.lam_off[a] + (long long)digit * SP + ip];
   }
+  Lc[x] = p;
+}
+
+// combined evidence configuration of every data row (API row order)
+__global__ void k_chain_cfg(const int* obs, long long rows, int n_obs, const int* col_slot,
+                            const int* col_stride, const int* col_card, const int* col_mult,
+                            int c_miss, int* cfg) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int c = c_miss;
+  for (int k = 0; k < n_obs; k++) {
+    const int o = obs[r * n_obs + k];
+    if (col_slot[k] >= 0 && o >= 0) c += (o - col_card[k]) * col_stride[k] * col_mult[k];
+  }
+  cfg[r] = c;
 }
 
 // ---------------------------------------------------------------- forward ---
-// lam[n][e] = lambda(state 8n+2q+e) = static part x the active leaves' evidence rows
-template <int NT>
-__device__ __forceinline__ void load_lambda(const ChainDev& C, const int* cfg_row, int q,
-                                            double (&lam)[NT][2]) {
-  const double2* ls = reinterpret_cast<const double2*>(C.lam_static);
-#pragma unroll
-  for (int n = 0; n < NT; n++) {
-    const double2 v = ls[4 * n + q];
-    lam[n][0] = v.x;
-    lam[n][1] = v.y;
-  }
-  for (int a = 0; a < C.n_active; a++) {
-    const double2* p =
-        reinterpret_cast<const double2*>(C.lam + C.lam_off[a] + (long long)cfg_row[a] * C.SP);
-#pragma unroll
-    for (int n = 0; n < NT; n++) {
-      const double2 v = p[4 * n + q];
-      lam[n][0] *= v.x;
-      lam[n][1] *= v.y;
-    }
-  }
-}
-
+// alpha_t = normalise((alpha_{t-1} . A) * lambda_t); log-likelihood terms m1/m2.
+// Per step and warp: 2*NT*NT DMMAs, the same number of 8-byte shared loads, one
+// evidence-row gather (issued before the MMA loop, consumed after it) and one
+// alpha-row store.  The next step's evidence index is prefetched a step ahead so
+// that no dependent global load sits on the critical path.
 template <int NT>
 __global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev B, int want_ll,
-                                                       double* __restrict__ alpha, double* post,
-                                                       int post_stride, int post_off,
-                                                       double* ll_out, int* status_out) {
+                                                       double* __restrict__ alpha,
+                                                       double* __restrict__ post, int post_stride,
+                                                       int post_off, double* ll_out,
+                                                       int* status_out) {
   constexpr int SP = 8 * NT;
   extern __shared__ double sB[];
+  double* s_lam0 = sB + SP * SP;
+  double* s_phi0 = s_lam0 + SP;
   for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) sB[i] = C.Bf1[i];
+  for (int i = threadIdx.x; i < SP; i += blockDim.x) { s_lam0[i] = C.lam0[i]; s_phi0[i] = C.phi0[i]; }
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -171,22 +170,33 @@ __global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev
   const bool valid = bp < B.n_series;
   const int T = valid ? B.len_sorted[bp] : 0;
   const int Tw = __shfl_sync(0xffffffffu, T, 0);  // sorted by length: row 0 is the longest
-  const long long prow0 = valid ? B.row_off[B.order[bp]] : 0;
-  const double2* lam0 = reinterpret_cast<const double2*>(C.lam0);
+  const int orig = valid ? B.order[bp] : 0;
+  const long long row0 = valid ? B.row_off[orig] : 0;
+  const int* cfg = B.cfg + row0;
   double own[NT][2], acc[NT][2], lam[NT][2];
 #pragma unroll
-  for (int n = 0; n < NT; n++) own[n][0] = own[n][1] = 0.0;
+  for (int n = 0; n < NT; n++) own[n][0] = own[n][1] = lam[n][0] = lam[n][1] = 0.0;
   double ll = 0;
   int bad = 0;
+  int c_next = T > 0 ? cfg[0] : 0;
   for (int t = 0; t < Tw; t++) {
     const bool active = t < T;
-    if (t == 0) {
-      const double2* p0 = reinterpret_cast<const double2*>(C.phi0);
+    const int c_cur = c_next;
+    if (active) {  // evidence row of this slice: in flight during the MMA loop
+      const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c_cur * SP);
 #pragma unroll
       for (int n = 0; n < NT; n++) {
-        const double2 v = p0[4 * n + q];
-        acc[n][0] = v.x;
-        acc[n][1] = v.y;
+        const double2 v = __ldg(p + 4 * n + q);
+        lam[n][0] = v.x;
+        lam[n][1] = v.y;
+      }
+    }
+    if (t + 1 < T) c_next = __ldg(cfg + t + 1);
+    if (t == 0) {
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        acc[n][0] = s_phi0[8 * n + 2 * q];
+        acc[n][1] = s_phi0[8 * n + 2 * q + 1];
       }
     } else {
 #pragma unroll
@@ -202,31 +212,27 @@ __global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev
         }
     }
     if (active) {
-      const long long row = B.cum[t] + bp;
-      load_lambda<NT>(C, B.cfg + row * C.n_active, q, lam);
       double m1 = 0, m2 = 0;
 #pragma unroll
       for (int n = 0; n < NT; n++) {
-        if (want_ll) {
-          const double2 l0 = lam0[4 * n + q];
-          m1 += acc[n][0] * l0.x + acc[n][1] * l0.y;
-        }
+        if (want_ll) m1 += acc[n][0] * s_lam0[8 * n + 2 * q] + acc[n][1] * s_lam0[8 * n + 2 * q + 1];
         acc[n][0] *= lam[n][0];
         acc[n][1] *= lam[n][1];
         m2 += acc[n][0] + acc[n][1];
       }
       m2 = quad_sum(m2);
       if (want_ll) m1 = quad_sum(m1);
-      const bool nz = m2 != 0;
+      const double inv = m2 != 0 ? 1.0 / m2 : 1.0;  // zero vector stays zero (nip_normalise_array)
+      const long long row = row0 + t;
       double2* arow = reinterpret_cast<double2*>(alpha + row * SP);
 #pragma unroll
       for (int n = 0; n < NT; n++) {
-        own[n][0] = nz ? acc[n][0] / m2 : acc[n][0];
-        own[n][1] = nz ? acc[n][1] / m2 : acc[n][1];
+        own[n][0] = acc[n][0] * inv;
+        own[n][1] = acc[n][1] * inv;
         arow[4 * n + q] = make_double2(own[n][0], own[n][1]);
       }
       if (post) {  // filtering: the forward marginal of I_t is alpha_t itself
-        double* prow = post + (prow0 + t) * post_stride + post_off;
+        double* prow = post + row * post_stride + post_off;
 #pragma unroll
         for (int n = 0; n < NT; n++) {
           const int c = 8 * n + 2 * q;
@@ -235,30 +241,36 @@ __global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev
         }
       }
       if (want_ll) {  // src/nip.c:1458-1474, BAD_LUCK test :1827-1831
-        if (m1 > 0 && m2 > 0) ll += log(m2) - log(m1);
-        if (m2 == 0) ll = -DBL_MAX;
-        if (m1 <= 0 || m2 <= 0 || ll > 0) bad = 1;
+        // a slice without any evidence has m2 == m1 by definition; do not let rounding decide
+        const double m2l = (c_cur == C.c_miss) ? m1 : m2;
+        if (m1 > 0 && m2l > 0) ll += log(m2l) - log(m1);
+        if (m2l == 0) ll = -DBL_MAX;
+        if (m1 <= 0 || m2l <= 0 || ll > 0) bad = 1;
       }
     }
   }
   if (valid && q == 0) {
-    if (ll_out) ll_out[B.order[bp]] = ll;
-    if (status_out) status_out[B.order[bp]] = bad;
+    if (ll_out) ll_out[orig] = ll;
+    if (status_out) status_out[orig] = bad;
   }
 }
 
 // --------------------------------------------------------------- backward ---
-template <int NT, bool B0_IN_SMEM>
+// Scaled backward recursion.  With beta_t = gamma_{t+1} / alpha_t (the ratio the
+// reference multiplies into out_clique, src/nip.c:1518-1529) one has
+//     beta_{t-1}  proportional to  A . (lambda_t * beta_t)
+//     P(I_t | all evidence) = normalise(alpha_t * beta_t)
+// so the only per-element division of the literal schedule disappears; where
+// alpha_t is 0 the posterior is 0 whatever beta_t holds, which is the reference's
+// 0/0 -> 0 rule (src/nippotential.c:486-491).
+template <int NT>
 __global__ void __launch_bounds__(128) k_chain_backward(ChainDev C, ChainBatchDev B,
                                                         const double* __restrict__ alpha,
-                                                        double* post, int post_stride,
+                                                        double* __restrict__ post, int post_stride,
                                                         int post_off) {
   constexpr int SP = 8 * NT;
   extern __shared__ double sB[];
-  for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) {
-    sB[i] = C.Bb1[i];
-    if (B0_IN_SMEM) sB[SP * SP + i] = C.Bb0[i];
-  }
+  for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) sB[i] = C.Bb1[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -266,86 +278,101 @@ __global__ void __launch_bounds__(128) k_chain_backward(ChainDev C, ChainBatchDe
   const bool valid = bp < B.n_series;
   const int T = valid ? B.len_sorted[bp] : 0;
   const int Tw = __shfl_sync(0xffffffffu, T, 0);
-  const long long prow0 = valid ? B.row_off[B.order[bp]] : 0;
-  double acur[NT][2], gnext[NT][2], r[NT][2], u[NT][2];
+  const int orig = valid ? B.order[bp] : 0;
+  const long long row0 = valid ? B.row_off[orig] : 0;
+  const int* cfg = B.cfg + row0;
+  const bool vec_post = ((post_stride | post_off) & 1) == 0 && C.S == SP;
+  double beta[NT][2], r[NT][2], lamn[NT][2], a[NT][2], u[NT][2];
 #pragma unroll
-  for (int n = 0; n < NT; n++) acur[n][0] = acur[n][1] = gnext[n][0] = gnext[n][1] = 0.0;
+  for (int n = 0; n < NT; n++)
+    beta[n][0] = beta[n][1] = r[n][0] = r[n][1] = lamn[n][0] = lamn[n][1] = u[n][0] = u[n][1] = 0.0;
+  // prologue: evidence row of the last slice, evidence index of the one before
+  int c_pre = 0;
+  if (Tw - 1 < T && Tw >= 1) {
+    const int c = cfg[Tw - 1];
+    const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c * SP);
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+      const double2 v = __ldg(p + 4 * n + q);
+      lamn[n][0] = v.x;
+      lamn[n][1] = v.y;
+    }
+  }
+  if (Tw - 2 < T && Tw >= 2) c_pre = cfg[Tw - 2];
   for (int t = Tw - 1; t >= 0; t--) {
     const bool active = t < T;
-    const bool last = t == T - 1;
-    const long long row = active ? B.cum[t] + bp : 0;
     if (active) {
-      if (last) {  // first slice processed for this sequence: alpha_{T-1} comes from HBM
-        const double2* arow = reinterpret_cast<const double2*>(alpha + row * SP);
+      const double2* arow = reinterpret_cast<const double2*>(alpha + (row0 + t) * SP);
 #pragma unroll
-        for (int n = 0; n < NT; n++) {
-          const double2 v = arow[4 * n + q];
-          acur[n][0] = v.x;
-          acur[n][1] = v.y;
-        }
+      for (int n = 0; n < NT; n++) {  // alpha_t: consumed after the MMA loop
+        const double2 v = __ldg(arow + 4 * n + q);
+        a[n][0] = v.x;
+        a[n][1] = v.y;
       }
-      load_lambda<NT>(C, B.cfg + row * C.n_active, q, r);
-      // r = lambda * gamma_{t+1} / alpha_t (0 where alpha_t == 0); posterior of I_t = alpha_t * ratio
-      double ps = 0;
+      const bool first = t == T - 1;  // beta_{T-1} = 1
 #pragma unroll
-      for (int n = 0; n < NT; n++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const double a = acur[n][e];
-          const double rho = last ? 1.0 : (a != 0 ? gnext[n][e] / a : 0.0);
-          r[n][e] *= rho;
-          u[n][e] = a * rho;  // un-normalised smoothed marginal, parked in u for the moment
-          ps += u[n][e];
-        }
-      ps = quad_sum(ps);
-      if (post) {
-        double* prow = post + (prow0 + t) * post_stride + post_off;
-        const bool nz = ps != 0;
-#pragma unroll
-        for (int n = 0; n < NT; n++) {
-          const int c = 8 * n + 2 * q;
-          if (c < C.S) prow[c] = nz ? u[n][0] / ps : u[n][0];
-          if (c + 1 < C.S) prow[c + 1] = nz ? u[n][1] / ps : u[n][1];
-        }
+      for (int n = 0; n < NT; n++) {
+        if (first) beta[n][0] = beta[n][1] = 1.0;
+        r[n][0] = lamn[n][0] * beta[n][0];
+        r[n][1] = lamn[n][1] * beta[n][1];
       }
-    } else {
-#pragma unroll
-      for (int n = 0; n < NT; n++) r[n][0] = r[n][1] = 0.0;
     }
-    {
-      // u = r . A^T  (k = current state, n = previous state); slice 0 uses the prior-weighted table
-      const double* tab = (t == 0) ? (B0_IN_SMEM ? sB + SP * SP : C.Bb0) : sB;
+    if (t - 1 < T && t >= 1) {  // evidence row of slice t-1 (its index arrived a step ago)
+      const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c_pre * SP);
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        const double2 v = __ldg(p + 4 * n + q);
+        lamn[n][0] = v.x;
+        lamn[n][1] = v.y;
+      }
+    }
+    if (t - 2 < T && t >= 2) c_pre = __ldg(cfg + t - 2);
+    if (t > 0) {  // u = r . A^T   (k = current state, n = previous state)
 #pragma unroll
       for (int n = 0; n < NT; n++) u[n][0] = u[n][1] = 0.0;
 #pragma unroll
       for (int j = 0; j < NT; j++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          const double a = r[j][e];
-          const double* brow = tab + (((j * 2 + e) * NT) << 5) + lane;
+          const double av = r[j][e];
+          const double* brow = sB + (((j * 2 + e) * NT) << 5) + lane;
 #pragma unroll
-          for (int n = 0; n < NT; n++) dmma(u[n][0], u[n][1], a, brow[n << 5]);
+          for (int n = 0; n < NT; n++) dmma(u[n][0], u[n][1], av, brow[n << 5]);
         }
     }
-    if (active && t > 0) {
-      // gamma_t = normalise(alpha_{t-1} * u); alpha_{t-1} becomes the next slice's alpha_t
-      const double2* arow = reinterpret_cast<const double2*>(alpha + (B.cum[t - 1] + bp) * SP);
-      double z = 0;
+    if (active) {
+      double ps = 0, us = 0;
 #pragma unroll
       for (int n = 0; n < NT; n++) {
-        const double2 v = arow[4 * n + q];
-        acur[n][0] = v.x;
-        acur[n][1] = v.y;
-        gnext[n][0] = v.x * u[n][0];
-        gnext[n][1] = v.y * u[n][1];
-        z += gnext[n][0] + gnext[n][1];
+        a[n][0] *= beta[n][0];
+        a[n][1] *= beta[n][1];
+        ps += a[n][0] + a[n][1];
+        us += u[n][0] + u[n][1];
       }
-      z = quad_sum(z);
-      if (z != 0) {
+      ps = quad_sum(ps);
+      us = quad_sum(us);
+      const double pinv = ps != 0 ? 1.0 / ps : 1.0;
+      const double uinv = us != 0 ? 1.0 / us : 1.0;
+      if (post) {
+        double* prow = post + (row0 + t) * post_stride + post_off;
+        if (vec_post) {
+          double2* p2 = reinterpret_cast<double2*>(prow);
+#pragma unroll
+          for (int n = 0; n < NT; n++) p2[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
+        } else {
+#pragma unroll
+          for (int n = 0; n < NT; n++) {
+            const int c = 8 * n + 2 * q;
+            if (c < C.S) prow[c] = a[n][0] * pinv;
+            if (c + 1 < C.S) prow[c + 1] = a[n][1] * pinv;
+          }
+        }
+      }
+      if (t > 0) {
 #pragma unroll
         for (int n = 0; n < NT; n++) {
-          gnext[n][0] /= z;
-          gnext[n][1] /= z;
+          beta[n][0] = u[n][0] * uinv;
+          beta[n][1] = u[n][1] * uinv;
         }
       }
     }
@@ -362,7 +389,7 @@ int set_smem(K kernel, size_t bytes) {
 template <int NT>
 int launch_forward(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
                    cudaStream_t st) {
-  const size_t smem = sizeof(double) * 64 * NT * NT;
+  const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
   if (int e = set_smem(k_chain_forward<NT>, smem)) return e;
   const int grid = (B.n_series + 31) / 32;
   k_chain_forward<NT><<<grid, 128, smem, st>>>(C, B, a.want_ll, alpha,
@@ -376,16 +403,9 @@ template <int NT>
 int launch_backward(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a,
                     const double* alpha, cudaStream_t st) {
   const int grid = (B.n_series + 31) / 32;
-  const size_t one = sizeof(double) * 64 * NT * NT;
-  if (2 * one <= 96 * 1024) {
-    if (int e = set_smem(k_chain_backward<NT, true>, 2 * one)) return e;
-    k_chain_backward<NT, true><<<grid, 128, 2 * one, st>>>(C, B, alpha, a.d_post, a.post_stride,
-                                                           a.post_off);
-  } else {
-    if (int e = set_smem(k_chain_backward<NT, false>, one)) return e;
-    k_chain_backward<NT, false><<<grid, 128, one, st>>>(C, B, alpha, a.d_post, a.post_stride,
-                                                        a.post_off);
-  }
+  const size_t smem = sizeof(double) * 64 * NT * NT;
+  if (int e = set_smem(k_chain_backward<NT>, smem)) return e;
+  k_chain_backward<NT><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride, a.post_off);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
@@ -562,6 +582,7 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
   NIPGPU_LAUNCHED();
   NIPGPU_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_rows);
+  cm.param_version++;
   return NIPGPU_OK;
 }
 
@@ -578,6 +599,7 @@ bool chain_plan(const HostModel& hm, const ChainModel& cm, int n_obs, const int*
   plan.col_leaf_slot.assign(n_obs, -1);
   plan.col_stride.assign(n_obs, 0);
   plan.col_card.assign(n_obs, 0);
+  plan.col_mult.assign(n_obs, 0);
   for (int k = 0; k < n_obs; k++) {
     const int v = obs_vars[k];
     if (use_evidence && !use_evidence[v]) continue;
@@ -590,29 +612,35 @@ bool chain_plan(const HostModel& hm, const ChainModel& cm, int n_obs, const int*
     plan.col_card[k] = hm.card[v];
   }
   plan.n_active = (int)plan.active_leaf.size();
-  return plan.n_active <= 8;
+  if (plan.n_active > 8) return false;
+  long long mult = 1;
+  plan.c_miss = 0;
+  for (int a = 0; a < plan.n_active; a++) {
+    const ChainLeafHost& L = cm.leaves[plan.active_leaf[a]];
+    plan.mult.push_back((int)mult);
+    plan.c_miss += L.miss_cfg * (int)mult;
+    mult *= L.n_cfg;
+    if (mult * cm.SP > (1LL << 25)) return false;  // combined evidence table too large
+  }
+  plan.n_comb = (int)mult;
+  for (int k = 0; k < n_obs; k++)
+    if (plan.col_leaf_slot[k] >= 0) plan.col_mult[k] = plan.mult[plan.col_leaf_slot[k]];
+  return true;
 }
 
 int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, const int* len,
                         long long rows, int t_max, cudaStream_t st) {
+  (void)t_max;
   if (cb.ready) return NIPGPU_OK;
   cb.order.resize(n_series);
   for (int i = 0; i < n_series; i++) cb.order[i] = i;
   std::stable_sort(cb.order.begin(), cb.order.end(), [&](int a, int b) { return len[a] > len[b]; });
   cb.len_sorted.resize(n_series);
   for (int i = 0; i < n_series; i++) cb.len_sorted[i] = len[cb.order[i]];
-  cb.cum.assign((size_t)t_max + 1, 0);
-  {
-    int act = n_series;
-    for (int t = 0; t < t_max; t++) {
-      while (act > 0 && cb.len_sorted[act - 1] <= t) act--;
-      cb.cum[t + 1] = cb.cum[t] + act;
-    }
-  }
   if (int e = upload(&cb.d_order, cb.order, st)) return e;
   if (int e = upload(&cb.d_len_sorted, cb.len_sorted, st)) return e;
-  if (int e = upload(&cb.d_cum, cb.cum, st)) return e;
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_alpha, std::max<long long>(rows, 1) * cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cb.d_cfg, std::max<long long>(rows, 1) * sizeof(int)));
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_lam_static, cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaStreamSynchronize(st));
   cb.ready = true;
@@ -620,57 +648,78 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
 }
 
 void chain_batch_free(ChainBatch& cb) {
-  cudaFree(cb.d_order); cudaFree(cb.d_len_sorted); cudaFree(cb.d_cum); cudaFree(cb.d_cfg);
-  cudaFree(cb.d_alpha); cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_active_off);
+  cudaFree(cb.d_order); cudaFree(cb.d_len_sorted); cudaFree(cb.d_cfg); cudaFree(cb.d_alpha);
+  cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_rows); cudaFree(cb.d_comb);
   cb = ChainBatch();
+}
+
+// per-call evidence plumbing: static lambda, combined table, per-row configuration.
+// Cached on the batch: a repeated call with the same plan only launches the hot kernels.
+static int chain_prepare_evidence(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
+                                  const ChainInferArgs& a, cudaStream_t st) {
+  std::vector<int> key;
+  key.insert(key.end(), plan.active_leaf.begin(), plan.active_leaf.end());
+  key.push_back(-1);
+  key.insert(key.end(), plan.col_leaf_slot.begin(), plan.col_leaf_slot.end());
+  key.push_back((int)cm.param_version);
+  if (cb.plan_key == key && cb.d_comb) return NIPGPU_OK;
+  const int na = plan.n_active;
+  std::vector<long long> inactive_rows;
+  for (int l = 0; l < cm.n_real; l++)
+    if (std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) == plan.active_leaf.end())
+      inactive_rows.push_back(cm.leaves[l].lam_off + (long long)cm.leaves[l].miss_cfg * cm.SP);
+  cudaFree(cb.d_rows);
+  cb.d_rows = nullptr;
+  if (int e = upload(&cb.d_rows, inactive_rows, st)) return e;
+  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, cb.d_rows, (int)inactive_rows.size(),
+                                                        cm.S, cm.SP, cb.d_lam_static);
+  NIPGPU_LAUNCHED();
+  ChainComb K;
+  for (int i = 0; i < 8; i++) {
+    K.mult[i] = i < na ? plan.mult[i] : 1;
+    K.n_cfg[i] = i < na ? cm.leaves[plan.active_leaf[i]].n_cfg : 1;
+    K.lam_off[i] = i < na ? cm.leaves[plan.active_leaf[i]].lam_off : 0;
+  }
+  const size_t need = (size_t)plan.n_comb * cm.SP;
+  if (cb.comb_cap < need) {
+    cudaFree(cb.d_comb);
+    cb.d_comb = nullptr;
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_comb, need * sizeof(double)));
+    cb.comb_cap = need;
+  }
+  k_chain_combine<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(cm.d_lam, cb.d_lam_static, na, K,
+                                                                 plan.n_comb, cm.S, cm.SP, cb.d_comb);
+  NIPGPU_LAUNCHED();
+  std::vector<int> cols;  // slot | stride | card | mult
+  cols.insert(cols.end(), plan.col_leaf_slot.begin(), plan.col_leaf_slot.end());
+  cols.insert(cols.end(), plan.col_stride.begin(), plan.col_stride.end());
+  cols.insert(cols.end(), plan.col_card.begin(), plan.col_card.end());
+  cols.insert(cols.end(), plan.col_mult.begin(), plan.col_mult.end());
+  cudaFree(cb.d_cols);
+  cb.d_cols = nullptr;
+  if (int e = upload(&cb.d_cols, cols, st)) return e;
+  if (a.rows > 0) {
+    k_chain_cfg<<<(unsigned)((a.rows + 255) / 256), 256, 0, st>>>(
+        a.d_obs, a.rows, a.n_obs, cb.d_cols, cb.d_cols + a.n_obs, cb.d_cols + 2 * a.n_obs,
+        cb.d_cols + 3 * a.n_obs, plan.c_miss, cb.d_cfg);
+    NIPGPU_LAUNCHED();
+  }
+  NIPGPU_CUDA(cudaStreamSynchronize(st));  // host vectors above die here
+  cb.plan_key = key;
+  return NIPGPU_OK;
 }
 
 int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
                 const ChainInferArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
   (void)hm;
-  const int na = plan.n_active;
-  // ---- per-call evidence configuration (time-major) ----
-  const size_t need = (size_t)std::max<long long>(a.rows, 1) * std::max(na, 1);
-  if (cb.cfg_cap < need) {
-    cudaFree(cb.d_cfg);
-    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_cfg, need * sizeof(int)));
-    cb.cfg_cap = need;
-  }
-  std::vector<int> cols;  // slot | stride | card | miss_cfg
-  cols.insert(cols.end(), plan.col_leaf_slot.begin(), plan.col_leaf_slot.end());
-  cols.insert(cols.end(), plan.col_stride.begin(), plan.col_stride.end());
-  cols.insert(cols.end(), plan.col_card.begin(), plan.col_card.end());
-  for (int l : plan.active_leaf) cols.push_back(cm.leaves[l].miss_cfg);
-  cudaFree(cb.d_cols);
-  cb.d_cols = nullptr;
-  if (int e = upload(&cb.d_cols, cols, st)) return e;
-  std::vector<long long> inactive_rows;
-  for (int l = 0; l < cm.n_real; l++)
-    if (std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) == plan.active_leaf.end())
-      inactive_rows.push_back(cm.leaves[l].lam_off + (long long)cm.leaves[l].miss_cfg * cm.SP);
-  cudaFree(cb.d_active_off);
-  cb.d_active_off = nullptr;
-  if (int e = upload(&cb.d_active_off, inactive_rows, st)) return e;
-  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, cb.d_active_off,
-                                                        (int)inactive_rows.size(), cm.S, cm.SP,
-                                                        cb.d_lam_static);
-  NIPGPU_LAUNCHED();
-
+  if (int e = chain_prepare_evidence(cm, cb, plan, a, st)) return e;
   ChainBatchDev B;
-  B.n_series = a.n_series; B.t_max = a.t_max; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
-  B.cum = cb.d_cum; B.cfg = cb.d_cfg; B.row_off = a.d_row_off;
-  if (na > 0 && a.rows > 0) {
-    dim3 grid((a.n_series + 127) / 128, a.t_max);
-    k_chain_cfg<<<grid, 128, 0, st>>>(B, a.d_obs, a.n_obs, cb.d_cols, cb.d_cols + a.n_obs,
-                                      cb.d_cols + 2 * a.n_obs, cb.d_cols + 3 * a.n_obs, na, cb.d_cfg);
-    NIPGPU_LAUNCHED();
-  }
+  B.n_series = a.n_series; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
+  B.cfg = cb.d_cfg; B.row_off = a.d_row_off;
   ChainDev C;
-  C.S = cm.S; C.SP = cm.SP; C.n_active = na;
+  C.S = cm.S; C.SP = cm.SP; C.c_miss = plan.c_miss;
   C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
-  C.lam_static = cb.d_lam_static; C.lam = cm.d_lam;
-  for (int i = 0; i < 8; i++) C.lam_off[i] = i < na ? cm.leaves[plan.active_leaf[i]].lam_off : 0;
-
+  C.lam_comb = cb.d_comb;
   if (a.n_series == 0) return NIPGPU_OK;
   if (ev0) NIPGPU_CUDA(cudaEventRecord(ev0, st));
   int e = NIPGPU_OK;
@@ -682,7 +731,7 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
     default: set_error("chain: unsupported interface size"); return NIPGPU_EUNSUPPORTED;
   }
   if (e) return e;
-  if (!a.forward_only) {
+  if (!a.forward_only && a.d_post) {
     switch (cm.NT) {
       case 1: e = launch_backward<1>(C, B, a, cb.d_alpha, st); break;
       case 2: e = launch_backward<2>(C, B, a, cb.d_alpha, st); break;

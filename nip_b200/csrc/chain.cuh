@@ -48,22 +48,23 @@ struct ChainModel {
   double* d_lam = nullptr;     // all Lambda tables
   long long lam_total = 0;
   int* d_leaf_meta = nullptr;  // flattened per-leaf metadata for the refresh kernel
+  long long param_version = 0; // bumped by chain_refresh: invalidates cached evidence tables
 };
 
 struct ChainBatch {
   bool ready = false;
   std::vector<int> order;          // sorted position -> series (length descending)
   std::vector<int> len_sorted;
-  std::vector<long long> cum;      // [t_max+1] rows before slice t in time-major order
   int* d_order = nullptr;
   int* d_len_sorted = nullptr;
-  long long* d_cum = nullptr;
-  int* d_cfg = nullptr;            // [rows][n_active] time-major
-  size_t cfg_cap = 0;
-  double* d_alpha = nullptr;       // [rows][SP] time-major
+  int* d_cfg = nullptr;            // [rows] combined evidence index per data row
+  double* d_alpha = nullptr;       // [rows][SP], same row order as the API
   double* d_lam_static = nullptr;  // [SP] product of the inactive real leaves' no-evidence rows
-  int* d_cols = nullptr;           // per-call column metadata
-  long long* d_active_off = nullptr;
+  double* d_comb = nullptr;        // [n_comb][SP] combined evidence table of the cached plan
+  size_t comb_cap = 0;
+  int* d_cols = nullptr;           // column metadata of the cached plan
+  long long* d_rows = nullptr;
+  std::vector<int> plan_key;       // identifies the cached plan
 };
 
 // per-call evidence plan: which leaves see evidence through which data columns
@@ -73,6 +74,9 @@ struct ChainPlan {
   std::vector<int> col_leaf_slot;     // [n_obs] index into active_leaf or -1
   std::vector<int> col_stride;        // [n_obs] cfg stride of the column's digit
   std::vector<int> col_card;          // [n_obs]
+  std::vector<int> col_mult;          // [n_obs] multiplier of the column's leaf in the combined index
+  std::vector<int> mult;              // per active leaf
+  int n_comb = 1, c_miss = 0;         // combined evidence configurations / the "no evidence" one
 };
 
 std::string chain_build(HostModel& hm, ChainModel& cm);

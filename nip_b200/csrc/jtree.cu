@@ -157,12 +157,15 @@ __device__ void do_distribute(const DProgram& P, const Work& w, const DMsg* list
   }
 }
 
-__device__ void enter_row(const DProgram& P, const Work& w, const int* obs, int n_obs,
-                          const int* obs_proj) {
+// returns how many observations were entered
+__device__ int enter_row(const DProgram& P, const Work& w, const int* obs, int n_obs,
+                         const int* obs_proj) {
+  int n = 0;
   for (int k = 0; k < n_obs; k++) {
     const int pj = obs_proj[k], o = obs[k];
-    if (pj >= 0 && o >= 0) op_evidence(P, w.tab, pj, o);
+    if (pj >= 0 && o >= 0) { op_evidence(P, w.tab, pj, o); n++; }
   }
+  return n;
 }
 
 __device__ void write_queries(const DProgram& P, const Work& w, const DQuery& Q, double* row,
@@ -202,10 +205,13 @@ __global__ void k_jt_forward(DProgram P, DBatch B, DQuery Q, double* gwork, size
           m1 = block_sum(s, red);
         }
       }
-      enter_row(P, w, B.obs + (row0 + t) * B.n_obs, B.n_obs, B.obs_proj);
+      const int entered = enter_row(P, w, B.obs + (row0 + t) * B.n_obs, B.n_obs, B.obs_proj);
       do_collect(P, w);
       double m2 = 0;
       if (want_ll) m2 = vec_sum(w.tab + P.root_tab, P.root_size, red);
+      // a slice without any evidence has m2 == m1 by definition; do not let rounding decide
+      // whether the running log-likelihood is "> 0" (the reference's BAD_LUCK test)
+      if (want_ll && entered == 0) m2 = m1;
       if (emit) {
         do_distribute(P, w, P.distribute, P.n_distribute);
         if (post) write_queries(P, w, Q, post + (row0 + t) * Q.row, red);
@@ -293,9 +299,10 @@ __global__ void k_jt_likelihood(DProgram P, DBatch B, const int* proj_off, const
       const double m1 = vec_sum(w.tab + P.root_tab, P.root_size, red);
       load_tables(P, w.tab, t == 0 ? P.base0 : P.base1);
       enter_row(P, w, obs, B.n_obs, proj_off);
-      enter_row(P, w, obs, B.n_obs, proj_on);
+      const int extra = enter_row(P, w, obs, B.n_obs, proj_on);
       do_collect(P, w);
-      const double m2 = vec_sum(w.tab + P.root_tab, P.root_size, red);
+      double m2 = vec_sum(w.tab + P.root_tab, P.root_size, red);
+      if (extra == 0) m2 = m1;
       if (threadIdx.x == 0) { out[(row0 + t) * 2] = m1; out[(row0 + t) * 2 + 1] = m2; }
     }
   }

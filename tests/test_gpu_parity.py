@@ -120,6 +120,34 @@ def test_em_golden(gpu_lib, name):
         counts_in = unhex(it["counts"])
 
 
+def test_bad_luck_is_reported(gpu_lib, oracle_lib):
+    """an impossible observation (m2 == 0) must surface as NIP_ERROR_BAD_LUCK
+    (src/nip.c:1827-1854), a clean set must not"""
+    c = Case("model_net")
+    m = gpu_lib.Model(c.fm)
+    om = oracle_lib.model(c.fm)
+    impossible = [np.array([0, 4, 0, 4]).reshape(-1, 1)]
+    fine = [np.array([2, 3, 2, 3, 2, 4]).reshape(-1, 1)]
+    for series, want in ((impossible, 8), (fine, 0), (fine + impossible, 8)):
+        _, _, st_o = om.estep(c.obs_vars, series)
+        _, _, st = m.batch(c.obs_vars, series).estep()
+        assert st == want and st_o == want
+
+
+def test_evidence_free_first_slice_is_not_bad_luck(gpu_lib):
+    """DESIGN.md, deviations: for a slice without evidence the reference computes
+    log(m2) - log(m1) from two masses that differ only by rounding and may flag
+    BAD_LUCK by chance; the device path defines m2 := m1 there."""
+    c = Case("hmm5")
+    m = gpu_lib.Model(c.fm)
+    series = [np.array([-1, 2, 1, -1, 0]).reshape(-1, 1), np.array([-1]).reshape(-1, 1)]
+    b = m.batch(c.obs_vars, series)
+    _, ll, st = b.estep()
+    assert st == 0 and ll < 0
+    _, lls = b.infer(c.query)
+    assert lls[1] == 0.0
+
+
 def test_em_pseudocount_once_and_device_mstep(gpu_lib):
     """counts without the 1.0 pseudo-count + 1 == counts with it; an M-step straight
     from the device accumulator equals an M-step from the same counts uploaded"""
