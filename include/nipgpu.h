@@ -121,6 +121,9 @@ int nipgpu_batch_create(nipgpu_model* m, int32_t n_series, const int32_t* length
                         int32_t n_obs, const int32_t* obs_vars, const int32_t* data,
                         nipgpu_batch** out);
 void nipgpu_batch_destroy(nipgpu_batch* b);
+/* Replace the observations of an existing batch (same shape as at creation):
+ * the host-to-device half of one end-to-end step.  `data` may be pinned. */
+int nipgpu_batch_update(nipgpu_batch* b, const int32_t* data);
 
 /* Batched forward_inference / forward_backward_inference
  * (src/nip.c:1103-1315, 1320-1581) for every series of the batch.

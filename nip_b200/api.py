@@ -24,7 +24,7 @@ EBADLUCK = 8
 ABI_SYMBOLS = [
     "nipgpu_last_error", "nipgpu_device_check", "nipgpu_model_create", "nipgpu_model_destroy",
     "nipgpu_model_engine", "nipgpu_model_set_parameters", "nipgpu_model_get_parameters",
-    "nipgpu_batch_create", "nipgpu_batch_destroy", "nipgpu_infer", "nipgpu_infer_device",
+    "nipgpu_batch_create", "nipgpu_batch_destroy", "nipgpu_batch_update", "nipgpu_infer", "nipgpu_infer_device",
     "nipgpu_em_estep", "nipgpu_model_counts_size", "nipgpu_model_counts_offsets",
     "nipgpu_em_counts_device", "nipgpu_em_mstep", "nipgpu_likelihood", "nipgpu_slice_reset",
     "nipgpu_slice_use_priors", "nipgpu_slice_enter_evidence", "nipgpu_slice_make_consistent",
@@ -63,6 +63,7 @@ def load_library(path=LIB_PATH):
     L.nipgpu_batch_create.argtypes = [_vp, _i, _vp, _i, _vp, _vp, C.POINTER(_vp)]
     L.nipgpu_batch_destroy.argtypes = [_vp]
     L.nipgpu_batch_destroy.restype = None
+    L.nipgpu_batch_update.argtypes = [_vp, _vp]
     L.nipgpu_infer.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp]
     L.nipgpu_infer_device.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]
     L.nipgpu_em_estep.argtypes = [_vp, _vp, _vp, _i, _vp, C.POINTER(_d), C.POINTER(_i)]
@@ -225,6 +226,11 @@ class Batch:
         self.h = None
 
     __del__ = close
+
+    def update(self, data):
+        """re-upload observations (int32, same shape); `data` may live in pinned memory"""
+        assert data.dtype == np.int32 and data.size == self.rows * max(len(self.obs_vars), 1)
+        _check(self.L.nipgpu_batch_update(self.h, _p(data)))
 
     def _row(self, query):
         return int(sum(self.model.fm.var_card[v] for v in query))

@@ -407,6 +407,16 @@ int nipgpu_batch_create(nipgpu_model* m, int32_t n_series, const int32_t* length
   return NIPGPU_OK;
 }
 
+int nipgpu_batch_update(nipgpu_batch* b, const int32_t* data) {
+  if (!b || !data) return fail(NIPGPU_EINVAL, "null argument");
+  NIPGPU_CUDA(cudaSetDevice(b->m->device));
+  NIPGPU_CUDA(cudaMemcpyAsync(b->d_obs, data, (size_t)b->rows * b->n_obs * sizeof(int),
+                              cudaMemcpyHostToDevice, b->m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(b->m->stream));
+  b->chain.plan_key.clear();  // cached per-row evidence configuration is stale
+  return NIPGPU_OK;
+}
+
 void nipgpu_batch_destroy(nipgpu_batch* b) {
   if (!b) return;
   if (b->m) { cudaSetDevice(b->m->device); cudaStreamSynchronize(b->m->stream); }

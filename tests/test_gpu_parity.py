@@ -126,7 +126,7 @@ def test_bad_luck_is_reported(gpu_lib, oracle_lib):
     c = Case("model_net")
     m = gpu_lib.Model(c.fm)
     om = oracle_lib.model(c.fm)
-    impossible = [np.array([0, 4, 0, 4]).reshape(-1, 1)]
+    impossible = [np.array([1, 0, 4]).reshape(-1, 1)]   # P(1,0,4) == 0 in examples/model.net
     fine = [np.array([2, 3, 2, 3, 2, 4]).reshape(-1, 1)]
     for series, want in ((impossible, 8), (fine, 0), (fine + impossible, 8)):
         _, _, st_o = om.estep(c.obs_vars, series)
