@@ -86,7 +86,7 @@ int refresh_derived(nipgpu_model* m) {
   if (one.gwork == nullptr && one.smem_bytes == 0) return fail(NIPGPU_EINVAL, "launch not configured");
   if (int e = jt_calibrate(m->prog, one, m->d_R1, m->d_m10, st)) return e;
   if (m->chain.ok)
-    if (int e = chain_refresh(hm, m->chain, m->d_base0, m->d_base1, m->tab_off, m->d_ipool, st)) return e;
+    if (int e = chain_refresh(hm, m->chain, m->d_base0, m->d_base1, m->tab_off, m->d_ipool, m->d_R1, m->d_m10, st)) return e;
   NIPGPU_CUDA(cudaStreamSynchronize(st));
   m->slice_consistent = false;
   return NIPGPU_OK;

@@ -22,29 +22,26 @@ namespace nipgpu {
 namespace {
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
 }
 
-// sum over the 4 lanes that share one sequence; only those lanes need to be converged
-__device__ __forceinline__ double quad_sum(double v) {
-  const unsigned mask = 0xFu << ((threadIdx.x & 31) & 28);
-  v += __shfl_xor_sync(mask, v, 1);
-  v += __shfl_xor_sync(mask, v, 2);
-  return v;
-}
 
 // position of A(k-state, n-state) inside a fragment-ordered SPxSP table
+// For NT >= 2 the fragments of n-tiles (2m, 2m+1) of one lane are adjacent (one LDS.128).
 __host__ __device__ inline int frag_index(int kstate, int nstate, int NT) {
   const int j = kstate >> 3, q = (kstate & 7) >> 1, e = kstate & 1;
   const int nt = nstate >> 3, g = nstate & 7;
-  return (((j * 2 + e) * NT + nt) << 5) + (g << 2) + q;
+  const int ks = j * 2 + e, lane = (g << 2) + q;
+  if (NT >= 2) return ((((ks * (NT / 2) + (nt >> 1)) << 5) + lane) << 1) + (nt & 1);
+  return ((ks * NT + nt) << 5) + lane;
 }
 
 struct ChainDev {
   int S, SP, c_miss;   // c_miss: combined evidence index meaning "no evidence in this slice"
-  const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *lam_comb;
+  double m1_0;         // mass of the evidence-free first slice
+  const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *R1, *lam_comb;
 };
 
 struct ChainBatchDev {
@@ -145,24 +142,95 @@ __global__ void k_chain_cfg(const int* obs, long long rows, int n_obs, const int
   cfg[r] = c;
 }
 
+// acc[n] += sum over the 2*NT k-steps of A(k-step) x B(k-step, n): the whole
+// [8 x SP] . [SP x SP] contraction of one slice.  One 16-byte shared load brings
+// the B fragments of two neighbouring n-tiles; they are fetched a k-step ahead.
+// `side(ks)` is called once per k-step with ks as a compile-time-foldable value:
+// the callers put work there that does not depend on this sweep, so that it fills
+// the issue slots between tensor instructions (a warp can issue one DMMA per ~16
+// cycles and is alone on its scheduler).
+template <int NT, class Side>
+__device__ __forceinline__ void mma_sweep(double (&acc)[NT][2], const double (&a)[NT][2],
+                                          const double* __restrict__ frag, Side side) {
+  double b[2][NT];
+  auto fetch = [&](int ks, double* dst) {
+    if constexpr (NT >= 2) {
+      const double2* p = reinterpret_cast<const double2*>(frag) + ((ks * (NT / 2)) << 5);
+#pragma unroll
+      for (int n2 = 0; n2 < NT / 2; n2++) {
+        const double2 v = p[n2 << 5];
+        dst[2 * n2] = v.x;
+        dst[2 * n2 + 1] = v.y;
+      }
+    } else {
+      dst[0] = frag[ks << 5];
+    }
+  };
+  fetch(0, b[0]);
+#pragma unroll
+  for (int ks = 0; ks < 2 * NT; ks++) {
+    if (ks + 1 < 2 * NT) fetch(ks + 1, b[(ks + 1) & 1]);
+    const double av = a[ks >> 1][ks & 1];
+#pragma unroll
+    for (int n = 0; n < NT; n++) dmma(acc[n][0], acc[n][1], av, b[ks & 1][n]);
+    side(ks);
+  }
+}
+
+// running log-likelihood sum_t log(m2_t) - log(m1_t) kept as a product with a
+// separate binary exponent: two multiplies per slice instead of two logarithms.
+struct LogAcc {
+  double p1 = 1.0, p2 = 1.0;  // mantissa products of the m1 / m2 factors
+  int e1 = 0, e2 = 0;         // their binary exponents
+  int zero = 0, bad = 0;
+  __device__ __forceinline__ static void renorm(double& p, int& e) {
+    const int hi = __double2hiint(p);
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    e += ex;
+    p = __hiloint2double(hi - (ex << 20), __double2loint(p));
+  }
+  // semantics of src/nip.c:1458-1474 and of the BAD_LUCK test :1827-1831
+  __device__ __forceinline__ void add(double m1, double m2, bool on) {
+    const bool both = on && m1 > 0 && m2 > 0;
+    p1 *= both ? m1 : 1.0;
+    p2 *= both ? m2 : 1.0;
+    renorm(p1, e1);
+    renorm(p2, e2);
+    if (on && m2 == 0) zero = 1;
+    // running log-likelihood > 0  <=>  prod m2 > prod m1
+    const bool pos = e2 > e1 || (e2 == e1 && p2 > p1);
+    if (on && (m1 <= 0 || m2 <= 0 || (pos && !zero))) bad = 1;
+  }
+  __device__ __forceinline__ double value() const {
+    if (zero) return -DBL_MAX;
+    return (log(p2) - log(p1)) + (double)(e2 - e1) * 0.693147180559945309417232121458;
+  }
+};
+
+__device__ __forceinline__ double quad_sum_full(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
 // ---------------------------------------------------------------- forward ---
 // alpha_t = normalise((alpha_{t-1} . A) * lambda_t); log-likelihood terms m1/m2.
-// Per step and warp: 2*NT*NT DMMAs, the same number of 8-byte shared loads, one
-// evidence-row gather (issued before the MMA loop, consumed after it) and one
-// alpha-row store.  The next step's evidence index is prefetched a step ahead so
-// that no dependent global load sits on the critical path.
+// The loop body is one branch-free block.  On the recurrence's critical path are
+// only the MMA sweep, the multiply by the evidence row, one quad reduction, one
+// reciprocal and the scaling.  Everything else of slice t-1 (alpha store,
+// filtered output, m1 = alpha_{t-1} . R1, likelihood bookkeeping) and the
+// prefetches for slice t+1 are issued inside the sweep of slice t.
 template <int NT>
-__global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev B, int want_ll,
-                                                       double* __restrict__ alpha,
-                                                       double* __restrict__ post, int post_stride,
-                                                       int post_off, double* ll_out,
-                                                       int* status_out) {
+__global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatchDev B, int want_ll,
+                                                          double* __restrict__ alpha,
+                                                          double* __restrict__ post, int post_stride,
+                                                          int post_off, double* ll_out,
+                                                          int* status_out) {
   constexpr int SP = 8 * NT;
   extern __shared__ double sB[];
-  double* s_lam0 = sB + SP * SP;
-  double* s_phi0 = s_lam0 + SP;
+  double* s_r1 = sB + SP * SP;
   for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) sB[i] = C.Bf1[i];
-  for (int i = threadIdx.x; i < SP; i += blockDim.x) { s_lam0[i] = C.lam0[i]; s_phi0[i] = C.phi0[i]; }
+  for (int i = threadIdx.x; i < SP; i += blockDim.x) s_r1[i] = C.R1[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -173,66 +241,51 @@ __global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev
   const int orig = valid ? B.order[bp] : 0;
   const long long row0 = valid ? B.row_off[orig] : 0;
   const int* cfg = B.cfg + row0;
+  const double* frag = sB + (NT >= 2 ? 2 * lane : lane);
+  const bool vec_post = post && ((post_stride | post_off) & 1) == 0 && C.S == SP;
+  double r1[NT][2];
+#pragma unroll
+  for (int n = 0; n < NT; n++) { r1[n][0] = s_r1[8 * n + 2 * q]; r1[n][1] = s_r1[8 * n + 2 * q + 1]; }
+
   double own[NT][2], acc[NT][2], lam[NT][2];
+  LogAcc L;
+  auto load_lam = [&](int c, bool on) {
+    const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c * SP);
 #pragma unroll
-  for (int n = 0; n < NT; n++) own[n][0] = own[n][1] = lam[n][0] = lam[n][1] = 0.0;
-  double ll = 0;
-  int bad = 0;
-  int c_next = T > 0 ? cfg[0] : 0;
-  for (int t = 0; t < Tw; t++) {
-    const bool active = t < T;
-    const int c_cur = c_next;
-    if (active) {  // evidence row of this slice: in flight during the MMA loop
-      const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c_cur * SP);
-#pragma unroll
-      for (int n = 0; n < NT; n++) {
-        const double2 v = __ldg(p + 4 * n + q);
-        lam[n][0] = v.x;
-        lam[n][1] = v.y;
-      }
+    for (int n = 0; n < NT; n++) {
+      const double2 v = on ? __ldg(p + 4 * n + q) : make_double2(0.0, 0.0);
+      lam[n][0] = v.x;
+      lam[n][1] = v.y;
     }
-    if (t + 1 < T) c_next = __ldg(cfg + t + 1);
-    if (t == 0) {
+  };
+  // critical path of a slice: acc (= alpha_{t-1}.A) -> alpha_t in `own`; returns m2
+  auto finish = [&]() {
+    double s0 = 0, s1 = 0;
 #pragma unroll
-      for (int n = 0; n < NT; n++) {
-        acc[n][0] = s_phi0[8 * n + 2 * q];
-        acc[n][1] = s_phi0[8 * n + 2 * q + 1];
-      }
-    } else {
-#pragma unroll
-      for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
-#pragma unroll
-      for (int j = 0; j < NT; j++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const double a = own[j][e];
-          const double* brow = sB + (((j * 2 + e) * NT) << 5) + lane;
-#pragma unroll
-          for (int n = 0; n < NT; n++) dmma(acc[n][0], acc[n][1], a, brow[n << 5]);
-        }
+    for (int n = 0; n < NT; n++) {
+      acc[n][0] *= lam[n][0];
+      acc[n][1] *= lam[n][1];
+      s0 += acc[n][0];
+      s1 += acc[n][1];
     }
-    if (active) {
-      double m1 = 0, m2 = 0;
+    const double m2 = quad_sum_full(s0 + s1);
+    const double inv = m2 != 0 ? 1.0 / m2 : 1.0;  // zero vector stays zero (nip_normalise_array)
 #pragma unroll
-      for (int n = 0; n < NT; n++) {
-        if (want_ll) m1 += acc[n][0] * s_lam0[8 * n + 2 * q] + acc[n][1] * s_lam0[8 * n + 2 * q + 1];
-        acc[n][0] *= lam[n][0];
-        acc[n][1] *= lam[n][1];
-        m2 += acc[n][0] + acc[n][1];
-      }
-      m2 = quad_sum(m2);
-      if (want_ll) m1 = quad_sum(m1);
-      const double inv = m2 != 0 ? 1.0 / m2 : 1.0;  // zero vector stays zero (nip_normalise_array)
-      const long long row = row0 + t;
-      double2* arow = reinterpret_cast<double2*>(alpha + row * SP);
+    for (int n = 0; n < NT; n++) { own[n][0] = acc[n][0] * inv; own[n][1] = acc[n][1] * inv; }
+    return m2;
+  };
+  // off the critical path: results of slice t (alpha_t in `own`)
+  auto emit = [&](int t, bool on) {
+    if (!on) return;
+    double2* arow = reinterpret_cast<double2*>(alpha + (row0 + t) * SP);
 #pragma unroll
-      for (int n = 0; n < NT; n++) {
-        own[n][0] = acc[n][0] * inv;
-        own[n][1] = acc[n][1] * inv;
-        arow[4 * n + q] = make_double2(own[n][0], own[n][1]);
-      }
-      if (post) {  // filtering: the forward marginal of I_t is alpha_t itself
-        double* prow = post + row * post_stride + post_off;
+    for (int n = 0; n < NT; n++) arow[4 * n + q] = make_double2(own[n][0], own[n][1]);
+    if (post) {  // filtering: the forward marginal of I_t is alpha_t itself
+      double* prow = post + (row0 + t) * post_stride + post_off;
+      if (vec_post) {
+#pragma unroll
+        for (int n = 0; n < NT; n++) reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(own[n][0], own[n][1]);
+      } else {
 #pragma unroll
         for (int n = 0; n < NT; n++) {
           const int c = 8 * n + 2 * q;
@@ -240,18 +293,46 @@ __global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev
           if (c + 1 < C.S) prow[c + 1] = own[n][1];
         }
       }
-      if (want_ll) {  // src/nip.c:1458-1474, BAD_LUCK test :1827-1831
-        // a slice without any evidence has m2 == m1 by definition; do not let rounding decide
-        const double m2l = (c_cur == C.c_miss) ? m1 : m2;
-        if (m1 > 0 && m2l > 0) ll += log(m2l) - log(m1);
-        if (m2l == 0) ll = -DBL_MAX;
-        if (m1 <= 0 || m2l <= 0 || ll > 0) bad = 1;
-      }
     }
+  };
+
+  // ---- slice 0: alpha_0 = normalise(phi0 * lambda_0), m1 = mass of the evidence-free slice
+  int c_cur = T > 0 ? cfg[0] : 0;
+  int c_next = T > 1 ? cfg[1] : 0;
+  load_lam(c_cur, T > 0);
+#pragma unroll
+  for (int n = 0; n < NT; n++) {
+    acc[n][0] = C.phi0[8 * n + 2 * q];
+    acc[n][1] = C.phi0[8 * n + 2 * q + 1];
   }
+  double m1 = C.m1_0;
+  double m2 = finish();
+  if (want_ll) L.add(m1, c_cur == C.c_miss ? m1 : m2, T > 0);
+
+  for (int t = 1; t < Tw; t++) {
+    const bool on = t < T;          // this row still has slices
+    const bool was = t - 1 < T;     // slice t-1 existed (its results are emitted now)
+    c_cur = c_next;
+    load_lam(c_cur, on);            // evidence row of slice t: in flight during the sweep
+    if (t + 1 < T) c_next = __ldg(cfg + t + 1);
+#pragma unroll
+    for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
+    double p0 = 0, p1 = 0;
+    mma_sweep<NT>(acc, own, frag, [&](int ks) {
+      if (ks == 0) emit(t - 1, was);
+      if (want_ll && ks < NT) {     // m1_t = alpha_{t-1} . R1, spread over the first k-steps
+        p0 += own[ks][0] * r1[ks][0];
+        p1 += own[ks][1] * r1[ks][1];
+      }
+    });
+    m1 = want_ll ? quad_sum_full(p0 + p1) : 1.0;
+    m2 = finish();
+    if (want_ll) L.add(m1, c_cur == C.c_miss ? m1 : m2, on);
+  }
+  emit(Tw - 1, Tw - 1 < T && Tw >= 1);
   if (valid && q == 0) {
-    if (ll_out) ll_out[orig] = ll;
-    if (status_out) status_out[orig] = bad;
+    if (ll_out) ll_out[orig] = T > 0 ? L.value() : 0.0;
+    if (status_out) status_out[orig] = L.bad;
   }
 }
 
@@ -263,11 +344,15 @@ __global__ void __launch_bounds__(128) k_chain_forward(ChainDev C, ChainBatchDev
 // so the only per-element division of the literal schedule disappears; where
 // alpha_t is 0 the posterior is 0 whatever beta_t holds, which is the reference's
 // 0/0 -> 0 rule (src/nippotential.c:486-491).
+// Critical path per slice: r = lambda_t * beta_t, the MMA sweep, one quad
+// reduction, one reciprocal, the scaling.  The posterior of slice t
+// (alpha_t * beta_t, normalised, stored) and the prefetches of alpha_{t-1},
+// lambda_{t-1} are issued inside the sweep.
 template <int NT>
-__global__ void __launch_bounds__(128) k_chain_backward(ChainDev C, ChainBatchDev B,
-                                                        const double* __restrict__ alpha,
-                                                        double* __restrict__ post, int post_stride,
-                                                        int post_off) {
+__global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatchDev B,
+                                                           const double* __restrict__ alpha,
+                                                           double* __restrict__ post,
+                                                           int post_stride, int post_off) {
   constexpr int SP = 8 * NT;
   extern __shared__ double sB[];
   for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) sB[i] = C.Bb1[i];
@@ -281,84 +366,63 @@ __global__ void __launch_bounds__(128) k_chain_backward(ChainDev C, ChainBatchDe
   const int orig = valid ? B.order[bp] : 0;
   const long long row0 = valid ? B.row_off[orig] : 0;
   const int* cfg = B.cfg + row0;
+  const double* frag = sB + (NT >= 2 ? 2 * lane : lane);
   const bool vec_post = ((post_stride | post_off) & 1) == 0 && C.S == SP;
-  double beta[NT][2], r[NT][2], lamn[NT][2], a[NT][2], u[NT][2];
-#pragma unroll
-  for (int n = 0; n < NT; n++)
-    beta[n][0] = beta[n][1] = r[n][0] = r[n][1] = lamn[n][0] = lamn[n][1] = u[n][0] = u[n][1] = 0.0;
-  // prologue: evidence row of the last slice, evidence index of the one before
-  int c_pre = 0;
-  if (Tw - 1 < T && Tw >= 1) {
-    const int c = cfg[Tw - 1];
-    const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c * SP);
+  double beta[NT][2], r[NT][2], lamn[NT][2], a[NT][2], an[NT][2], u[NT][2];
+  auto load_row = [&](const double* base, bool on, double (&dst)[NT][2]) {
+    const double2* p = reinterpret_cast<const double2*>(base);
 #pragma unroll
     for (int n = 0; n < NT; n++) {
-      const double2 v = __ldg(p + 4 * n + q);
-      lamn[n][0] = v.x;
-      lamn[n][1] = v.y;
+      const double2 v = on ? __ldg(p + 4 * n + q) : make_double2(0.0, 0.0);
+      dst[n][0] = v.x;
+      dst[n][1] = v.y;
     }
-  }
-  if (Tw - 2 < T && Tw >= 2) c_pre = cfg[Tw - 2];
+  };
+  // prologue: alpha and evidence row of the last slice, evidence index of the one before
+#pragma unroll
+  for (int n = 0; n < NT; n++) beta[n][0] = beta[n][1] = 1.0;
+  const bool has_last = Tw >= 1 && Tw - 1 < T;
+  load_row(C.lam_comb + (long long)(has_last ? cfg[Tw - 1] : 0) * SP, has_last, lamn);
+  load_row(alpha + (row0 + Tw - 1) * SP, has_last, an);
+  int c_pre = (Tw >= 2 && Tw - 2 < T) ? cfg[Tw - 2] : 0;
+
   for (int t = Tw - 1; t >= 0; t--) {
-    const bool active = t < T;
-    if (active) {
-      const double2* arow = reinterpret_cast<const double2*>(alpha + (row0 + t) * SP);
+    const bool on = t < T;
+    const bool first = t == T - 1;          // beta_{T-1} = 1
+    const bool pre = t >= 1 && t - 1 < T;   // slice t-1 exists for this row
 #pragma unroll
-      for (int n = 0; n < NT; n++) {  // alpha_t: consumed after the MMA loop
-        const double2 v = __ldg(arow + 4 * n + q);
-        a[n][0] = v.x;
-        a[n][1] = v.y;
-      }
-      const bool first = t == T - 1;  // beta_{T-1} = 1
-#pragma unroll
-      for (int n = 0; n < NT; n++) {
-        if (first) beta[n][0] = beta[n][1] = 1.0;
-        r[n][0] = lamn[n][0] * beta[n][0];
-        r[n][1] = lamn[n][1] * beta[n][1];
-      }
+    for (int n = 0; n < NT; n++) {
+      beta[n][0] = first ? 1.0 : beta[n][0];
+      beta[n][1] = first ? 1.0 : beta[n][1];
+      r[n][0] = lamn[n][0] * beta[n][0];
+      r[n][1] = lamn[n][1] * beta[n][1];
+      a[n][0] = an[n][0];
+      a[n][1] = an[n][1];
+      u[n][0] = u[n][1] = 0.0;
     }
-    if (t - 1 < T && t >= 1) {  // evidence row of slice t-1 (its index arrived a step ago)
-      const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c_pre * SP);
-#pragma unroll
-      for (int n = 0; n < NT; n++) {
-        const double2 v = __ldg(p + 4 * n + q);
-        lamn[n][0] = v.x;
-        lamn[n][1] = v.y;
-      }
-    }
-    if (t - 2 < T && t >= 2) c_pre = __ldg(cfg + t - 2);
-    if (t > 0) {  // u = r . A^T   (k = current state, n = previous state)
-#pragma unroll
-      for (int n = 0; n < NT; n++) u[n][0] = u[n][1] = 0.0;
-#pragma unroll
-      for (int j = 0; j < NT; j++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const double av = r[j][e];
-          const double* brow = sB + (((j * 2 + e) * NT) << 5) + lane;
-#pragma unroll
-          for (int n = 0; n < NT; n++) dmma(u[n][0], u[n][1], av, brow[n << 5]);
-        }
-    }
-    if (active) {
-      double ps = 0, us = 0;
+    // prefetches for slice t-1 (consumed in the next iteration)
+    load_row(C.lam_comb + (long long)c_pre * SP, pre, lamn);
+    load_row(alpha + (row0 + t - 1) * SP, pre, an);
+    if (t >= 2 && t - 2 < T) c_pre = __ldg(cfg + t - 2);
+    auto side = [&](int ks) {
+      if (ks != 0) return;
+      // posterior of slice t: normalise(alpha_t * beta_t)
+      double s0 = 0, s1 = 0;
 #pragma unroll
       for (int n = 0; n < NT; n++) {
         a[n][0] *= beta[n][0];
         a[n][1] *= beta[n][1];
-        ps += a[n][0] + a[n][1];
-        us += u[n][0] + u[n][1];
+        s0 += a[n][0];
+        s1 += a[n][1];
       }
-      ps = quad_sum(ps);
-      us = quad_sum(us);
+      const double ps = quad_sum_full(s0 + s1);
       const double pinv = ps != 0 ? 1.0 / ps : 1.0;
-      const double uinv = us != 0 ? 1.0 / us : 1.0;
-      if (post) {
+      if (post && on) {
         double* prow = post + (row0 + t) * post_stride + post_off;
         if (vec_post) {
-          double2* p2 = reinterpret_cast<double2*>(prow);
 #pragma unroll
-          for (int n = 0; n < NT; n++) p2[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
+          for (int n = 0; n < NT; n++)
+            reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
         } else {
 #pragma unroll
           for (int n = 0; n < NT; n++) {
@@ -368,13 +432,18 @@ __global__ void __launch_bounds__(128) k_chain_backward(ChainDev C, ChainBatchDe
           }
         }
       }
-      if (t > 0) {
+    };
+    if (t > 0) {  // u = r . A^T   (k = current state, n = previous state)
+      mma_sweep<NT>(u, r, frag, side);
+      double s0 = 0, s1 = 0;
 #pragma unroll
-        for (int n = 0; n < NT; n++) {
-          beta[n][0] = u[n][0] * uinv;
-          beta[n][1] = u[n][1] * uinv;
-        }
-      }
+      for (int n = 0; n < NT; n++) { s0 += u[n][0]; s1 += u[n][1]; }
+      const double us = quad_sum_full(s0 + s1);
+      const double uinv = us != 0 ? 1.0 / us : 1.0;
+#pragma unroll
+      for (int n = 0; n < NT; n++) { beta[n][0] = u[n][0] * uinv; beta[n][1] = u[n][1] * uinv; }
+    } else {
+      side(0);
     }
   }
 }
@@ -523,6 +592,7 @@ int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st)
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_Bb0, sp2 * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_phi0, cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_lam0, cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_R1, cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_lam, std::max<long long>(cm.lam_total, 1) * sizeof(double)));
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_lam, 0, std::max<long long>(cm.lam_total, 1) * sizeof(double), st));
   // pseudo leaves never change: Lambda[o][ip] = [state(ip) == o], Lambda[card][ip] = 1
@@ -541,9 +611,14 @@ int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st)
 }
 
 int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, const double* d_base1,
-                  const std::vector<int>& tab_off, const int* d_ipool,
-                  cudaStream_t st) {
+                  const std::vector<int>& tab_off, const int* d_ipool, const double* d_R1,
+                  const double* d_m10, cudaStream_t st) {
   if (!cm.ok) return NIPGPU_OK;
+  // mass of the evidence-free slice per previous interface state / of the first slice
+  // (k_jt_calibrate): m1_t = alpha_{t-1} . R1
+  NIPGPU_CUDA(cudaMemsetAsync(cm.d_R1, 0, cm.SP * sizeof(double), st));
+  NIPGPU_CUDA(cudaMemcpyAsync(cm.d_R1, d_R1, cm.S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  NIPGPU_CUDA(cudaMemcpyAsync(&cm.m1_0, d_m10, sizeof(double), cudaMemcpyDeviceToHost, st));
   const size_t sp2 = (size_t)cm.SP * cm.SP;
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_Bf1, 0, sp2 * sizeof(double), st));
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_Bb1, 0, sp2 * sizeof(double), st));
@@ -588,7 +663,7 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
 
 void chain_free(ChainModel& cm) {
   cudaFree(cm.d_ent_of); cudaFree(cm.d_Bf1); cudaFree(cm.d_Bb1); cudaFree(cm.d_Bb0);
-  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta);
+  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_R1);
   cm = ChainModel();
 }
 
@@ -719,7 +794,7 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   ChainDev C;
   C.S = cm.S; C.SP = cm.SP; C.c_miss = plan.c_miss;
   C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
-  C.lam_comb = cb.d_comb;
+  C.R1 = cm.d_R1; C.m1_0 = cm.m1_0; C.lam_comb = cb.d_comb;
   if (a.n_series == 0) return NIPGPU_OK;
   if (ev0) NIPGPU_CUDA(cudaEventRecord(ev0, st));
   int e = NIPGPU_OK;

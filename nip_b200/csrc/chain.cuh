@@ -44,7 +44,8 @@ struct ChainModel {
   // device
   int* d_ent_of = nullptr;
   double *d_Bf1 = nullptr, *d_Bb1 = nullptr, *d_Bb0 = nullptr;  // fragment-ordered SPxSP
-  double *d_phi0 = nullptr, *d_lam0 = nullptr;                  // [SP]
+  double *d_phi0 = nullptr, *d_lam0 = nullptr, *d_R1 = nullptr; // [SP]
+  double m1_0 = 1.0;           // mass of the evidence-free first slice
   double* d_lam = nullptr;     // all Lambda tables
   long long lam_total = 0;
   int* d_leaf_meta = nullptr;  // flattened per-leaf metadata for the refresh kernel
@@ -83,8 +84,8 @@ std::string chain_build(HostModel& hm, ChainModel& cm);
 int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st);
 // recompute Bf1/Bb1/Bb0/phi0/lam0/Lambda from the base tables (after any parameter change)
 int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, const double* d_base1,
-                  const std::vector<int>& tab_off, const int* d_ipool,
-                  cudaStream_t st);
+                  const std::vector<int>& tab_off, const int* d_ipool, const double* d_R1,
+                  const double* d_m10, cudaStream_t st);
 void chain_free(ChainModel& cm);
 
 struct ChainInferArgs {

@@ -104,3 +104,56 @@ extern "C" int nipgpu_probe_peaks(int device, double* dmma_tflops, double* dfma_
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return NIPGPU_OK;
 }
+
+// ---- development probe: DMMA issue/latency behaviour of ONE warp per SM sub-partition.
+// out[0] = clocks per DMMA with `chains` independent accumulators issued round-robin.
+namespace nipgpu {
+namespace {
+template <int CH>
+__global__ void k_probe_dmma_chain(double* out, long long* clk, int iters) {
+  double c[CH][2];
+#pragma unroll
+  for (int i = 0; i < CH; i++) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i * 1e-9; }
+  const double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CH; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  const long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = t1 - t0;
+}
+}  // namespace
+}  // namespace nipgpu
+
+extern "C" int nipgpu_probe_dmma_chain(int chains, int warps_per_block, int blocks, double* clocks_per_dmma) {
+  using namespace nipgpu;
+  double* d = nullptr;
+  long long* c = nullptr;
+  NIPGPU_CUDA(cudaMalloc((void**)&d, 64));
+  NIPGPU_CUDA(cudaMalloc((void**)&c, 64));
+  const int iters = 4096;
+  for (int rep = 0; rep < 2; rep++) {
+    switch (chains) {
+      case 1: k_probe_dmma_chain<1><<<blocks, 32 * warps_per_block>>>(d, c, iters); break;
+      case 2: k_probe_dmma_chain<2><<<blocks, 32 * warps_per_block>>>(d, c, iters); break;
+      case 4: k_probe_dmma_chain<4><<<blocks, 32 * warps_per_block>>>(d, c, iters); break;
+      case 8: k_probe_dmma_chain<8><<<blocks, 32 * warps_per_block>>>(d, c, iters); break;
+      case 16: k_probe_dmma_chain<16><<<blocks, 32 * warps_per_block>>>(d, c, iters); break;
+      default: return NIPGPU_EINVAL;
+    }
+    NIPGPU_LAUNCHED();
+    NIPGPU_CUDA(cudaDeviceSynchronize());
+  }
+  long long h = 0;
+  NIPGPU_CUDA(cudaMemcpy(&h, c, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaFree(c);
+  if (clocks_per_dmma) *clocks_per_dmma = (double)h / ((double)iters * chains);
+  return NIPGPU_OK;
+}
