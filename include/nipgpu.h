@@ -190,12 +190,16 @@ int nipgpu_likelihood(nipgpu_model* m, nipgpu_batch* b, const uint8_t* evidence_
  * slices by hand (util/nipjoint.c, test/hmmtest.c). */
 int nipgpu_slice_reset(nipgpu_model* m);
 int nipgpu_slice_use_priors(nipgpu_model* m, int has_history);
+/* mark the prior of one parentless variable as entered (what use_priors does per variable) */
+int nipgpu_slice_enter_prior(nipgpu_model* m, int32_t var);
 int nipgpu_slice_enter_evidence(nipgpu_model* m, int32_t var, const double* likelihood);
 int nipgpu_slice_make_consistent(nipgpu_model* m);
 int nipgpu_slice_mass(nipgpu_model* m, double* mass);
 int nipgpu_slice_marginal(nipgpu_model* m, int32_t var, double* out /*[card]*/);
 /* D2H copy of a clique's current belief table (clique->p) */
 int nipgpu_slice_get_clique(nipgpu_model* m, int32_t clique, double* out);
+/* D2H copy of a sepset's current potential (sepset->new), sepsets numbered as in the description */
+int nipgpu_slice_get_sepset(nipgpu_model* m, int32_t sepset, double* out);
 
 /* ---- instrumentation -------------------------------------------------- */
 /* number of kernels this library launched since the counter was last reset */

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "nipgpu_batch_create", "nipgpu_batch_destroy", "nipgpu_batch_update", "nipgpu_infer", "nipgpu_infer_device",
     "nipgpu_em_estep", "nipgpu_model_counts_size", "nipgpu_model_counts_offsets",
     "nipgpu_em_counts_device", "nipgpu_em_mstep", "nipgpu_likelihood", "nipgpu_slice_reset",
-    "nipgpu_slice_use_priors", "nipgpu_slice_enter_evidence", "nipgpu_slice_make_consistent",
+    "nipgpu_slice_use_priors", "nipgpu_slice_enter_prior", "nipgpu_slice_enter_evidence", "nipgpu_slice_get_sepset", "nipgpu_slice_make_consistent",
     "nipgpu_slice_mass", "nipgpu_slice_marginal", "nipgpu_slice_get_clique",
     "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_model_stream", "nipgpu_probe_peaks",
 ]
@@ -76,6 +76,8 @@ def load_library(path=LIB_PATH):
     L.nipgpu_slice_reset.argtypes = [_vp]
     L.nipgpu_slice_use_priors.argtypes = [_vp, _i]
     L.nipgpu_slice_enter_evidence.argtypes = [_vp, _i, _vp]
+    L.nipgpu_slice_enter_prior.argtypes = [_vp, _i]
+    L.nipgpu_slice_get_sepset.argtypes = [_vp, _i, _vp]
     L.nipgpu_slice_make_consistent.argtypes = [_vp]
     L.nipgpu_slice_mass.argtypes = [_vp, C.POINTER(_d)]
     L.nipgpu_slice_marginal.argtypes = [_vp, _i, _vp]

@@ -583,6 +583,21 @@ int nipgpu_slice_use_priors(nipgpu_model* m, int has_history) {
   return NIPGPU_OK;
 }
 
+int nipgpu_slice_enter_prior(nipgpu_model* m, int32_t var) {
+  if (!m || var < 0 || var >= m->hm.nv || m->hm.nparents(var) != 0) return fail(NIPGPU_EINVAL, "bad arguments");
+  m->prior_entered[var] = 1;
+  m->slice_consistent = false;
+  return NIPGPU_OK;
+}
+
+int nipgpu_slice_get_sepset(nipgpu_model* m, int32_t sepset, double* out) {
+  if (!m || sepset < 0 || sepset >= m->hm.ns || !out) return fail(NIPGPU_EINVAL, "bad arguments");
+  if (!m->slice_consistent) return fail(NIPGPU_EINVAL, "call nipgpu_slice_make_consistent first");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  NIPGPU_CUDA(cudaMemcpy(out, m->d_slice_msg + m->hm.sep_slot[sepset], (size_t)m->hm.ssize[sepset] * sizeof(double), cudaMemcpyDeviceToHost));
+  return NIPGPU_OK;
+}
+
 int nipgpu_slice_enter_evidence(nipgpu_model* m, int32_t var, const double* likelihood) {
   if (!m || var < 0 || var >= m->hm.nv || !likelihood) return fail(NIPGPU_EINVAL, "bad arguments");
   // nip_enter_evidence replaces the old likelihood by the new one (old is divided out,

@@ -41,7 +41,7 @@ __host__ __device__ inline int frag_index(int kstate, int nstate, int NT) {
 struct ChainDev {
   int S, SP, c_miss;   // c_miss: combined evidence index meaning "no evidence in this slice"
   double m1_0;         // mass of the evidence-free first slice
-  const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *R1, *lam_comb;
+  const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *R1, *colsum, *lam_comb;
 };
 
 struct ChainBatchDev {
@@ -189,7 +189,8 @@ struct LogAcc {
     e += ex;
     p = __hiloint2double(hi - (ex << 20), __double2loint(p));
   }
-  // semantics of src/nip.c:1458-1474 and of the BAD_LUCK test :1827-1831
+  // semantics of src/nip.c:1458-1474 and of the BAD_LUCK test :1827-1831; m1 and m2 may
+  // carry a common positive factor (only their ratio enters the sum)
   __device__ __forceinline__ void add(double m1, double m2, bool on) {
     const bool both = on && m1 > 0 && m2 > 0;
     p1 *= both ? m1 : 1.0;
@@ -197,8 +198,7 @@ struct LogAcc {
     renorm(p1, e1);
     renorm(p2, e2);
     if (on && m2 == 0) zero = 1;
-    // running log-likelihood > 0  <=>  prod m2 > prod m1
-    const bool pos = e2 > e1 || (e2 == e1 && p2 > p1);
+    const bool pos = e2 > e1 || (e2 == e1 && p2 > p1);  // running log-likelihood > 0
     if (on && (m1 <= 0 || m2 <= 0 || (pos && !zero))) bad = 1;
   }
   __device__ __forceinline__ double value() const {
@@ -207,21 +207,38 @@ struct LogAcc {
   }
 };
 
+// 16-byte read-only global load that ptxas may not sink towards its use: it has to be
+// issued where it is written (before / early in a sweep) to have its latency hidden.
+__device__ __forceinline__ double2 ldg_pinned(const double2* p, bool on) {
+  double2 v = make_double2(0.0, 0.0);
+  if (on) asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ double quad_sum_full(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
   return v;
 }
 
+__device__ __forceinline__ double safe_rcp(double x) { return x != 0 ? 1.0 / x : 1.0; }
+
 // ---------------------------------------------------------------- forward ---
-// alpha_t = normalise((alpha_{t-1} . A) * lambda_t); log-likelihood terms m1/m2.
-// The loop body is one branch-free block.  On the recurrence's critical path are
-// only the MMA sweep, the multiply by the evidence row, one quad reduction, one
-// reciprocal and the scaling.  Everything else of slice t-1 (alpha store,
-// filtered output, m1 = alpha_{t-1} . R1, likelihood bookkeeping) and the
-// prefetches for slice t+1 are issued inside the sweep of slice t.
-template <int NT>
-__global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatchDev B, int want_ll,
+// alpha_t = normalise((alpha_{t-1} . A) * lambda_t) and the likelihood terms.
+//
+// The recurrence is sequential in t and a warp is alone on its scheduler, so
+// everything between two MMA sweeps is exposed latency.  Only ONE multiply per
+// element is left there: the vector carried from slice to slice is
+//     own_t = (own_{t-1} . A) * lambda_t * g_t
+// where g_t is a scale factor computed DURING sweep t from own_{t-1} alone
+// (g_t = 1 / (c_{t-1} m2_{t-1}), c = sum of own), so own stays O(1) without a
+// reduction on the critical path.  alpha_t is own_t up to the scale c_t; the
+// exact masses follow one slice later, inside the next sweep's issue gaps:
+//     m2_t = c_t / (c_{t-1} g_t),      m1_t = (own_{t-1} . R1) / c_{t-1}.
+// The alpha rows stored for the backward pass keep the scale c_t (the backward
+// pass normalises every posterior by its own sum, as the reference does).
+template <int NT, bool FILT, bool WLL>
+__global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatchDev B,
                                                           double* __restrict__ alpha,
                                                           double* __restrict__ post, int post_stride,
                                                           int post_off, double* ll_out,
@@ -242,10 +259,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
   const long long row0 = valid ? B.row_off[orig] : 0;
   const int* cfg = B.cfg + row0;
   const double* frag = sB + (NT >= 2 ? 2 * lane : lane);
-  const bool vec_post = post && ((post_stride | post_off) & 1) == 0 && C.S == SP;
-  double r1[NT][2];
-#pragma unroll
-  for (int n = 0; n < NT; n++) { r1[n][0] = s_r1[8 * n + 2 * q]; r1[n][1] = s_r1[8 * n + 2 * q + 1]; }
+  const double2* r1v = reinterpret_cast<const double2*>(s_r1);
 
   double own[NT][2], acc[NT][2], lam[NT][2];
   LogAcc L;
@@ -253,85 +267,103 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
     const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c * SP);
 #pragma unroll
     for (int n = 0; n < NT; n++) {
-      const double2 v = on ? __ldg(p + 4 * n + q) : make_double2(0.0, 0.0);
+      const double2 v = ldg_pinned(p + 4 * n + q, on);
       lam[n][0] = v.x;
       lam[n][1] = v.y;
     }
   };
-  // critical path of a slice: acc (= alpha_{t-1}.A) -> alpha_t in `own`; returns m2
-  auto finish = [&]() {
+  // what is still owed for the slice whose vector sits in `own`
+  double K = 0;          // m2 of that slice = (sum of own) * K
+  double Pp = 0;         // its m1 numerator (already times c of the slice before)
+  double cp = 1.0;       // c of the slice before it
+  bool noev_p = false, on_p = false;
+  double gscale = 1.0;   // g_t for the sweep in progress
+
+  // books of slice s (vector in `own`): masses, likelihood, outputs; returns c_s
+  auto settle = [&](int s, double& m2s) {
     double s0 = 0, s1 = 0;
 #pragma unroll
-    for (int n = 0; n < NT; n++) {
-      acc[n][0] *= lam[n][0];
-      acc[n][1] *= lam[n][1];
-      s0 += acc[n][0];
-      s1 += acc[n][1];
+    for (int n = 0; n < NT; n++) { s0 += own[n][0]; s1 += own[n][1]; }
+    const double c = quad_sum_full(s0 + s1);
+    m2s = c * K;
+    if (WLL) L.add(Pp, noev_p ? Pp : m2s * cp, on_p);
+    if (on_p) {
+      double2* arow = reinterpret_cast<double2*>(alpha + (row0 + s) * SP);
+#pragma unroll
+      for (int n = 0; n < NT; n++) arow[4 * n + q] = make_double2(own[n][0], own[n][1]);
     }
-    const double m2 = quad_sum_full(s0 + s1);
-    const double inv = m2 != 0 ? 1.0 / m2 : 1.0;  // zero vector stays zero (nip_normalise_array)
+    if (FILT) {  // filtering: the forward marginal of I_s is alpha_s = own / c
+      const double cinv = safe_rcp(c);
+      double* prow = post + (row0 + s) * post_stride + post_off;
 #pragma unroll
-    for (int n = 0; n < NT; n++) { own[n][0] = acc[n][0] * inv; own[n][1] = acc[n][1] * inv; }
-    return m2;
-  };
-  // off the critical path: results of slice t (alpha_t in `own`)
-  auto emit = [&](int t, bool on) {
-    if (!on) return;
-    double2* arow = reinterpret_cast<double2*>(alpha + (row0 + t) * SP);
-#pragma unroll
-    for (int n = 0; n < NT; n++) arow[4 * n + q] = make_double2(own[n][0], own[n][1]);
-    if (post) {  // filtering: the forward marginal of I_t is alpha_t itself
-      double* prow = post + (row0 + t) * post_stride + post_off;
-      if (vec_post) {
-#pragma unroll
-        for (int n = 0; n < NT; n++) reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(own[n][0], own[n][1]);
-      } else {
-#pragma unroll
-        for (int n = 0; n < NT; n++) {
-          const int c = 8 * n + 2 * q;
-          if (c < C.S) prow[c] = own[n][0];
-          if (c + 1 < C.S) prow[c + 1] = own[n][1];
-        }
+      for (int n = 0; n < NT; n++) {
+        const int col = 8 * n + 2 * q;
+        if (on_p && col < C.S) prow[col] = own[n][0] * cinv;
+        if (on_p && col + 1 < C.S) prow[col + 1] = own[n][1] * cinv;
       }
     }
+    return c;
   };
 
-  // ---- slice 0: alpha_0 = normalise(phi0 * lambda_0), m1 = mass of the evidence-free slice
+  // ---- slice 0: own_0 = phi0 * lambda_0 / S0 (c_0 = 1), m1_0 = mass of the evidence-free slice
   int c_cur = T > 0 ? cfg[0] : 0;
   int c_next = T > 1 ? cfg[1] : 0;
   load_lam(c_cur, T > 0);
+  {
+    double s0 = 0, s1 = 0;
 #pragma unroll
-  for (int n = 0; n < NT; n++) {
-    acc[n][0] = C.phi0[8 * n + 2 * q];
-    acc[n][1] = C.phi0[8 * n + 2 * q + 1];
+    for (int n = 0; n < NT; n++) {
+      acc[n][0] = C.phi0[8 * n + 2 * q] * lam[n][0];
+      acc[n][1] = C.phi0[8 * n + 2 * q + 1] * lam[n][1];
+      s0 += acc[n][0];
+      s1 += acc[n][1];
+    }
+    const double S0 = quad_sum_full(s0 + s1);
+    const double inv = safe_rcp(S0);
+#pragma unroll
+    for (int n = 0; n < NT; n++) { own[n][0] = acc[n][0] * inv; own[n][1] = acc[n][1] * inv; }
+    K = S0; Pp = C.m1_0; cp = 1.0; noev_p = c_cur == C.c_miss; on_p = T > 0;
   }
-  double m1 = C.m1_0;
-  double m2 = finish();
-  if (want_ll) L.add(m1, c_cur == C.c_miss ? m1 : m2, T > 0);
 
   for (int t = 1; t < Tw; t++) {
-    const bool on = t < T;          // this row still has slices
-    const bool was = t - 1 < T;     // slice t-1 existed (its results are emitted now)
+    const bool on = t < T;
     c_cur = c_next;
     load_lam(c_cur, on);            // evidence row of slice t: in flight during the sweep
     if (t + 1 < T) c_next = __ldg(cfg + t + 1);
 #pragma unroll
     for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
-    double p0 = 0, p1 = 0;
+    double d0 = 0, d1 = 0, m2p = 0, c = 0;
     mma_sweep<NT>(acc, own, frag, [&](int ks) {
-      if (ks == 0) emit(t - 1, was);
-      if (want_ll && ks < NT) {     // m1_t = alpha_{t-1} . R1, spread over the first k-steps
-        p0 += own[ks][0] * r1[ks][0];
-        p1 += own[ks][1] * r1[ks][1];
+      if (ks == 0) {
+        c = settle(t - 1, m2p);
+        if (WLL) {                  // m1 numerator of slice t: own_{t-1} . R1
+#pragma unroll
+          for (int n = 0; n < NT; n++) {
+            const double2 v = r1v[4 * n + q];
+            d0 += own[n][0] * v.x;
+            d1 += own[n][1] * v.y;
+          }
+        }
+      }
+      if (ks == 2 * NT - 1) {       // scale of this slice; fold it into the evidence row
+        const double den = c * m2p;
+        gscale = safe_rcp(den);
+        K = den != 0 ? m2p : 0.0;
+#pragma unroll
+        for (int n = 0; n < NT; n++) { lam[n][0] *= gscale; lam[n][1] *= gscale; }
       }
     });
-    m1 = want_ll ? quad_sum_full(p0 + p1) : 1.0;
-    m2 = finish();
-    if (want_ll) L.add(m1, c_cur == C.c_miss ? m1 : m2, on);
+    if (WLL) Pp = quad_sum_full(d0 + d1);
+    cp = c; noev_p = c_cur == C.c_miss; on_p = on;
+#pragma unroll
+    for (int n = 0; n < NT; n++) { own[n][0] = acc[n][0] * lam[n][0]; own[n][1] = acc[n][1] * lam[n][1]; }
   }
-  emit(Tw - 1, Tw - 1 < T && Tw >= 1);
+  {
+    double m2last;
+    settle(Tw - 1, m2last);
+  }
   if (valid && q == 0) {
-    if (ll_out) ll_out[orig] = T > 0 ? L.value() : 0.0;
+    if (ll_out) ll_out[orig] = (WLL && T > 0) ? L.value() : 0.0;
     if (status_out) status_out[orig] = L.bad;
   }
 }
@@ -341,21 +373,23 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
 // reference multiplies into out_clique, src/nip.c:1518-1529) one has
 //     beta_{t-1}  proportional to  A . (lambda_t * beta_t)
 //     P(I_t | all evidence) = normalise(alpha_t * beta_t)
-// so the only per-element division of the literal schedule disappears; where
-// alpha_t is 0 the posterior is 0 whatever beta_t holds, which is the reference's
+// so the per-element division of the literal schedule disappears; where alpha_t
+// is 0 the posterior is 0 whatever beta_t holds, which is the reference's
 // 0/0 -> 0 rule (src/nippotential.c:486-491).
-// Critical path per slice: r = lambda_t * beta_t, the MMA sweep, one quad
-// reduction, one reciprocal, the scaling.  The posterior of slice t
-// (alpha_t * beta_t, normalised, stored) and the prefetches of alpha_{t-1},
-// lambda_{t-1} are issued inside the sweep.
-template <int NT>
+// Between two sweeps only two multiplies per element remain: the scale of
+// beta_{t-1} (1 / sum of the sweep's result) is obtained during the sweep as
+// 1 / (r . colsum(A)), and the posterior of slice t, the alpha / evidence
+// prefetches and the stores all sit in the sweep's issue gaps.
+template <int NT, bool VEC>
 __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatchDev B,
                                                            const double* __restrict__ alpha,
                                                            double* __restrict__ post,
                                                            int post_stride, int post_off) {
   constexpr int SP = 8 * NT;
   extern __shared__ double sB[];
+  double* s_cs = sB + SP * SP;
   for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) sB[i] = C.Bb1[i];
+  for (int i = threadIdx.x; i < SP; i += blockDim.x) s_cs[i] = C.colsum[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -367,85 +401,86 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   const long long row0 = valid ? B.row_off[orig] : 0;
   const int* cfg = B.cfg + row0;
   const double* frag = sB + (NT >= 2 ? 2 * lane : lane);
-  const bool vec_post = ((post_stride | post_off) & 1) == 0 && C.S == SP;
-  double beta[NT][2], r[NT][2], lamn[NT][2], a[NT][2], an[NT][2], u[NT][2];
+  const double2* csv = reinterpret_cast<const double2*>(s_cs);
+  double beta[NT][2], r[NT][2], lam[NT][2], a[NT][2], u[NT][2];
   auto load_row = [&](const double* base, bool on, double (&dst)[NT][2]) {
     const double2* p = reinterpret_cast<const double2*>(base);
 #pragma unroll
     for (int n = 0; n < NT; n++) {
-      const double2 v = on ? __ldg(p + 4 * n + q) : make_double2(0.0, 0.0);
+      const double2 v = ldg_pinned(p + 4 * n + q, on);
       dst[n][0] = v.x;
       dst[n][1] = v.y;
     }
   };
-  // prologue: alpha and evidence row of the last slice, evidence index of the one before
-#pragma unroll
-  for (int n = 0; n < NT; n++) beta[n][0] = beta[n][1] = 1.0;
-  const bool has_last = Tw >= 1 && Tw - 1 < T;
-  load_row(C.lam_comb + (long long)(has_last ? cfg[Tw - 1] : 0) * SP, has_last, lamn);
-  load_row(alpha + (row0 + Tw - 1) * SP, has_last, an);
-  int c_pre = (Tw >= 2 && Tw - 2 < T) ? cfg[Tw - 2] : 0;
-
-  for (int t = Tw - 1; t >= 0; t--) {
-    const bool on = t < T;
-    const bool first = t == T - 1;          // beta_{T-1} = 1
-    const bool pre = t >= 1 && t - 1 < T;   // slice t-1 exists for this row
+  // posterior of slice t from alpha_t (in `a`) and beta_t: normalise(alpha_t * beta_t)
+  auto emit_post = [&](int t, bool on) {
+    double s0 = 0, s1 = 0;
 #pragma unroll
     for (int n = 0; n < NT; n++) {
-      beta[n][0] = first ? 1.0 : beta[n][0];
-      beta[n][1] = first ? 1.0 : beta[n][1];
-      r[n][0] = lamn[n][0] * beta[n][0];
-      r[n][1] = lamn[n][1] * beta[n][1];
-      a[n][0] = an[n][0];
-      a[n][1] = an[n][1];
-      u[n][0] = u[n][1] = 0.0;
+      a[n][0] *= beta[n][0];
+      a[n][1] *= beta[n][1];
+      s0 += a[n][0];
+      s1 += a[n][1];
     }
-    // prefetches for slice t-1 (consumed in the next iteration)
-    load_row(C.lam_comb + (long long)c_pre * SP, pre, lamn);
-    load_row(alpha + (row0 + t - 1) * SP, pre, an);
-    if (t >= 2 && t - 2 < T) c_pre = __ldg(cfg + t - 2);
-    auto side = [&](int ks) {
-      if (ks != 0) return;
-      // posterior of slice t: normalise(alpha_t * beta_t)
-      double s0 = 0, s1 = 0;
+    const double pinv = safe_rcp(quad_sum_full(s0 + s1));
+    double* prow = post + (row0 + t) * post_stride + post_off;
+    if (VEC) {
+#pragma unroll
+      for (int n = 0; n < NT; n++)
+        if (on) reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
+    } else {
 #pragma unroll
       for (int n = 0; n < NT; n++) {
-        a[n][0] *= beta[n][0];
-        a[n][1] *= beta[n][1];
-        s0 += a[n][0];
-        s1 += a[n][1];
+        const int col = 8 * n + 2 * q;
+        if (on && col < C.S) prow[col] = a[n][0] * pinv;
+        if (on && col + 1 < C.S) prow[col + 1] = a[n][1] * pinv;
       }
-      const double ps = quad_sum_full(s0 + s1);
-      const double pinv = ps != 0 ? 1.0 / ps : 1.0;
-      if (post && on) {
-        double* prow = post + (row0 + t) * post_stride + post_off;
-        if (vec_post) {
+    }
+  };
+  // prologue: the longest rows start at slice Tw-1 with beta = 1, r = lambda
+  const bool has_last = Tw >= 1 && Tw - 1 < T;
+  load_row(C.lam_comb + (long long)(has_last ? cfg[Tw - 1] : 0) * SP, has_last, r);
+  load_row(alpha + (row0 + Tw - 1) * SP, has_last, a);
 #pragma unroll
-          for (int n = 0; n < NT; n++)
-            reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
-        } else {
+  for (int n = 0; n < NT; n++) beta[n][0] = beta[n][1] = 1.0;
+  int c_pre = (Tw >= 2 && Tw - 2 < T) ? cfg[Tw - 2] : 0;
+
+  for (int t = Tw - 1; t >= 1; t--) {
+    const bool on = t < T;
+    const bool pre = t - 1 < T;             // slice t-1 exists for this row
+    const bool first_next = t - 1 == T - 1; // ... and is the row's last slice: beta = 1 there
+    load_row(C.lam_comb + (long long)c_pre * SP, pre, lam);   // lambda_{t-1}, used late in the sweep
+    if (t >= 2 && t - 2 < T) c_pre = __ldg(cfg + t - 2);
 #pragma unroll
-          for (int n = 0; n < NT; n++) {
-            const int c = 8 * n + 2 * q;
-            if (c < C.S) prow[c] = a[n][0] * pinv;
-            if (c + 1 < C.S) prow[c + 1] = a[n][1] * pinv;
-          }
+    for (int n = 0; n < NT; n++) u[n][0] = u[n][1] = 0.0;
+    double d0 = 0, d1 = 0, h = 1.0;
+    mma_sweep<NT>(u, r, frag, [&](int ks) {   // u = r . A^T  (k = current state, n = previous state)
+      if (ks == 0) {
+        emit_post(t, on);
+        load_row(alpha + (row0 + t - 1) * SP, pre, a);   // alpha_{t-1} for the next round
+#pragma unroll
+        for (int n = 0; n < NT; n++) {        // sum of the sweep's result, known in advance
+          const double2 v = csv[4 * n + q];
+          d0 += r[n][0] * v.x;
+          d1 += r[n][1] * v.y;
         }
       }
-    };
-    if (t > 0) {  // u = r . A^T   (k = current state, n = previous state)
-      mma_sweep<NT>(u, r, frag, side);
-      double s0 = 0, s1 = 0;
+      if (ks == 2 * NT - 1) {
+        h = safe_rcp(quad_sum_full(d0 + d1));
+        const double hs = first_next ? 1.0 : h;
 #pragma unroll
-      for (int n = 0; n < NT; n++) { s0 += u[n][0]; s1 += u[n][1]; }
-      const double us = quad_sum_full(s0 + s1);
-      const double uinv = us != 0 ? 1.0 / us : 1.0;
+        for (int n = 0; n < NT; n++) { lam[n][0] *= hs; lam[n][1] *= hs; }
+      }
+    });
 #pragma unroll
-      for (int n = 0; n < NT; n++) { beta[n][0] = u[n][0] * uinv; beta[n][1] = u[n][1] * uinv; }
-    } else {
-      side(0);
+    for (int n = 0; n < NT; n++) {
+      beta[n][0] = first_next ? 1.0 : u[n][0] * h;
+      beta[n][1] = first_next ? 1.0 : u[n][1] * h;
+      r[n][0] = first_next ? lam[n][0] : u[n][0] * lam[n][0];
+      r[n][1] = first_next ? lam[n][1] : u[n][1] * lam[n][1];
     }
   }
+  if (Tw >= 1) emit_post(0, 0 < T);
 }
 
 template <class K>
@@ -455,26 +490,41 @@ int set_smem(K kernel, size_t bytes) {
   return NIPGPU_OK;
 }
 
+template <int NT, bool FILT, bool WLL>
+int launch_forward_v(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
+                     cudaStream_t st) {
+  const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
+  if (int e = set_smem(k_chain_forward<NT, FILT, WLL>, smem)) return e;
+  const int grid = (B.n_series + 31) / 32;
+  k_chain_forward<NT, FILT, WLL><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                          a.post_off, a.d_ll, a.d_status);
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
 template <int NT>
 int launch_forward(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
                    cudaStream_t st) {
-  const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
-  if (int e = set_smem(k_chain_forward<NT>, smem)) return e;
-  const int grid = (B.n_series + 31) / 32;
-  k_chain_forward<NT><<<grid, 128, smem, st>>>(C, B, a.want_ll, alpha,
-                                                a.forward_only ? a.d_post : nullptr, a.post_stride,
-                                                a.post_off, a.d_ll, a.d_status);
-  NIPGPU_LAUNCHED();
-  return NIPGPU_OK;
+  const bool filt = a.forward_only && a.d_post;
+  if (filt) return a.want_ll ? launch_forward_v<NT, true, true>(C, B, a, alpha, st)
+                             : launch_forward_v<NT, true, false>(C, B, a, alpha, st);
+  return a.want_ll ? launch_forward_v<NT, false, true>(C, B, a, alpha, st)
+                   : launch_forward_v<NT, false, false>(C, B, a, alpha, st);
 }
 
 template <int NT>
 int launch_backward(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a,
                     const double* alpha, cudaStream_t st) {
   const int grid = (B.n_series + 31) / 32;
-  const size_t smem = sizeof(double) * 64 * NT * NT;
-  if (int e = set_smem(k_chain_backward<NT>, smem)) return e;
-  k_chain_backward<NT><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride, a.post_off);
+  const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
+  const bool vec = ((a.post_stride | a.post_off) & 1) == 0 && C.S == C.SP;
+  if (vec) {
+    if (int e = set_smem(k_chain_backward<NT, true>, smem)) return e;
+    k_chain_backward<NT, true><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride, a.post_off);
+  } else {
+    if (int e = set_smem(k_chain_backward<NT, false>, smem)) return e;
+    k_chain_backward<NT, false><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride, a.post_off);
+  }
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
@@ -593,6 +643,7 @@ int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st)
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_phi0, cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_lam0, cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_R1, cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cm.d_colsum, cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_lam, std::max<long long>(cm.lam_total, 1) * sizeof(double)));
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_lam, 0, std::max<long long>(cm.lam_total, 1) * sizeof(double), st));
   // pseudo leaves never change: Lambda[o][ip] = [state(ip) == o], Lambda[card][ip] = 1
@@ -630,6 +681,9 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
   NIPGPU_LAUNCHED();
   k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base0 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_phi0);
   NIPGPU_LAUNCHED();
+  NIPGPU_CUDA(cudaMemsetAsync(cm.d_colsum, 0, cm.SP * sizeof(double), st));
+  k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base1 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_colsum);
+  NIPGPU_LAUNCHED();
   std::vector<long long> miss_rows;
   for (int l = 0; l < cm.n_real; l++) {
     const ChainLeafHost& L = cm.leaves[l];
@@ -663,7 +717,7 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
 
 void chain_free(ChainModel& cm) {
   cudaFree(cm.d_ent_of); cudaFree(cm.d_Bf1); cudaFree(cm.d_Bb1); cudaFree(cm.d_Bb0);
-  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_R1);
+  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_R1); cudaFree(cm.d_colsum);
   cm = ChainModel();
 }
 
@@ -794,7 +848,7 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   ChainDev C;
   C.S = cm.S; C.SP = cm.SP; C.c_miss = plan.c_miss;
   C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
-  C.R1 = cm.d_R1; C.m1_0 = cm.m1_0; C.lam_comb = cb.d_comb;
+  C.R1 = cm.d_R1; C.colsum = cm.d_colsum; C.m1_0 = cm.m1_0; C.lam_comb = cb.d_comb;
   if (a.n_series == 0) return NIPGPU_OK;
   if (ev0) NIPGPU_CUDA(cudaEventRecord(ev0, st));
   int e = NIPGPU_OK;

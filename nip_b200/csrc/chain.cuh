@@ -44,7 +44,7 @@ struct ChainModel {
   // device
   int* d_ent_of = nullptr;
   double *d_Bf1 = nullptr, *d_Bb1 = nullptr, *d_Bb0 = nullptr;  // fragment-ordered SPxSP
-  double *d_phi0 = nullptr, *d_lam0 = nullptr, *d_R1 = nullptr; // [SP]
+  double *d_phi0 = nullptr, *d_lam0 = nullptr, *d_R1 = nullptr, *d_colsum = nullptr; // [SP]
   double m1_0 = 1.0;           // mass of the evidence-free first slice
   double* d_lam = nullptr;     // all Lambda tables
   long long lam_total = 0;

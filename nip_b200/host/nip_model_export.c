@@ -50,6 +50,24 @@ static int family_clique_of(nip_model model, nip_variable v) {
   return -1;
 }
 
+nip_sepset* nipgpu_model_sepsets(nip_model model, int* n) {
+  nip_sepset* seen;
+  nip_sepset_link l;
+  int i, j, ns = 0, cap = 0;
+  for (i = 0; i < model->num_of_cliques; i++)
+    for (l = model->cliques[i]->sepsets; l; l = l->fwd) cap++;
+  seen = (nip_sepset*)calloc((size_t)(cap > 0 ? cap : 1), sizeof(nip_sepset));
+  if (!seen) return NULL;
+  for (i = 0; i < model->num_of_cliques; i++)
+    for (l = model->cliques[i]->sepsets; l; l = l->fwd) {
+      for (j = 0; j < ns; j++)
+        if (seen[j] == (nip_sepset)l->data) break;
+      if (j == ns) seen[ns++] = (nip_sepset)l->data;
+    }
+  *n = ns;
+  return seen;
+}
+
 #define ALLOC(ptr, n, type)                                   \
   do {                                                        \
     (ptr) = (type*)calloc((size_t)((n) > 0 ? (n) : 1), sizeof(type)); \

@@ -21,6 +21,10 @@ extern "C" {
 nipgpu_model_desc* nipgpu_desc_from_model(nip_model model);
 void nipgpu_desc_free(nipgpu_model_desc* d);
 
+/* The model's sepsets in the order the description numbers them (walk of every
+ * clique's sepset list, first occurrence wins).  Caller frees the array. */
+nip_sepset* nipgpu_model_sepsets(nip_model model, int* n);
+
 /* position of `v` in model->variables[], or -1 */
 int nipgpu_var_index(nip_model model, nip_variable v);
 

@@ -296,3 +296,36 @@ double refh_time_em_iteration(void** tsp, int n_ts, double* counts, double* logl
   refh_estep(tsp, n_ts, counts, loglik);
   return now_s() - t0;
 }
+
+/* ---- helpers for tests of the nip.h drop-in (nip_b200/host/nip_gpu_backend.c) ---- */
+void* refh_variable(void* m, int var) { return ((nip_model)m)->variables[var]; }
+
+int refh_ucs_length(void* u) { return ((uncertain_series)u)->length; }
+
+void refh_flatten_ucs(void* up, double* out) {
+  uncertain_series u = (uncertain_series)up;
+  int t, i, s;
+  size_t o = 0;
+  for (t = 0; t < u->length; t++)
+    for (i = 0; i < u->num_of_vars; i++)
+      for (s = 0; s < NIP_CARDINALITY(u->variables[i]); s++) out[o++] = u->data[t][i][s];
+}
+
+void refh_free_ucs(void* u) { free_uncertainseries((uncertain_series)u); }
+
+void* refh_new_double_list(void) { return nip_new_double_list(); }
+
+int refh_double_list_to_array(void* lp, double* out, int cap) {
+  nip_double_list l = (nip_double_list)lp;
+  nip_double_link k;
+  int n = 0;
+  for (k = NIP_LIST_ITERATOR(l); k && n < cap; k = NIP_LIST_NEXT(k)) out[n++] = k->data;
+  return NIP_LIST_LENGTH(l);
+}
+
+void refh_free_double_list(void* lp) {
+  nip_empty_double_list((nip_double_list)lp);
+  free(lp);
+}
+
+long refh_seed(long seed) { return random_seed(&seed); }

@@ -1,0 +1,134 @@
+"""GPU suite: the nip.h drop-in (nip_b200/host/nip_gpu_backend.c) called exactly as
+util/nipinference.c and util/niptrain.c call libnip, on a model parsed by the
+reference's own host code, against the reference's own functions in the same
+process (same parsed nip_model, same in-memory time_series)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cases import assert_close
+from nip_b200.synth import HmmSpec, net_text_generic
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BACKEND = os.path.join(ROOT, "nip_b200", "libnip_gpu_backend.so")
+vp, i32, f64 = C.c_void_p, C.c_int, C.c_double
+
+
+@pytest.fixture(scope="module")
+def libs(gpu_lib):
+    from oracle.bindings import REF_SO, RefLib, have_ref
+    if not have_ref() or not os.path.exists(BACKEND):
+        pytest.skip("needs the prebuilt oracle/_ref/libnip_ref.so and nip_b200/libnip_gpu_backend.so")
+    C.CDLL(REF_SO, mode=C.RTLD_GLOBAL)      # the unchanged host code: parser, lists, error handler
+    ref = RefLib()
+    gpu = C.CDLL(BACKEND)
+    for f in (gpu.forward_backward_inference, gpu.forward_inference):
+        f.restype = vp
+        f.argtypes = [vp, vp, i32, C.POINTER(f64)]
+    gpu.em_learn.argtypes = [vp, i32, f64, vp]
+    gpu.make_consistent.argtypes = [vp]
+    gpu.nip_gpu_release.argtypes = [vp]
+    L = ref.L
+    L.refh_variable.restype = vp
+    L.refh_variable.argtypes = [vp, i32]
+    L.refh_ucs_length.argtypes = [vp]
+    L.refh_flatten_ucs.argtypes = [vp, vp]
+    L.refh_free_ucs.argtypes = [vp]
+    L.refh_new_double_list.restype = vp
+    L.refh_double_list_to_array.argtypes = [vp, vp, i32]
+    L.refh_free_double_list.argtypes = [vp]
+    L.refh_seed.argtypes = [C.c_long]
+    return ref, gpu
+
+
+def _vars(ref, model, idx):
+    return (vp * len(idx))(*[ref.L.refh_variable(model.h, v) for v in idx])
+
+
+def _flat(ref, ucs, row):
+    out = np.zeros((ref.L.refh_ucs_length(ucs), row))
+    ref.L.refh_flatten_ucs(ucs, out.ctypes.data_as(vp))
+    ref.L.refh_free_ucs(ucs)
+    return out
+
+
+def test_forward_backward_inference_dropin(libs, tmp_path):
+    ref, gpu = libs
+    h = HmmSpec(24, 7, seed=21)
+    p = tmp_path / "h.net"
+    p.write_text(h.net_text())
+    model = ref.parse(p)
+    query = [1, 2, 0]
+    row = 24 + 24 + 7
+    for s in h.sample(5, 30, seed=3, missing=0.1):
+        ts = model.timeseries(h.obs_vars, s)
+        want, ll_want = model.infer(ts, query)
+        ll = f64()
+        got = _flat(ref, gpu.forward_backward_inference(ts, _vars(ref, model, query), 3, C.byref(ll)), row)
+        assert_close(got, want, "forward_backward_inference posteriors")
+        assert_close(ll.value, ll_want, "forward_backward_inference loglikelihood")
+        want, ll_want = model.infer(ts, query, forward_only=True)
+        got = _flat(ref, gpu.forward_inference(ts, _vars(ref, model, query), 3, C.byref(ll)), row)
+        assert_close(got, want, "forward_inference posteriors")
+        assert_close(ll.value, ll_want, "forward_inference loglikelihood")
+        # loglikelihood == NULL is allowed (util/nipmap.c:145)
+        got = _flat(ref, gpu.forward_backward_inference(ts, _vars(ref, model, [1]), 1, None), 24)
+        assert_close(got, model.infer(ts, [1])[0], "posteriors without likelihood")
+    # unmarked variables are ignored (nip_unmark_variable, src/nip.c:993)
+    model.mark(0, False)
+    ts = model.timeseries(h.obs_vars, h.sample(1, 12, seed=9)[0])
+    want, _ = model.infer(ts, [1])
+    got = _flat(ref, gpu.forward_backward_inference(ts, _vars(ref, model, [1]), 1, None), 24)
+    assert_close(got, want, "unmarked evidence column")
+    gpu.nip_gpu_release(model.h)
+
+
+def test_em_learn_dropin(libs, tmp_path):
+    ref, gpu = libs
+    text = net_text_generic(
+        [("Y1", 3, None), ("X1", 4, None), ("X0", 4, "X1")],
+        [("Y1", ["X1"], np.ones((4, 3))), ("X1", ["X0"], np.ones((4, 4))), ("X0", [], np.ones((1, 4)))])
+    p = tmp_path / "e.net"
+    p.write_text(text)
+    rng = np.random.default_rng(4)
+    series = [rng.integers(0, 3, size=(int(rng.integers(5, 20)), 1)).astype(np.int32) for _ in range(6)]
+    m_ref, m_gpu = ref.parse(p), ref.parse(p)
+    ts_ref = [m_ref.timeseries([0], s) for s in series]
+    ts_gpu = [m_gpu.timeseries([0], s) for s in series]
+    st_ref, curve_ref = m_ref.em_learn(ts_ref, 1.0, 99)          # threshold 1.0 => exactly 3 iterations
+    ref.L.refh_seed(99)
+    lc = ref.L.refh_new_double_list()
+    arr = (vp * len(ts_gpu))(*ts_gpu)
+    st_gpu = gpu.em_learn(arr, len(ts_gpu), 1.0, lc)
+    curve = np.zeros(64)
+    n = ref.L.refh_double_list_to_array(lc, curve.ctypes.data_as(vp), 64)
+    ref.L.refh_free_double_list(lc)
+    assert st_gpu == st_ref == 0
+    assert n == len(curve_ref) == 3
+    assert_close(curve[:n], curve_ref, "learning curve")
+    t_ref, p_ref = m_ref.parameters()
+    t_gpu, p_gpu = m_gpu.parameters()                             # trained CPTs are back on the host model
+    assert_close(t_gpu, t_ref, "trained original_p")
+    assert_close(p_gpu, p_ref, "trained priors")
+    gpu.nip_gpu_release(m_gpu.h)
+
+
+def test_make_consistent_dropin(libs, tmp_path):
+    ref, gpu = libs
+    h = HmmSpec(6, 4, seed=2)
+    p = tmp_path / "m.net"
+    p.write_text(h.net_text())
+    m_ref, m_gpu = ref.parse(p), ref.parse(p)
+    for m in (m_ref, m_gpu):
+        m.reset()
+        m.use_priors(0)
+        m.enter_evidence(0, [0.1, 0.7, 0.0, 0.2])
+    m_ref.make_consistent()
+    gpu.make_consistent(m_gpu.h)
+    assert_close(m_gpu.mass(), m_ref.mass(), "model_prob_mass on the mirrored tree")
+    for v in range(3):
+        assert_close(m_gpu.marginal(v), m_ref.marginal(v), "get_probability on the mirrored tree")
+    gpu.nip_gpu_release(m_gpu.h)
