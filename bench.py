@@ -53,12 +53,15 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -72,7 +75,7 @@ class ClockSampler:
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
             except (ValueError, IndexError):
@@ -179,11 +182,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                     # nvidia-smi needs ~1 s to start streaming: start before warm-up
     for _ in range(W):
         batch.infer_device(query)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()                      # samples from here on belong to the timed regions
     api.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
@@ -197,7 +201,6 @@ def main():
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     launches = api.launch_count()
-    clocks = sampler.stop()
 
     # ---- end to end through the host-buffer entry point (pinned host memory) ----
     obs_host = torch.from_numpy(np.ascontiguousarray(data.reshape(-1, 1))).pin_memory()
@@ -215,6 +218,7 @@ def main():
         e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - t1) / args.e2e_steps
+    clocks = sampler.stop()             # covers the device-timed steps and the end-to-end steps
 
     times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
