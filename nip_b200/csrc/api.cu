@@ -475,6 +475,33 @@ int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidenc
   NIPGPU_CUDA(cudaSetDevice(m->device));
   const HostModel& hm = m->hm;
   const long long n = hm.coff[hm.nv];
+  // ---- engine 2: counts as DMMA GEMMs ----
+  ChainPlan plan;
+  if (m->engine == NIPGPU_ENGINE_CHAIN && m->chain.ok &&
+      chain_plan(hm, m->chain, b->n_obs, b->obs_vars.data(), use_evidence, plan)) {
+    if (int e = chain_batch_prepare(m->chain, b->chain, b->n_series, b->len.data(), b->rows, b->t_max, m->stream)) return e;
+    ChainEmArgs x;
+    x.base.n_series = b->n_series; x.base.n_obs = b->n_obs; x.base.t_max = b->t_max; x.base.rows = b->rows;
+    x.base.d_obs = b->d_obs; x.base.d_row_off = b->d_row_off; x.base.want_ll = 1; x.base.forward_only = 0;
+    x.base.d_post = nullptr; x.base.post_stride = 0; x.base.post_off = 0;
+    x.base.d_ll = b->d_ll; x.base.d_status = b->d_status;
+    x.d_base0 = m->d_base0; x.d_base1 = m->d_base1; x.tab_off = &m->tab_off; x.d_ipool = m->d_ipool;
+    x.pseudo = add_pseudocount ? 1.0 : 0.0; x.d_counts = m->d_counts; x.sm_count = m->sm_count;
+    const int rc = chain_estep(hm, m->chain, b->chain, plan, x, m->stream, m->ev0, m->ev1);
+    if (rc == NIPGPU_OK) {
+      double tail[2] = {0, 0};
+      NIPGPU_CUDA(cudaMemcpyAsync(tail, m->d_counts + n, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+      if (counts)
+        NIPGPU_CUDA(cudaMemcpyAsync(counts, m->d_counts, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+      NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 7; }
+      if (loglik) *loglik = tail[0];
+      if (status) *status = tail[1] != 0 ? NIPGPU_EBADLUCK : 0;
+      return NIPGPU_OK;
+    }
+    if (rc != NIPGPU_EUNSUPPORTED) return rc;
+  }
   const int* obs_proj = nullptr;
   if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;
   if (int e = ensure_alpha(m, b)) return e;

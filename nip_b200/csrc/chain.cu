@@ -380,11 +380,17 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
 // beta_{t-1} (1 / sum of the sweep's result) is obtained during the sweep as
 // 1 / (r . colsum(A)), and the posterior of slice t, the alpha / evidence
 // prefetches and the stores all sit in the sweep's issue gaps.
-template <int NT, bool VEC>
+// EM variant: additionally stores, per slice, the row  rt[t] = r_t / Z_t  with
+// Z_t = own_{t-1} . (A . r_t) the mass of the slice's joint, so that the expected
+// transition counts become one GEMM  sum_t own_{t-1}^T rt[t]  (k_chain_counts), and
+// r0[series] = r_0 / (phi0 . r_0) for the first slice.
+template <int NT, bool VEC, bool EM>
 __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatchDev B,
                                                            const double* __restrict__ alpha,
                                                            double* __restrict__ post,
-                                                           int post_stride, int post_off) {
+                                                           int post_stride, int post_off,
+                                                           double* __restrict__ rt,
+                                                           double* __restrict__ r0) {
   constexpr int SP = 8 * NT;
   extern __shared__ double sB[];
   double* s_cs = sB + SP * SP;
@@ -472,6 +478,16 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
         for (int n = 0; n < NT; n++) { lam[n][0] *= hs; lam[n][1] *= hs; }
       }
     });
+    if (EM) {  // a = own_{t-1} (loaded in the sweep), u = A . r_t
+      double z0 = 0, z1 = 0;
+#pragma unroll
+      for (int n = 0; n < NT; n++) { z0 += a[n][0] * u[n][0]; z1 += a[n][1] * u[n][1]; }
+      const double zinv = safe_rcp(quad_sum_full(z0 + z1));
+      double2* rrow = reinterpret_cast<double2*>(rt + (row0 + t) * SP);
+#pragma unroll
+      for (int n = 0; n < NT; n++)
+        if (on) rrow[4 * n + q] = make_double2(r[n][0] * zinv, r[n][1] * zinv);
+    }
 #pragma unroll
     for (int n = 0; n < NT; n++) {
       beta[n][0] = first_next ? 1.0 : u[n][0] * h;
@@ -481,6 +497,181 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
     }
   }
   if (Tw >= 1) emit_post(0, 0 < T);
+  if (EM && Tw >= 1) {  // first slice: joint = A0 * r_0 / (phi0 . r_0)
+    double z0 = 0, z1 = 0;
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+      z0 += C.phi0[8 * n + 2 * q] * r[n][0];
+      z1 += C.phi0[8 * n + 2 * q + 1] * r[n][1];
+    }
+    const double zinv = safe_rcp(quad_sum_full(z0 + z1));
+    if (0 < T) {
+      double2* out0 = reinterpret_cast<double2*>(r0 + (long long)orig * SP);
+      double2* rrow = reinterpret_cast<double2*>(rt + row0 * SP);
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        out0[4 * n + q] = make_double2(r[n][0] * zinv, r[n][1] * zinv);
+        rrow[4 * n + q] = make_double2(0.0, 0.0);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------- EM ----
+// G[i_prev][i_cur] = sum over data rows k >= 1 of own[k-1][i_prev] * rt[k][i_cur]
+// (rt is zero on every series' first row, so the shifted product never pairs two
+// series).  Split-K over CTAs, partial tiles reduced afterwards in a fixed order.
+template <int NT>
+__global__ void __launch_bounds__(32 * NT) k_chain_counts(const double* __restrict__ own,
+                                                          const double* __restrict__ rt,
+                                                          long long rows, double* __restrict__ part) {
+  constexpr int SP = 8 * NT, KC = 32, LD = SP + 2;
+  extern __shared__ double sm[];
+  double* sA = sm;
+  double* sR = sm + KC * LD;
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, w = threadIdx.x >> 5;
+  long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+  chunk = (chunk + KC - 1) / KC * KC;
+  const long long k_begin = (long long)blockIdx.x * chunk;
+  const long long k_end = k_begin + chunk < rows ? k_begin + chunk : rows;
+  double acc[NT][2];
+#pragma unroll
+  for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
+  for (long long k0 = k_begin; k0 < k_end; k0 += KC) {
+    for (int x = threadIdx.x; x < KC * SP; x += blockDim.x) {
+      const int i = x / SP, c = x - i * SP;
+      const long long k = k0 + i;
+      sR[i * LD + c] = k < k_end ? rt[k * SP + c] : 0.0;
+      sA[i * LD + c] = (k < k_end && k >= 1) ? own[(k - 1) * SP + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC / 4; kk++) {
+      const double a = sA[(4 * kk + q) * LD + 8 * w + g];
+#pragma unroll
+      for (int n = 0; n < NT; n++) dmma(acc[n][0], acc[n][1], a, sR[(4 * kk + q) * LD + 8 * n + g]);
+    }
+    __syncthreads();
+  }
+  double* out = part + (long long)blockIdx.x * SP * SP;
+#pragma unroll
+  for (int n = 0; n < NT; n++) {
+    out[(8 * w + g) * SP + 8 * n + 2 * q] = acc[n][0];
+    out[(8 * w + g) * SP + 8 * n + 2 * q + 1] = acc[n][1];
+  }
+}
+
+// out[x] = sum_p part[p][x] in a fixed order
+__global__ void k_chain_sum_parts(const double* part, int parts, long long n, double* out) {
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+       x += (long long)gridDim.x * blockDim.x) {
+    double s = 0;
+    for (int p = 0; p < parts; p++) s += part[(long long)p * n + x];
+    out[x] = s;
+  }
+}
+
+// g0[ip] = sum over series of r0[series][ip]
+__global__ void k_chain_g0(const double* r0, int n_series, int SP, double* g0) {
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= SP) return;
+  double s = 0;
+  for (int b = 0; b < n_series; b++) s += r0[(long long)b * SP + ip];
+  g0[ip] = s;
+}
+
+// Cc[c][ip] += posterior rows grouped by their combined evidence index; every warp owns a
+// private table in shared memory and a contiguous range of rows (deterministic).
+__global__ void k_chain_leafcount(const double* __restrict__ postj, const int* __restrict__ cfg,
+                                  long long rows, int n_comb, int SP, double* __restrict__ part) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int tab = n_comb * SP;
+  double* mine = sm + (long long)w * tab;
+  for (int x = lane; x < tab; x += 32) mine[x] = 0.0;
+  __syncwarp();
+  const long long nwarps = (long long)gridDim.x * nw, me = (long long)blockIdx.x * nw + w;
+  const long long per = (rows + nwarps - 1) / nwarps;
+  const long long k_end = (me + 1) * per < rows ? (me + 1) * per : rows;
+  for (long long k = me * per; k < k_end; k++) {
+    double* dst = mine + cfg[k] * SP;
+    for (int c = lane; c < SP; c += 32) dst[c] += postj[k * SP + c];
+  }
+  __syncthreads();
+  double* out = part + (long long)blockIdx.x * tab;
+  for (int x = threadIdx.x; x < tab; x += blockDim.x) {
+    double s = 0;
+    for (int k = 0; k < nw; k++) s += sm[(long long)k * tab + x];
+    out[x] = s;
+  }
+}
+
+// expected table of the interface clique over all slices (E) and over first slices (E0)
+__global__ void k_chain_expect_c0(const double* base0, const double* base1, const int* ent_im,
+                                  const int* ent_ip, int n, int SP, const double* G,
+                                  const double* g0, double* E, double* E0) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double first = base0[e] * g0[ent_ip[e]];
+  E0[e] = first;
+  E[e] = base1[e] * G[ent_im[e] * SP + ent_ip[e]] + first;
+}
+
+struct LeafExpect {
+  int n_free, card[8], stride[8];   // free variables of the leaf, their cfg strides
+  int slot;                          // position among the plan's active leaves, -1 = no evidence columns
+  int mult, n_cfg, miss_cfg;         // combined-index digit of this leaf
+  int m, R, S, SP, n_comb;
+  long long lam_off;
+};
+
+// expected table of a leaf clique: E(s, y) = base(s, y) * sum over evidence configurations
+// compatible with y of  [posterior mass of s observed under that configuration] / Lambda(cfg, s)
+__global__ void k_chain_expect_leaf(const double* base1, const int* pbase, const int* poff,
+                                    const int* ip_to_s, LeafExpect L, const double* Cc,
+                                    const double* lam, double* E) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= L.m * L.R) return;
+  const int s = x / L.R, r = x - s * L.R;
+  const int entry = pbase[s] + poff[r];
+  int digit[8], rem = r;
+  for (int k = 0; k < L.n_free; k++) { digit[k] = rem % L.card[k]; rem /= L.card[k]; }
+  double W = 0;
+  for (int mask = 0; mask < (1 << L.n_free); mask++) {   // each free variable: observed as y_k, or not observed
+    int cl = 0;
+    for (int k = 0; k < L.n_free; k++) cl += ((mask >> k) & 1 ? L.card[k] : digit[k]) * L.stride[k];
+    if (L.slot < 0 && cl != L.miss_cfg) continue;
+    double mass = 0, lam_s = 0;
+    for (int ip = 0; ip < L.S; ip++) {
+      if (ip_to_s[ip] != s) continue;
+      lam_s = lam[L.lam_off + (long long)cl * L.SP + ip];
+      for (int c = 0; c < L.n_comb; c++)
+        if (L.slot < 0 || (c / L.mult) % L.n_cfg == cl) mass += Cc[(long long)c * L.SP + ip];
+    }
+    if (lam_s != 0) W += mass / lam_s;
+  }
+  E[entry] = base1[entry] * W;
+}
+
+// counts[j] = pseudo + sum_r E[base[j] + off[r]]   (family table of one variable)
+__global__ void k_chain_family(const double* E, const int* pbase, const int* poff, int m, int R,
+                               double pseudo, double* counts) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double s = 0;
+  const int b = pbase[j];
+  for (int r = 0; r < R; r++) s += E[b + poff[r]];
+  counts[j] = pseudo + s;
+}
+
+__global__ void k_chain_tail(const double* ll, const int* status, int n_series, double* tail) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double L = 0;
+    int bad = 0;
+    for (int s = 0; s < n_series; s++) { L += ll[s]; bad |= status[s]; }
+    tail[0] = L;
+    tail[1] = bad ? 1.0 : 0.0;
+  }
 }
 
 template <class K>
@@ -519,12 +710,30 @@ int launch_backward(const ChainDev& C, const ChainBatchDev& B, const ChainInferA
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
   const bool vec = ((a.post_stride | a.post_off) & 1) == 0 && C.S == C.SP;
   if (vec) {
-    if (int e = set_smem(k_chain_backward<NT, true>, smem)) return e;
-    k_chain_backward<NT, true><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride, a.post_off);
+    if (int e = set_smem(k_chain_backward<NT, true, false>, smem)) return e;
+    k_chain_backward<NT, true, false><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                                a.post_off, nullptr, nullptr);
   } else {
-    if (int e = set_smem(k_chain_backward<NT, false>, smem)) return e;
-    k_chain_backward<NT, false><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride, a.post_off);
+    if (int e = set_smem(k_chain_backward<NT, false, false>, smem)) return e;
+    k_chain_backward<NT, false, false><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                                 a.post_off, nullptr, nullptr);
   }
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
+template <int NT>
+int launch_em(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
+              double* postj, double* rt, double* r0, long long rows, int parts, double* part,
+              cudaStream_t st) {
+  if (int e = launch_forward_v<NT, false, true>(C, B, a, alpha, st)) return e;
+  const int grid = (B.n_series + 31) / 32;
+  const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
+  if (int e = set_smem(k_chain_backward<NT, true, true>, smem)) return e;
+  k_chain_backward<NT, true, true><<<grid, 128, smem, st>>>(C, B, alpha, postj, C.SP, 0, rt, r0);
+  NIPGPU_LAUNCHED();
+  const size_t smem2 = sizeof(double) * 2 * 32 * (8 * NT + 2);
+  k_chain_counts<NT><<<parts, 32 * NT, smem2, st>>>(alpha, rt, rows, part);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
@@ -637,6 +846,16 @@ int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st)
   if (!cm.ok) return NIPGPU_OK;
   const size_t sp2 = (size_t)cm.SP * cm.SP;
   if (int e = upload(&cm.d_ent_of, cm.ent_of, st)) return e;
+  {  // entry of the interface clique -> (previous state, current state); leaves: state -> sepset entry
+    std::vector<int> im((size_t)hm.csize[cm.c0]), ip((size_t)hm.csize[cm.c0]), i2s;
+    for (int a = 0; a < cm.S; a++)
+      for (int b = 0; b < cm.S; b++) { im[cm.ent_of[(size_t)a * cm.S + b]] = a; ip[cm.ent_of[(size_t)a * cm.S + b]] = b; }
+    for (int l = 0; l < cm.n_real; l++) i2s.insert(i2s.end(), cm.leaves[l].ip_to_s.begin(), cm.leaves[l].ip_to_s.end());
+    if (int e = upload(&cm.d_ent_im, im, st)) return e;
+    if (int e = upload(&cm.d_ent_ip, ip, st)) return e;
+    if (int e = upload(&cm.d_ip_to_s, i2s, st)) return e;
+    NIPGPU_CUDA(cudaStreamSynchronize(st));
+  }
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_Bf1, sp2 * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_Bb1, sp2 * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cm.d_Bb0, sp2 * sizeof(double)));
@@ -717,7 +936,7 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
 
 void chain_free(ChainModel& cm) {
   cudaFree(cm.d_ent_of); cudaFree(cm.d_Bf1); cudaFree(cm.d_Bb1); cudaFree(cm.d_Bb0);
-  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_R1); cudaFree(cm.d_colsum);
+  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_R1); cudaFree(cm.d_colsum); cudaFree(cm.d_ent_im); cudaFree(cm.d_ent_ip); cudaFree(cm.d_ip_to_s);
   cm = ChainModel();
 }
 
@@ -779,6 +998,7 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
 void chain_batch_free(ChainBatch& cb) {
   cudaFree(cb.d_order); cudaFree(cb.d_len_sorted); cudaFree(cb.d_cfg); cudaFree(cb.d_alpha);
   cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_rows); cudaFree(cb.d_comb);
+  cudaFree(cb.d_postj); cudaFree(cb.d_rt); cudaFree(cb.d_r0); cudaFree(cb.d_em_scratch);
   cb = ChainBatch();
 }
 
@@ -870,6 +1090,120 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
     if (e) return e;
   }
   if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
+  return NIPGPU_OK;
+}
+
+// E-step of a whole batch on the chain engine: forward, backward (EM flavour), transition
+// counts as a DMMA GEMM, leaf counts, then expected clique tables -> per-variable family
+// counts in the layout of em_learn's `parameters[]` (src/nip.c:2108-2128).
+// Returns NIPGPU_EUNSUPPORTED when the evidence layout does not fit (caller uses engine 1).
+int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
+                const ChainEmArgs& x, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+  const ChainInferArgs& a = x.base;
+  const int SP = cm.SP, S = cm.S;
+  const size_t tab = (size_t)plan.n_comb * SP;
+  int lc_warps = 8;
+  while (lc_warps > 1 && lc_warps * tab * sizeof(double) > 200 * 1024) lc_warps /= 2;
+  if (lc_warps * tab * sizeof(double) > 200 * 1024) return NIPGPU_EUNSUPPORTED;
+  for (int l = 0; l < cm.n_real; l++)
+    if (cm.leaves[l].free_vars.size() > 8) return NIPGPU_EUNSUPPORTED;
+  if (int e = chain_prepare_evidence(cm, cb, plan, a, st)) return e;
+
+  const long long rows = std::max<long long>(a.rows, 1);
+  const int parts = std::max(1, x.sm_count);
+  if (!cb.d_postj) {
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_postj, rows * SP * sizeof(double)));
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_rt, rows * SP * sizeof(double)));
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_r0, (size_t)std::max(a.n_series, 1) * SP * sizeof(double)));
+  }
+  // scratch: part_G | G | g0 | part_C | Cc | E | E0
+  const size_t n_partG = (size_t)parts * SP * SP, n_G = (size_t)SP * SP, n_partC = (size_t)parts * tab;
+  const size_t n_E = (size_t)hm.toff[hm.nc], n_E0 = (size_t)hm.csize[cm.c0];
+  const size_t need = n_partG + n_G + SP + n_partC + tab + n_E + n_E0;
+  if (cb.em_scratch_cap < need) {
+    cudaFree(cb.d_em_scratch);
+    cb.d_em_scratch = nullptr;
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_em_scratch, need * sizeof(double)));
+    cb.em_scratch_cap = need;
+  }
+  double* partG = cb.d_em_scratch;
+  double* G = partG + n_partG;
+  double* g0 = G + n_G;
+  double* partC = g0 + SP;
+  double* Cc = partC + n_partC;
+  double* E = Cc + tab;
+  double* E0 = E + n_E;
+
+  ChainBatchDev B;
+  B.n_series = a.n_series; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
+  B.cfg = cb.d_cfg; B.row_off = a.d_row_off;
+  ChainDev C;
+  C.S = S; C.SP = SP; C.c_miss = plan.c_miss;
+  C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
+  C.R1 = cm.d_R1; C.colsum = cm.d_colsum; C.m1_0 = cm.m1_0; C.lam_comb = cb.d_comb;
+  NIPGPU_CUDA(cudaMemsetAsync(cb.d_r0, 0, (size_t)std::max(a.n_series, 1) * SP * sizeof(double), st));
+  if (ev0) NIPGPU_CUDA(cudaEventRecord(ev0, st));
+  int e = NIPGPU_OK;
+  if (a.n_series > 0) {
+    switch (cm.NT) {
+      case 1: e = launch_em<1>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
+      case 2: e = launch_em<2>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
+      case 4: e = launch_em<4>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
+      case 8: e = launch_em<8>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
+      default: return NIPGPU_EUNSUPPORTED;
+    }
+    if (e) return e;
+  } else {
+    NIPGPU_CUDA(cudaMemsetAsync(partG, 0, n_partG * sizeof(double), st));
+  }
+  k_chain_sum_parts<<<(unsigned)((n_G + 255) / 256), 256, 0, st>>>(partG, parts, (long long)n_G, G);
+  NIPGPU_LAUNCHED();
+  k_chain_g0<<<(SP + 63) / 64, 64, 0, st>>>(cb.d_r0, a.n_series, SP, g0);
+  NIPGPU_LAUNCHED();
+  {
+    const size_t smem = (size_t)lc_warps * tab * sizeof(double);
+    if (int e2 = set_smem(k_chain_leafcount, smem)) return e2;
+    k_chain_leafcount<<<parts, 32 * lc_warps, smem, st>>>(cb.d_postj, cb.d_cfg, a.rows, plan.n_comb, SP, partC);
+    NIPGPU_LAUNCHED();
+    k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, parts, (long long)tab, Cc);
+    NIPGPU_LAUNCHED();
+  }
+  if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
+  // ---- expected clique tables ----
+  const int n0 = hm.csize[cm.c0];
+  k_chain_expect_c0<<<(n0 + 255) / 256, 256, 0, st>>>(x.d_base0 + (*x.tab_off)[cm.c0], x.d_base1 + (*x.tab_off)[cm.c0],
+                                                      cm.d_ent_im, cm.d_ent_ip, n0, SP, G, g0,
+                                                      E + (*x.tab_off)[cm.c0], E0);
+  NIPGPU_LAUNCHED();
+  for (int l = 0; l < cm.n_real; l++) {
+    const ChainLeafHost& Lh = cm.leaves[l];
+    const Proj& p = hm.projs[Lh.proj];
+    LeafExpect L;
+    L.n_free = (int)Lh.free_vars.size();
+    for (int k = 0; k < L.n_free; k++) { L.card[k] = hm.card[Lh.free_vars[k]]; L.stride[k] = Lh.cfg_stride[k]; }
+    L.slot = (int)(std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) - plan.active_leaf.begin());
+    if (L.slot == (int)plan.active_leaf.size()) L.slot = -1;
+    L.mult = L.slot >= 0 ? plan.mult[L.slot] : 1;
+    L.n_cfg = Lh.n_cfg; L.miss_cfg = Lh.miss_cfg;
+    L.m = p.m; L.R = p.R; L.S = S; L.SP = SP; L.n_comb = plan.n_comb; L.lam_off = Lh.lam_off;
+    const int n = p.m * p.R;
+    k_chain_expect_leaf<<<(n + 127) / 128, 128, 0, st>>>(x.d_base1 + (*x.tab_off)[Lh.clique], x.d_ipool + p.base_pos,
+                                                         x.d_ipool + p.off_pos, cm.d_ip_to_s + (size_t)l * S, L, Cc,
+                                                         cm.d_lam, E + (*x.tab_off)[Lh.clique]);
+    NIPGPU_LAUNCHED();
+  }
+  // ---- family counts of every variable ----
+  for (int v = 0; v < hm.nv; v++) {
+    const Proj& p = hm.projs[hm.proj_fam[v]];
+    const int c = hm.family[v];
+    const bool first_only = (hm.flags[v] & NIPGPU_IF_OLD_OUTGOING) != 0;   // src/nip.c:1932
+    const double* src = (first_only && c == cm.c0) ? E0 : E + (*x.tab_off)[c];
+    k_chain_family<<<(p.m + 127) / 128, 128, 0, st>>>(src, x.d_ipool + p.base_pos, x.d_ipool + p.off_pos, p.m,
+                                                      p.R, x.pseudo, x.d_counts + hm.coff[v]);
+    NIPGPU_LAUNCHED();
+  }
+  k_chain_tail<<<1, 32, 0, st>>>(a.d_ll, a.d_status, a.n_series, x.d_counts + hm.coff[hm.nv]);
+  NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
 

@@ -43,6 +43,8 @@ struct ChainModel {
   std::vector<int> ent_of;     // [S*S] (i_prev * S + i_cur) -> entry of the interface clique
   // device
   int* d_ent_of = nullptr;
+  int *d_ent_im = nullptr, *d_ent_ip = nullptr;  // entry of the interface clique -> (previous, current) state
+  int* d_ip_to_s = nullptr;                      // [n_real][S] state -> leaf sepset entry
   double *d_Bf1 = nullptr, *d_Bb1 = nullptr, *d_Bb0 = nullptr;  // fragment-ordered SPxSP
   double *d_phi0 = nullptr, *d_lam0 = nullptr, *d_R1 = nullptr, *d_colsum = nullptr; // [SP]
   double m1_0 = 1.0;           // mass of the evidence-free first slice
@@ -66,6 +68,9 @@ struct ChainBatch {
   int* d_cols = nullptr;           // column metadata of the cached plan
   long long* d_rows = nullptr;
   std::vector<int> plan_key;       // identifies the cached plan
+  // EM (chain_estep)
+  double *d_postj = nullptr, *d_rt = nullptr, *d_r0 = nullptr, *d_em_scratch = nullptr;
+  size_t em_scratch_cap = 0;
 };
 
 // per-call evidence plan: which leaves see evidence through which data columns
@@ -108,5 +113,17 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
 int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
                 const ChainInferArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 void chain_batch_free(ChainBatch& cb);
+
+struct ChainEmArgs {
+  ChainInferArgs base;           // d_post / forward_only unused
+  const double *d_base0, *d_base1;
+  const std::vector<int>* tab_off;
+  const int* d_ipool;
+  double pseudo;                 // 1.0 = the reference's pseudo-count (src/nip.c:2171-2172), or 0
+  double* d_counts;              // [counts + 2]
+  int sm_count;
+};
+int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
+                const ChainEmArgs& x, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 
 }  // namespace nipgpu

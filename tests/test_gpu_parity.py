@@ -63,6 +63,25 @@ def test_unmarked_columns_are_ignored(gpu_lib, oracle_lib, engine):
 
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("S,M,B,T", [(64, 32, 48, 40), (7, 3, 100, 17), (33, 5, 19, 9)])
+def test_hmm_em_vs_oracle(gpu_lib, oracle_lib, engine, S, M, B, T):
+    """E-step of seeded synthetic HMMs (ragged, missing data) against the oracle"""
+    from nip_b200.synth import HmmSpec
+    h = HmmSpec(S, M, seed=S + M)
+    fm = h.flat()
+    data = h.sample(B, T, seed=3, missing=0.1)
+    data[:, 0, 0] = np.abs(data[:, 0, 0])      # observed first slices (DESIGN.md section 7)
+    rng = np.random.default_rng(5)
+    series = [data[i, :int(rng.integers(1, T + 1))] for i in range(B)]
+    want, ll_want, st_want = oracle_lib.model(fm).estep(h.obs_vars, series)
+    m = gpu_lib.Model(fm, engine=engine)
+    counts, ll, st = m.batch(h.obs_vars, series).estep()
+    assert st == st_want == 0
+    assert_close(counts, want, "HMM-%d expected counts (engine %d)" % (S, m.engine))
+    assert_close(ll, ll_want, "HMM-%d EM loglik" % S)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("S,M,B,T", [(64, 32, 48, 40), (7, 3, 100, 17), (33, 5, 19, 9)])
 def test_hmm_vs_oracle(gpu_lib, oracle_lib, engine, S, M, B, T):
     """seeded synthetic HMMs of the benchmark family, ragged lengths, missing data"""
     from nip_b200.synth import HmmSpec
@@ -99,12 +118,14 @@ def test_empty_and_single_slice(gpu_lib):
     assert post.shape[0] == 0 and ll.shape[0] == 0
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", EM_CASES)
-def test_em_golden(gpu_lib, name):
+def test_em_golden(gpu_lib, name, engine):
     """each EM iteration from the reference's own inputs: M-step tables/priors, then
-    E-step expected counts and log-likelihood"""
+    E-step expected counts and log-likelihood (engine 1: per-slice family marginals;
+    engine 2: transition counts as one DMMA GEMM)"""
     c = Case(name)
-    m = gpu_lib.Model(c.fm)
+    m = gpu_lib.Model(c.fm, engine=engine)
     b = m.batch(c.obs_vars, c.series)
     counts_in = unhex(c.j["em"]["init"])
     for k, it in enumerate(c.j["em"]["iters"]):
@@ -120,11 +141,12 @@ def test_em_golden(gpu_lib, name):
         counts_in = unhex(it["counts"])
 
 
-def test_bad_luck_is_reported(gpu_lib, oracle_lib):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_bad_luck_is_reported(gpu_lib, oracle_lib, engine):
     """an impossible observation (m2 == 0) must surface as NIP_ERROR_BAD_LUCK
     (src/nip.c:1827-1854), a clean set must not"""
     c = Case("model_net")
-    m = gpu_lib.Model(c.fm)
+    m = gpu_lib.Model(c.fm, engine=engine)
     om = oracle_lib.model(c.fm)
     impossible = [np.array([1, 0, 4]).reshape(-1, 1)]   # P(1,0,4) == 0 in examples/model.net
     fine = [np.array([2, 3, 2, 3, 2, 4]).reshape(-1, 1)]
