@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--em-iters", type=int, default=5)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -220,10 +221,24 @@ def main():
     e2e_s = (time.perf_counter() - t1) / args.e2e_steps
     clocks = sampler.stop()             # covers the device-timed steps and the end-to-end steps
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device="cuda")
+    # ---- EM: E-step + one all-reduce of the sufficient statistics + M-step per iteration ----
+    from nip_b200.dist import EmWorker, GpuEmBackend
+    rng = np.random.default_rng(7)
+    model.mstep(rng.random(model.counts_size()) + 0.1)     # same random start on every rank
+    worker = EmWorker(GpuEmBackend(model, batch), rank, world)
+    worker.iteration()
+    barrier()
+    t2 = time.perf_counter()
+    em_ll = 0.0
+    for _ in range(args.em_iters):
+        em_ll, em_bad = worker.iteration()
+    barrier()
+    em_s = (time.perf_counter() - t2) / args.em_iters
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, em_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms = [float(x) for x in times.cpu()]
+    dev_ms, e2e_ms, wall_ms, em_ms = [float(x) for x in times.cpu()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -266,6 +281,11 @@ def main():
                 "h2d_bytes_per_step": int(obs_np.nbytes), "d2h_bytes_per_step": int(post_np.nbytes + ll_np.nbytes),
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches), "clocks": clocks,
+        "em": {"metric": "EM iterations/s (E-step over the whole set + all-reduce + M-step)",
+               "value": 1e3 / em_ms, "unit": "iter/s", "ms_per_iteration": em_ms,
+               "slice_steps_per_s": units / (em_ms * 1e-3),
+               "workload": "same model and data, %d x %d slices per GPU, %d GPU(s)" % (N_SERIES, T, world),
+               "allreduce_doubles": int(model.counts_size() + 2), "loglik_per_slice": em_ll / units},
     }
     if not args.no_cpu_baseline:
         v, cores, kind, what, _ = cpu_reference(h, data)
