@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <type_traits>
 
 namespace nipgpu {
 
@@ -142,39 +143,69 @@ __global__ void k_chain_cfg(const int* obs, long long rows, int n_obs, const int
   cfg[r] = c;
 }
 
-// acc[n] += sum over the 2*NT k-steps of A(k-step) x B(k-step, n): the whole
-// [8 x SP] . [SP x SP] contraction of one slice.  One 16-byte shared load brings
-// the B fragments of two neighbouring n-tiles; they are fetched a k-step ahead.
-// `side(ks)` is called once per k-step with ks as a compile-time-foldable value:
-// the callers put work there that does not depend on this sweep, so that it fills
-// the issue slots between tensor instructions (a warp can issue one DMMA per ~16
-// cycles and is alone on its scheduler).
+__device__ __forceinline__ void dmma_init(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
+               : "=d"(c0), "=d"(c1)
+               : "d"(a), "d"(b), "d"(0.0));
+}
+
+// acc[n] = sum over the 2*NT k-steps of A(k-step) x B(k-step, n): the whole
+// [8 x SP] . [SP x SP] contraction of one slice (2*NT*NT tensor instructions).
+// One 16-byte shared load brings the B fragments of two neighbouring n-tiles;
+// they are fetched a k-step ahead.
+//
+// A warp can issue one DMMA per ~16 cycles and is alone on its scheduler, so the
+// issue slots between two DMMAs are free.  `side(slot)` is called after every
+// tensor instruction with a compile-time slot number 0 .. 2*NT*NT-1; callers hang
+// small pieces of work there that do not depend on this sweep's result.
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
 template <int NT, class Side>
 __device__ __forceinline__ void mma_sweep(double (&acc)[NT][2], const double (&a)[NT][2],
                                           const double* __restrict__ frag, Side side) {
   double b[2][NT];
-  auto fetch = [&](int ks, double* dst) {
+  auto fetch = [&](auto ksc, auto bufc) {
+    constexpr int ks = decltype(ksc)::value, buf = decltype(bufc)::value;
     if constexpr (NT >= 2) {
       const double2* p = reinterpret_cast<const double2*>(frag) + ((ks * (NT / 2)) << 5);
-#pragma unroll
-      for (int n2 = 0; n2 < NT / 2; n2++) {
+      static_for<0, NT / 2>([&](auto n2c) {
+        constexpr int n2 = decltype(n2c)::value;
         const double2 v = p[n2 << 5];
-        dst[2 * n2] = v.x;
-        dst[2 * n2 + 1] = v.y;
-      }
+        b[buf][2 * n2] = v.x;
+        b[buf][2 * n2 + 1] = v.y;
+      });
     } else {
-      dst[0] = frag[ks << 5];
+      b[buf][0] = frag[ks << 5];
     }
   };
-  fetch(0, b[0]);
-#pragma unroll
-  for (int ks = 0; ks < 2 * NT; ks++) {
-    if (ks + 1 < 2 * NT) fetch(ks + 1, b[(ks + 1) & 1]);
+  fetch(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+  static_for<0, 2 * NT>([&](auto ksc) {
+    constexpr int ks = decltype(ksc)::value;
+    if constexpr (ks + 1 < 2 * NT)
+      fetch(std::integral_constant<int, ks + 1>{}, std::integral_constant<int, (ks + 1) & 1>{});
     const double av = a[ks >> 1][ks & 1];
-#pragma unroll
-    for (int n = 0; n < NT; n++) dmma(acc[n][0], acc[n][1], av, b[ks & 1][n]);
-    side(ks);
-  }
+    static_for<0, NT>([&](auto nc) {
+      constexpr int n = decltype(nc)::value;
+      if constexpr (ks == 0) dmma_init(acc[n][0], acc[n][1], av, b[0][n]);
+      else dmma(acc[n][0], acc[n][1], av, b[ks & 1][n]);
+      side(std::integral_constant<int, ks * NT + n>{});
+    });
+  });
+}
+
+// Spreads W work items evenly over the NS side slots of a sweep: slot s runs the items
+// w with  w*NS/W == s  (several per slot when W > NS).  Everything folds at compile time.
+template <int NS, int W, int SLOT, class Item>
+__device__ __forceinline__ void run_items(Item& item) {
+  static_for<0, W>([&](auto wc) {
+    if constexpr ((decltype(wc)::value * NS) / W == SLOT) item(wc);
+  });
 }
 
 // running log-likelihood sum_t log(m2_t) - log(m1_t) kept as a product with a
@@ -221,7 +252,17 @@ __device__ __forceinline__ double quad_sum_full(double v) {
   return v;
 }
 
-__device__ __forceinline__ double safe_rcp(double x) { return x != 0 ? 1.0 / x : 1.0; }
+// 1/x for the positive, normal-range scale factors of the recursions (0 -> 1: a zero vector
+// stays zero, nip_normalise_array).  Hardware seed + two Newton steps: branch-free, so it
+// does not split the sweep's basic block the way the IEEE division's slow path would;
+// relative error ~2e-16, far inside the 1e-9 gate.
+__device__ __forceinline__ double safe_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(fma(-x, y, 1.0), y, y);
+  y = fma(fma(-x, y, 1.0), y, y);
+  return x != 0 ? y : 1.0;
+}
 
 // ---------------------------------------------------------------- forward ---
 // alpha_t = normalise((alpha_{t-1} . A) * lambda_t) and the likelihood terms.
@@ -277,33 +318,6 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
   double Pp = 0;         // its m1 numerator (already times c of the slice before)
   double cp = 1.0;       // c of the slice before it
   bool noev_p = false, on_p = false;
-  double gscale = 1.0;   // g_t for the sweep in progress
-
-  // books of slice s (vector in `own`): masses, likelihood, outputs; returns c_s
-  auto settle = [&](int s, double& m2s) {
-    double s0 = 0, s1 = 0;
-#pragma unroll
-    for (int n = 0; n < NT; n++) { s0 += own[n][0]; s1 += own[n][1]; }
-    const double c = quad_sum_full(s0 + s1);
-    m2s = c * K;
-    if (WLL) L.add(Pp, noev_p ? Pp : m2s * cp, on_p);
-    if (on_p) {
-      double2* arow = reinterpret_cast<double2*>(alpha + (row0 + s) * SP);
-#pragma unroll
-      for (int n = 0; n < NT; n++) arow[4 * n + q] = make_double2(own[n][0], own[n][1]);
-    }
-    if (FILT) {  // filtering: the forward marginal of I_s is alpha_s = own / c
-      const double cinv = safe_rcp(c);
-      double* prow = post + (row0 + s) * post_stride + post_off;
-#pragma unroll
-      for (int n = 0; n < NT; n++) {
-        const int col = 8 * n + 2 * q;
-        if (on_p && col < C.S) prow[col] = own[n][0] * cinv;
-        if (on_p && col + 1 < C.S) prow[col + 1] = own[n][1] * cinv;
-      }
-    }
-    return c;
-  };
 
   // ---- slice 0: own_0 = phi0 * lambda_0 / S0 (c_0 = 1), m1_0 = mass of the evidence-free slice
   int c_cur = T > 0 ? cfg[0] : 0;
@@ -325,43 +339,97 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
     K = S0; Pp = C.m1_0; cp = 1.0; noev_p = c_cur == C.c_miss; on_p = T > 0;
   }
 
-  for (int t = 1; t < Tw; t++) {
-    const bool on = t < T;
-    c_cur = c_next;
-    load_lam(c_cur, on);            // evidence row of slice t: in flight during the sweep
-    if (t + 1 < T) c_next = __ldg(cfg + t + 1);
-#pragma unroll
-    for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
-    double d0 = 0, d1 = 0, m2p = 0, c = 0;
-    mma_sweep<NT>(acc, own, frag, [&](int ks) {
-      if (ks == 0) {
-        c = settle(t - 1, m2p);
-        if (WLL) {                  // m1 numerator of slice t: own_{t-1} . R1
-#pragma unroll
-          for (int n = 0; n < NT; n++) {
-            const double2 v = r1v[4 * n + q];
-            d0 += own[n][0] * v.x;
-            d1 += own[n][1] * v.y;
-          }
-        }
+  // Work of one slice that is NOT on the recurrence's critical path, cut into items that are
+  // hung between the tensor instructions of the next sweep (or run back to back after the last
+  // slice).  It settles slice s = t-1 whose vector is the sweep's A operand `own`.
+  constexpr int E = 2 * NT;                  // elements of a vector held by one lane
+  constexpr int I_SUM = 0;                   // E items : partial sums of own
+  constexpr int I_RED = I_SUM + E;           // 3 items : combine + two quad shuffles -> c
+  constexpr int I_LL = I_RED + 3;            // 1 item  : masses, likelihood bookkeeping
+  constexpr int I_ST = I_LL + 1;             // NT items: alpha row (and filtered output)
+  constexpr int I_DOT = I_ST + NT;           // NT items: own . R1 (m1 numerator of the next slice)
+  constexpr int I_DRED = I_DOT + NT;         // 3 items
+  constexpr int I_G = I_DRED + 3;            // 1 item  : scale of the sweep in progress
+  constexpr int I_LAM = I_G + 1;             // NT items: fold it into the evidence row
+  constexpr int W_ITEMS = I_LAM + NT;
+  double ps[4], cs = 0, m2p = 0, cinv = 1.0, d0 = 0, d1 = 0, Pn = 0, gscale = 1.0;
+  int s_slice = 0;
+  bool fold = true;                          // false for the epilogue after the last slice
+  auto item = [&](auto wc) {
+    constexpr int w = decltype(wc)::value;
+    if constexpr (w >= I_SUM && w < I_RED) {
+      constexpr int i = w - I_SUM;
+      const double x = own[i >> 1][i & 1];
+      if constexpr (i < 4) ps[i & 3] = x;
+      else ps[i & 3] += x;
+    } else if constexpr (w == I_RED) {
+      if constexpr (E >= 4) cs = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      else cs = ps[0] + ps[1];
+    } else if constexpr (w == I_RED + 1) {
+      cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+    } else if constexpr (w == I_RED + 2) {
+      cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+    } else if constexpr (w == I_LL) {
+      m2p = cs * K;
+      if (WLL) L.add(Pp, noev_p ? Pp : m2p * cp, on_p);
+      if (FILT) cinv = safe_rcp(cs);
+    } else if constexpr (w >= I_ST && w < I_DOT) {
+      constexpr int n = w - I_ST;
+      if (on_p) reinterpret_cast<double2*>(alpha + (row0 + s_slice) * SP)[4 * n + q] = make_double2(own[n][0], own[n][1]);
+      if (FILT) {  // filtering: the forward marginal of I_s is alpha_s = own / c
+        double* prow = post + (row0 + s_slice) * post_stride + post_off;
+        const int col = 8 * n + 2 * q;
+        if (on_p && col < C.S) prow[col] = own[n][0] * cinv;
+        if (on_p && col + 1 < C.S) prow[col + 1] = own[n][1] * cinv;
       }
-      if (ks == 2 * NT - 1) {       // scale of this slice; fold it into the evidence row
-        const double den = c * m2p;
+    } else if constexpr (w >= I_DOT && w < I_DRED) {
+      if (WLL && fold) {
+        constexpr int n = w - I_DOT;
+        const double2 v = r1v[4 * n + q];
+        if constexpr (n == 0) { d0 = own[n][0] * v.x; d1 = own[n][1] * v.y; }
+        else { d0 += own[n][0] * v.x; d1 += own[n][1] * v.y; }
+      }
+    } else if constexpr (w == I_DRED) {
+      if (WLL && fold) Pn = d0 + d1;
+    } else if constexpr (w == I_DRED + 1) {
+      if (WLL && fold) Pn += __shfl_xor_sync(0xffffffffu, Pn, 1);
+    } else if constexpr (w == I_DRED + 2) {
+      if (WLL && fold) Pn += __shfl_xor_sync(0xffffffffu, Pn, 2);
+    } else if constexpr (w == I_G) {
+      if (fold) {
+        const double den = cs * m2p;
         gscale = safe_rcp(den);
         K = den != 0 ? m2p : 0.0;
-#pragma unroll
-        for (int n = 0; n < NT; n++) { lam[n][0] *= gscale; lam[n][1] *= gscale; }
       }
-    });
-    if (WLL) Pp = quad_sum_full(d0 + d1);
-    cp = c; noev_p = c_cur == C.c_miss; on_p = on;
+    } else if constexpr (w >= I_LAM && w < W_ITEMS) {
+      if (fold) {
+        constexpr int n = w - I_LAM;
+        lam[n][0] *= gscale;
+        lam[n][1] *= gscale;
+      }
+    }
+  };
+
+  // The evidence row of slice t is requested at the END of iteration t-1 (ptxas sinks a load
+  // towards its first use but not across the loop's back edge), so it is in flight during
+  // the whole sweep of slice t and is consumed only by the sweep's last side items.
+  c_cur = c_next;
+  load_lam(c_cur, 1 < T);
+  if (2 < T) c_next = __ldg(cfg + 2);
+  for (int t = 1; t < Tw; t++) {
+    const bool on = t < T;
+    s_slice = t - 1;
+    mma_sweep<NT>(acc, own, frag, [&](auto sc) { run_items<2 * NT * NT, W_ITEMS, decltype(sc)::value>(item); });
+    Pp = Pn; cp = cs; noev_p = c_cur == C.c_miss; on_p = on;
 #pragma unroll
     for (int n = 0; n < NT; n++) { own[n][0] = acc[n][0] * lam[n][0]; own[n][1] = acc[n][1] * lam[n][1]; }
+    c_cur = c_next;
+    load_lam(c_cur, t + 1 < T);     // evidence row of slice t+1
+    if (t + 2 < T) c_next = __ldg(cfg + t + 2);
   }
-  {
-    double m2last;
-    settle(Tw - 1, m2last);
-  }
+  fold = false;
+  s_slice = Tw - 1;
+  static_for<0, W_ITEMS>(item);
   if (valid && q == 0) {
     if (ll_out) ll_out[orig] = (WLL && T > 0) ? L.value() : 0.0;
     if (status_out) status_out[orig] = L.bad;
@@ -408,7 +476,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   const int* cfg = B.cfg + row0;
   const double* frag = sB + (NT >= 2 ? 2 * lane : lane);
   const double2* csv = reinterpret_cast<const double2*>(s_cs);
-  double beta[NT][2], r[NT][2], lam[NT][2], a[NT][2], u[NT][2];
+  double beta[NT][2], r[NT][2], lam[NT][2], a[NT][2], an[NT][2], u[NT][2];
   auto load_row = [&](const double* base, bool on, double (&dst)[NT][2]) {
     const double2* p = reinterpret_cast<const double2*>(base);
 #pragma unroll
@@ -416,31 +484,6 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
       const double2 v = ldg_pinned(p + 4 * n + q, on);
       dst[n][0] = v.x;
       dst[n][1] = v.y;
-    }
-  };
-  // posterior of slice t from alpha_t (in `a`) and beta_t: normalise(alpha_t * beta_t)
-  auto emit_post = [&](int t, bool on) {
-    double s0 = 0, s1 = 0;
-#pragma unroll
-    for (int n = 0; n < NT; n++) {
-      a[n][0] *= beta[n][0];
-      a[n][1] *= beta[n][1];
-      s0 += a[n][0];
-      s1 += a[n][1];
-    }
-    const double pinv = safe_rcp(quad_sum_full(s0 + s1));
-    double* prow = post + (row0 + t) * post_stride + post_off;
-    if (VEC) {
-#pragma unroll
-      for (int n = 0; n < NT; n++)
-        if (on) reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
-    } else {
-#pragma unroll
-      for (int n = 0; n < NT; n++) {
-        const int col = 8 * n + 2 * q;
-        if (on && col < C.S) prow[col] = a[n][0] * pinv;
-        if (on && col + 1 < C.S) prow[col + 1] = a[n][1] * pinv;
-      }
     }
   };
   // prologue: the longest rows start at slice Tw-1 with beta = 1, r = lambda
@@ -451,33 +494,89 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   for (int n = 0; n < NT; n++) beta[n][0] = beta[n][1] = 1.0;
   int c_pre = (Tw >= 2 && Tw - 2 < T) ? cfg[Tw - 2] : 0;
 
+  // Work of slice t that is not on the recurrence's critical path, cut into items hung
+  // between the tensor instructions of sweep t (see mma_sweep / run_items).
+  constexpr int E = 2 * NT;
+  constexpr int I_MUL = 0;                 // E items : a = alpha_t * beta_t, partial sums
+  constexpr int I_RED = I_MUL + E;         // 3 items : combine + two quad shuffles
+  constexpr int I_INV = I_RED + 3;         // 1 item  : reciprocal of the posterior's sum
+  constexpr int I_ST = I_INV + 1;          // NT items: store the posterior of slice t
+  constexpr int I_LD = I_ST + NT;          // NT items: alpha_{t-1} (prefetched into `an` before the sweep) -> `a`
+  constexpr int I_DOT = I_LD + NT;         // NT items: r . colsum(A) = sum of the sweep's result
+  constexpr int I_DRED = I_DOT + NT;       // 3 items
+  constexpr int I_H = I_DRED + 3;          // 1 item  : scale of beta_{t-1}
+  constexpr int I_LAM = I_H + 1;           // NT items: fold it into the evidence row of slice t-1
+  constexpr int W_ITEMS = I_LAM + NT;
+  double ps[4], psum = 0, pinv = 1.0, d0 = 0, d1 = 0, dsum = 0, h = 1.0, hs = 1.0;
+  int t_cur = 0;
+  bool on = false, pre = false, first_next = false;
+  auto item = [&](auto wc) {
+    constexpr int w = decltype(wc)::value;
+    if constexpr (w >= I_MUL && w < I_RED) {
+      constexpr int i = w - I_MUL;
+      a[i >> 1][i & 1] *= beta[i >> 1][i & 1];
+      if constexpr (i < 4) ps[i & 3] = a[i >> 1][i & 1];
+      else ps[i & 3] += a[i >> 1][i & 1];
+    } else if constexpr (w == I_RED) {
+      if constexpr (E >= 4) psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      else psum = ps[0] + ps[1];
+    } else if constexpr (w == I_RED + 1) {
+      psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+    } else if constexpr (w == I_RED + 2) {
+      psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+    } else if constexpr (w == I_INV) {
+      pinv = safe_rcp(psum);
+    } else if constexpr (w >= I_ST && w < I_LD) {   // posterior of slice t: normalise(alpha_t * beta_t)
+      constexpr int n = w - I_ST;
+      double* prow = post + (row0 + t_cur) * post_stride + post_off;
+      if (VEC) {
+        if (on) reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
+      } else {
+        const int col = 8 * n + 2 * q;
+        if (on && col < C.S) prow[col] = a[n][0] * pinv;
+        if (on && col + 1 < C.S) prow[col + 1] = a[n][1] * pinv;
+      }
+    } else if constexpr (w >= I_LD && w < I_DOT) {
+      constexpr int n = w - I_LD;
+      a[n][0] = an[n][0];
+      a[n][1] = an[n][1];
+    } else if constexpr (w >= I_DOT && w < I_DRED) {
+      constexpr int n = w - I_DOT;
+      const double2 v = csv[4 * n + q];
+      if constexpr (n == 0) { d0 = r[n][0] * v.x; d1 = r[n][1] * v.y; }
+      else { d0 += r[n][0] * v.x; d1 += r[n][1] * v.y; }
+    } else if constexpr (w == I_DRED) {
+      dsum = d0 + d1;
+    } else if constexpr (w == I_DRED + 1) {
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    } else if constexpr (w == I_DRED + 2) {
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+    } else if constexpr (w == I_H) {
+      h = safe_rcp(dsum);
+      hs = first_next ? 1.0 : h;
+    } else if constexpr (w >= I_LAM && w < W_ITEMS) {
+      constexpr int n = w - I_LAM;
+      lam[n][0] *= hs;
+      lam[n][1] *= hs;
+    }
+  };
+
+  // lambda_{t-1} (used by the last side items of sweep t) and alpha_{t-1} (used at the start
+  // of sweep t-1) are requested at the END of iteration t+1: ptxas sinks a load towards its
+  // first use but not across the loop's back edge, so they are in flight for a whole sweep.
+  {
+    const bool p0 = Tw >= 2 && Tw - 2 < T;
+    load_row(C.lam_comb + (long long)c_pre * SP, p0, lam);
+    load_row(alpha + (row0 + Tw - 2) * SP, p0, an);
+    if (Tw >= 3 && Tw - 3 < T) c_pre = __ldg(cfg + Tw - 3);
+  }
   for (int t = Tw - 1; t >= 1; t--) {
-    const bool on = t < T;
-    const bool pre = t - 1 < T;             // slice t-1 exists for this row
-    const bool first_next = t - 1 == T - 1; // ... and is the row's last slice: beta = 1 there
-    load_row(C.lam_comb + (long long)c_pre * SP, pre, lam);   // lambda_{t-1}, used late in the sweep
-    if (t >= 2 && t - 2 < T) c_pre = __ldg(cfg + t - 2);
-#pragma unroll
-    for (int n = 0; n < NT; n++) u[n][0] = u[n][1] = 0.0;
-    double d0 = 0, d1 = 0, h = 1.0;
-    mma_sweep<NT>(u, r, frag, [&](int ks) {   // u = r . A^T  (k = current state, n = previous state)
-      if (ks == 0) {
-        emit_post(t, on);
-        load_row(alpha + (row0 + t - 1) * SP, pre, a);   // alpha_{t-1} for the next round
-#pragma unroll
-        for (int n = 0; n < NT; n++) {        // sum of the sweep's result, known in advance
-          const double2 v = csv[4 * n + q];
-          d0 += r[n][0] * v.x;
-          d1 += r[n][1] * v.y;
-        }
-      }
-      if (ks == 2 * NT - 1) {
-        h = safe_rcp(quad_sum_full(d0 + d1));
-        const double hs = first_next ? 1.0 : h;
-#pragma unroll
-        for (int n = 0; n < NT; n++) { lam[n][0] *= hs; lam[n][1] *= hs; }
-      }
-    });
+    on = t < T;
+    pre = t - 1 < T;                 // slice t-1 exists for this row
+    first_next = t - 1 == T - 1;     // ... and is the row's last slice: beta = 1 there
+    t_cur = t;
+    // u = r . A^T  (k = current state, n = previous state)
+    mma_sweep<NT>(u, r, frag, [&](auto sc) { run_items<2 * NT * NT, W_ITEMS, decltype(sc)::value>(item); });
     if (EM) {  // a = own_{t-1} (loaded in the sweep), u = A . r_t
       double z0 = 0, z1 = 0;
 #pragma unroll
@@ -495,8 +594,18 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
       r[n][0] = first_next ? lam[n][0] : u[n][0] * lam[n][0];
       r[n][1] = first_next ? lam[n][1] : u[n][1] * lam[n][1];
     }
+    {  // requests for iteration t-1: lambda_{t-2}, alpha_{t-2}, evidence index of slice t-3
+      const bool p2 = t >= 2 && t - 2 < T;
+      load_row(C.lam_comb + (long long)c_pre * SP, p2, lam);
+      load_row(alpha + (row0 + t - 2) * SP, p2, an);
+      if (t >= 3 && t - 3 < T) c_pre = __ldg(cfg + t - 3);
+    }
   }
-  if (Tw >= 1) emit_post(0, 0 < T);
+  if (Tw >= 1) {   // posterior of slice 0
+    on = 0 < T;
+    t_cur = 0;
+    static_for<0, I_LD>(item);
+  }
   if (EM && Tw >= 1) {  // first slice: joint = A0 * r_0 / (phi0 . r_0)
     double z0 = 0, z1 = 0;
 #pragma unroll
