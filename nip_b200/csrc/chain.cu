@@ -647,11 +647,14 @@ __global__ void __launch_bounds__(32 * NT) k_chain_counts(const double* __restri
 #pragma unroll
   for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
   for (long long k0 = k_begin; k0 < k_end; k0 += KC) {
-    for (int x = threadIdx.x; x < KC * SP; x += blockDim.x) {
-      const int i = x / SP, c = x - i * SP;
+    for (int x = threadIdx.x; x < KC * (SP / 2); x += blockDim.x) {
+      const int i = x / (SP / 2), c = 2 * (x - i * (SP / 2));
       const long long k = k0 + i;
-      sR[i * LD + c] = k < k_end ? rt[k * SP + c] : 0.0;
-      sA[i * LD + c] = (k < k_end && k >= 1) ? own[(k - 1) * SP + c] : 0.0;
+      const double2 vr = k < k_end ? __ldg(reinterpret_cast<const double2*>(rt + k * SP + c)) : make_double2(0.0, 0.0);
+      const double2 va = (k < k_end && k >= 1) ? __ldg(reinterpret_cast<const double2*>(own + (k - 1) * SP + c))
+                                               : make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(sR + i * LD + c) = vr;
+      *reinterpret_cast<double2*>(sA + i * LD + c) = va;
     }
     __syncthreads();
 #pragma unroll
@@ -680,13 +683,14 @@ __global__ void k_chain_sum_parts(const double* part, int parts, long long n, do
   }
 }
 
-// g0[ip] = sum over series of r0[series][ip]
+// g0[ip] = sum over series of r0[series][ip]   (one block per column, fixed reduction order)
 __global__ void k_chain_g0(const double* r0, int n_series, int SP, double* g0) {
-  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip >= SP) return;
+  __shared__ double red[40];
+  const int ip = blockIdx.x;
   double s = 0;
-  for (int b = 0; b < n_series; b++) s += r0[(long long)b * SP + ip];
-  g0[ip] = s;
+  for (int b = threadIdx.x; b < n_series; b += blockDim.x) s += r0[(long long)b * SP + ip];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) g0[ip] = s;
 }
 
 // Cc[c][ip] += posterior rows grouped by their combined evidence index; every warp owns a
@@ -702,9 +706,18 @@ __global__ void k_chain_leafcount(const double* __restrict__ postj, const int* _
   const long long nwarps = (long long)gridDim.x * nw, me = (long long)blockIdx.x * nw + w;
   const long long per = (rows + nwarps - 1) / nwarps;
   const long long k_end = (me + 1) * per < rows ? (me + 1) * per : rows;
-  for (long long k = me * per; k < k_end; k++) {
-    double* dst = mine + cfg[k] * SP;
-    for (int c = lane; c < SP; c += 32) dst[c] += postj[k * SP + c];
+  constexpr int U = 8;                       // rows in flight: the loads are issued before any is used
+  for (long long k0 = me * per; k0 < k_end; k0 += U) {
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) c[u] = k0 + u < k_end ? __ldg(cfg + k0 + u) : 0;
+    for (int col = lane; col < SP; col += 32) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = k0 + u < k_end ? __ldg(postj + (k0 + u) * SP + col) : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; u++) mine[c[u] * SP + col] += v[u];   // in row order: deterministic
+    }
   }
   __syncthreads();
   double* out = part + (long long)blockIdx.x * tab;
@@ -774,13 +787,12 @@ __global__ void k_chain_family(const double* E, const int* pbase, const int* pof
 }
 
 __global__ void k_chain_tail(const double* ll, const int* status, int n_series, double* tail) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double L = 0;
-    int bad = 0;
-    for (int s = 0; s < n_series; s++) { L += ll[s]; bad |= status[s]; }
-    tail[0] = L;
-    tail[1] = bad ? 1.0 : 0.0;
-  }
+  __shared__ double red[40];
+  double L = 0, bad = 0;
+  for (int i = threadIdx.x; i < n_series; i += blockDim.x) { L += ll[i]; bad += status[i] ? 1.0 : 0.0; }
+  L = block_sum(L, red);
+  bad = block_sum(bad, red);
+  if (threadIdx.x == 0) { tail[0] = L; tail[1] = bad != 0 ? 1.0 : 0.0; }
 }
 
 template <class K>
@@ -1219,7 +1231,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   if (int e = chain_prepare_evidence(cm, cb, plan, a, st)) return e;
 
   const long long rows = std::max<long long>(a.rows, 1);
-  const int parts = std::max(1, x.sm_count);
+  const int parts = std::max(1, x.sm_count) * 4;   // CTAs of the split-K count GEMM (4 per SM)
   if (!cb.d_postj) {
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_postj, rows * SP * sizeof(double)));
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_rt, rows * SP * sizeof(double)));
@@ -1267,14 +1279,14 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   }
   k_chain_sum_parts<<<(unsigned)((n_G + 255) / 256), 256, 0, st>>>(partG, parts, (long long)n_G, G);
   NIPGPU_LAUNCHED();
-  k_chain_g0<<<(SP + 63) / 64, 64, 0, st>>>(cb.d_r0, a.n_series, SP, g0);
+  k_chain_g0<<<SP, 256, 0, st>>>(cb.d_r0, a.n_series, SP, g0);
   NIPGPU_LAUNCHED();
   {
     const size_t smem = (size_t)lc_warps * tab * sizeof(double);
     if (int e2 = set_smem(k_chain_leafcount, smem)) return e2;
-    k_chain_leafcount<<<parts, 32 * lc_warps, smem, st>>>(cb.d_postj, cb.d_cfg, a.rows, plan.n_comb, SP, partC);
+    k_chain_leafcount<<<x.sm_count, 32 * lc_warps, smem, st>>>(cb.d_postj, cb.d_cfg, a.rows, plan.n_comb, SP, partC);
     NIPGPU_LAUNCHED();
-    k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, parts, (long long)tab, Cc);
+    k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, x.sm_count, (long long)tab, Cc);
     NIPGPU_LAUNCHED();
   }
   if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
@@ -1311,7 +1323,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
                                                       p.R, x.pseudo, x.d_counts + hm.coff[v]);
     NIPGPU_LAUNCHED();
   }
-  k_chain_tail<<<1, 32, 0, st>>>(a.d_ll, a.d_status, a.n_series, x.d_counts + hm.coff[hm.nv]);
+  k_chain_tail<<<1, 512, 0, st>>>(a.d_ll, a.d_status, a.n_series, x.d_counts + hm.coff[hm.nv]);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
