@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace nipgpu {
@@ -38,7 +39,10 @@ int choose_launch(nipgpu_model* m) {
   JtLaunch& l = m->launch;
   l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
   const size_t bytes = jt_work_doubles(m->prog) * sizeof(double);
-  if (bytes <= 200 * 1024) {
+  // NIPGPU_FORCE_HBM_WORKSPACE=1 exercises the large-clique path (tables in a per-CTA HBM
+  // workspace instead of shared memory) on small models; used by the tests only
+  const char* force = getenv("NIPGPU_FORCE_HBM_WORKSPACE");
+  if (bytes <= 200 * 1024 && !(force && force[0] == '1')) {
     l.smem_bytes = bytes;
     l.gwork = nullptr;
     const int by_smem = (int)std::max<size_t>(1, (220 * 1024) / (bytes + 1024));
@@ -681,44 +685,22 @@ int nipgpu_slice_get_clique(nipgpu_model* m, int32_t clique, double* out) {
 int nipgpu_slice_mass(nipgpu_model* m, double* mass) {
   if (!m || !mass) return fail(NIPGPU_EINVAL, "bad arguments");
   if (!m->slice_consistent) return fail(NIPGPU_EINVAL, "call nipgpu_slice_make_consistent first");
-  // nip_probability_mass: sum of cliques - sum of sepsets (src/nipjointree.c:1156-1188)
-  const HostModel& hm = m->hm;
-  std::vector<double> tab(m->prog.tab_total), msg(std::max(hm.msg_total, 1));
   NIPGPU_CUDA(cudaSetDevice(m->device));
-  NIPGPU_CUDA(cudaMemcpy(tab.data(), m->d_slice_tab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  if (hm.msg_total)
-    NIPGPU_CUDA(cudaMemcpy(msg.data(), m->d_slice_msg, (size_t)hm.msg_total * sizeof(double), cudaMemcpyDeviceToHost));
-  double r = 0;
-  for (int c = 0; c < hm.nc; c++) {
-    double x = 0;
-    for (int i = 0; i < hm.csize[c]; i++) x += tab[m->tab_off[c] + i];
-    r += x;
-  }
-  for (int s = 0; s < hm.ns; s++) {
-    double x = 0;
-    for (int i = 0; i < hm.ssize[s]; i++) x += msg[hm.sep_slot[s] + i];
-    r -= x;
-  }
-  *mass = r;
+  double* d_out = m->d_slice_start;  // scratch: the start tables are dead once the slice is consistent
+  if (int e = jt_mass(m->d_slice_tab, m->prog.tab_total, m->d_slice_msg, m->hm.msg_total, d_out, m->stream)) return e;
+  NIPGPU_CUDA(cudaMemcpyAsync(mass, d_out, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
   return NIPGPU_OK;
 }
 
 int nipgpu_slice_marginal(nipgpu_model* m, int32_t var, double* out) {
   if (!m || var < 0 || var >= m->hm.nv || !out) return fail(NIPGPU_EINVAL, "bad arguments");
   if (!m->slice_consistent) return fail(NIPGPU_EINVAL, "call nipgpu_slice_make_consistent first");
-  const HostModel& hm = m->hm;
-  const int c = hm.family[var];
-  std::vector<double> tab(hm.csize[c]);
   NIPGPU_CUDA(cudaSetDevice(m->device));
-  NIPGPU_CUDA(cudaMemcpy(tab.data(), m->d_slice_tab + m->tab_off[c], tab.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  int stride = 1;
-  for (int j = 0; j < hm.var_pos(c, var); j++) stride *= hm.card[hm.clique_vars(c)[j]];
-  double sum = 0;
-  for (int i = 0; i < hm.card[var]; i++) out[i] = 0;
-  for (int i = 0; i < hm.csize[c]; i++) out[(i / stride) % hm.card[var]] += tab[i];
-  for (int i = 0; i < hm.card[var]; i++) sum += out[i];
-  if (sum != 0)
-    for (int i = 0; i < hm.card[var]; i++) out[i] /= sum;
+  double* d_out = m->d_slice_start;
+  if (int e = jt_marginal(m->prog, m->d_slice_tab, m->hm.proj_var[var], d_out, m->stream)) return e;
+  NIPGPU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m->hm.card[var] * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
   return NIPGPU_OK;
 }
 

@@ -341,6 +341,23 @@ __global__ void k_jt_slice(DProgram P, double* gwork, const double* start, doubl
   for (int i = threadIdx.x; i < P.msg_total; i += blockDim.x) out_msgs[i] = w.msg[i];
 }
 
+// single-slice API: mass = sum of cliques - sum of sepsets (nip_probability_mass,
+// src/nipjointree.c:1156-1188) of the consistent tables left by k_jt_slice
+__global__ void k_jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out) {
+  __shared__ double red[40];
+  const double a = vec_sum(tables, n_tab, red);
+  const double b = vec_sum(msgs, n_msg, red);
+  if (threadIdx.x == 0) *out = a - b;
+}
+
+// get_probability (src/nip.c:2261-2298): normalised one-variable marginal of the family clique
+__global__ void k_jt_marginal(DProgram P, const double* tables, int pj, double* out) {
+  __shared__ double red[40];
+  const int m = P.projs[pj].m;
+  op_marg(P, tables, pj, out);
+  vec_normalise(out, m, red);
+}
+
 template <class K>
 int prep_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024)
@@ -380,6 +397,18 @@ int jt_likelihood(const DProgram& p, const DBatch& b, const int* proj_off, const
 int jt_calibrate(const DProgram& p, const JtLaunch& l, double* R1, double* m1_0, cudaStream_t st) {
   if (int e = prep_smem(k_jt_calibrate, l.smem_bytes)) return e;
   k_jt_calibrate<<<1, l.threads, l.smem_bytes, st>>>(p, l.gwork, R1, m1_0);
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
+int jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out, cudaStream_t st) {
+  k_jt_mass<<<1, 256, 0, st>>>(tables, n_tab, msgs, n_msg, out);
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
+int jt_marginal(const DProgram& p, const double* tables, int proj, double* out, cudaStream_t st) {
+  k_jt_marginal<<<1, 128, 0, st>>>(p, tables, proj, out);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }

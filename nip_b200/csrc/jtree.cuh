@@ -79,4 +79,8 @@ int jt_calibrate(const DProgram& p, const JtLaunch& l, double* R1, double* m1_0,
 int jt_slice(const DProgram& p, const JtLaunch& l, const double* start_tables, double* out_tables,
              double* out_msgs, cudaStream_t st);
 
+// reductions of the single-slice API on the consistent tables (device side)
+int jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out, cudaStream_t st);
+int jt_marginal(const DProgram& p, const double* tables, int proj, double* out, cudaStream_t st);
+
 }  // namespace nipgpu

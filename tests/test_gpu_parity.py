@@ -104,6 +104,26 @@ def test_hmm_vs_oracle(gpu_lib, oracle_lib, engine, S, M, B, T):
         assert_close(fll[i], llw, "HMM-%d series %d loglik (filter)" % (S, i))
 
 
+@pytest.mark.parametrize("name", ["demo1_net", "coupled2x3"])
+def test_hbm_workspace_path(gpu_lib, name, monkeypatch):
+    """cliques too large for shared memory are staged in a per-CTA HBM workspace (config C3's
+    16^6-entry cliques); force that path on small models and check it against the goldens"""
+    monkeypatch.setenv("NIPGPU_FORCE_HBM_WORKSPACE", "1")
+    c = Case(name)
+    m = gpu_lib.Model(c.fm, engine=1)
+    b = m.batch(c.obs_vars, c.series)
+    posts, lls = c.expected("smooth")
+    post, ll = b.infer(c.query)
+    for i, got in enumerate(b.split(post)):
+        assert_close(got, posts[i], "%s series %d posterior (HBM workspace)" % (name, i))
+    assert_close(ll, lls, "%s loglik (HBM workspace)" % name)
+    it = c.j["em"]["iters"][0]
+    m.mstep(unhex(c.j["em"]["init"]))
+    counts, L, st = b.estep()
+    assert st == 0
+    assert_close(counts, unhex(it["counts"]), "%s expected counts (HBM workspace)" % name)
+
+
 def test_empty_and_single_slice(gpu_lib):
     c = Case("hmm5")
     m = gpu_lib.Model(c.fm)
