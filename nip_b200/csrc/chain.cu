@@ -877,8 +877,10 @@ std::string chain_build(HostModel& hm, ChainModel& cm) {
   const int S = hm.S;
   int SP = 8;
   while (SP < S) SP *= 2;
-  if (SP > 64) return "interface larger than 64 states: warp-resident DMMA path not applicable";
-  cm.S = S; cm.SP = SP; cm.NT = SP / 8; cm.c0 = hm.in_clique;
+  cm.dense = SP > 64;          // large interface: per-slice tiled GEMM (dense.cu)
+  if (cm.dense) SP = (S + 127) / 128 * 128;
+  if (SP > 4096) return "interface larger than 4096 states";
+  cm.S = S; cm.SP = SP; cm.NT = cm.dense ? 0 : SP / 8; cm.c0 = hm.in_clique;
   const int c0 = cm.c0, nd = hm.clique_dim(c0);
   // entry -> (previous-slice interface state, current interface state)
   std::vector<int> istride_prev(hm.nv, 0), istride_cur(hm.nv, 0);
@@ -1016,9 +1018,13 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_Bb0, 0, sp2 * sizeof(double), st));
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_phi0, 0, cm.SP * sizeof(double), st));
   const int S = cm.S;
-  k_chain_mats<<<(S * S + 255) / 256, 256, 0, st>>>(d_base0 + tab_off[cm.c0], d_base1 + tab_off[cm.c0],
-                                                    cm.d_ent_of, S, cm.NT, cm.d_Bf1, cm.d_Bb1, cm.d_Bb0);
-  NIPGPU_LAUNCHED();
+  if (cm.dense) {
+    if (int e = dense_refresh_mats(cm, d_base1 + tab_off[cm.c0], st)) return e;
+  } else {
+    k_chain_mats<<<(S * S + 255) / 256, 256, 0, st>>>(d_base0 + tab_off[cm.c0], d_base1 + tab_off[cm.c0],
+                                                      cm.d_ent_of, S, cm.NT, cm.d_Bf1, cm.d_Bb1, cm.d_Bb0);
+    NIPGPU_LAUNCHED();
+  }
   k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base0 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_phi0);
   NIPGPU_LAUNCHED();
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_colsum, 0, cm.SP * sizeof(double), st));
@@ -1120,6 +1126,7 @@ void chain_batch_free(ChainBatch& cb) {
   cudaFree(cb.d_order); cudaFree(cb.d_len_sorted); cudaFree(cb.d_cfg); cudaFree(cb.d_alpha);
   cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_rows); cudaFree(cb.d_comb);
   cudaFree(cb.d_postj); cudaFree(cb.d_rt); cudaFree(cb.d_r0); cudaFree(cb.d_em_scratch);
+  cudaFree(cb.d_dense); cudaFree(cb.d_dense_i);
   cb = ChainBatch();
 }
 
@@ -1192,6 +1199,11 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   C.R1 = cm.d_R1; C.colsum = cm.d_colsum; C.m1_0 = cm.m1_0; C.lam_comb = cb.d_comb;
   if (a.n_series == 0) return NIPGPU_OK;
   if (ev0) NIPGPU_CUDA(cudaEventRecord(ev0, st));
+  if (cm.dense) {
+    if (int e = dense_infer(cm, cb, plan, a, st)) return e;
+    if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
+    return NIPGPU_OK;
+  }
   int e = NIPGPU_OK;
   switch (cm.NT) {
     case 1: e = launch_forward<1>(C, B, a, cb.d_alpha, st); break;
@@ -1222,6 +1234,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
                 const ChainEmArgs& x, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
   const ChainInferArgs& a = x.base;
   const int SP = cm.SP, S = cm.S;
+  if (cm.dense) return NIPGPU_EUNSUPPORTED;   // EM for |I| > 64 goes through the generic engine
   const size_t tab = (size_t)plan.n_comb * SP;
   int lc_warps = 8;
   while (lc_warps > 1 && lc_warps * tab * sizeof(double) > 200 * 1024) lc_warps /= 2;

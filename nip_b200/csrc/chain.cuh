@@ -35,7 +35,8 @@ struct ChainLeafHost {
 
 struct ChainModel {
   bool ok = false;
-  int S = 0, SP = 0, NT = 0;   // interface size, padded size (8*NT)
+  bool dense = false;          // |I| > 64: per-slice tiled DMMA GEMM (dense.cu) instead of warp-resident recursion
+  int S = 0, SP = 0, NT = 0;   // interface size, padded size (8*NT; multiple of 128 when dense)
   int c0 = -1;
   std::vector<ChainLeafHost> leaves;  // real leaves first, then pseudo leaves
   int n_real = 0;
@@ -68,6 +69,9 @@ struct ChainBatch {
   int* d_cols = nullptr;           // column metadata of the cached plan
   long long* d_rows = nullptr;
   std::vector<int> plan_key;       // identifies the cached plan
+  // dense engine (dense.cu): per-sequence state, beta / R rows
+  double* d_dense = nullptr;
+  int* d_dense_i = nullptr;
   // EM (chain_estep)
   double *d_postj = nullptr, *d_rt = nullptr, *d_r0 = nullptr, *d_em_scratch = nullptr;
   size_t em_scratch_cap = 0;
@@ -113,6 +117,10 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
 int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
                 const ChainInferArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 void chain_batch_free(ChainBatch& cb);
+// dense.cu
+int dense_refresh_mats(const ChainModel& cm, const double* d_base1_c0, cudaStream_t st);
+int dense_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan, const ChainInferArgs& a,
+                cudaStream_t st);
 
 struct ChainEmArgs {
   ChainInferArgs base;           // d_post / forward_only unused
