@@ -192,6 +192,20 @@ def main():
     make_case(R, "coupled2x3", write("coupled.net", text), ["YA", "YB"], series, ["A1", "B1", "A0", "YA"],
               em_seed=3, likelihood_marked=["YA", "YB"])
 
+    # 6b. config C3's topology in small: 4 chains, ring-coupled X^i_t | X^i_{t-1}, X^{i-1}_{t-1},
+    #     per-chain observations; the reference's triangulation yields 3^6-entry cliques
+    r5 = np.random.default_rng(15)
+    K, ns, ny = 4, 3, 2
+    nodes = [("Y%d" % i, ny, None) for i in range(K)] + [("X%d" % i, ns, None) for i in range(K)] + \
+            [("W%d" % i, ns, "X%d" % i) for i in range(K)]
+    pots = [("Y%d" % i, ["X%d" % i], r5.random((ns, ny)) + 0.05) for i in range(K)]
+    pots += [("X%d" % i, ["W%d" % ((i - 1) % K), "W%d" % i], r5.random((ns, ns, ns)) + 0.05) for i in range(K)]
+    pots += [("W%d" % i, [], (r5.random(ns) + 0.1)[None, :]) for i in range(K)]
+    text = net_text_generic(nodes, pots)
+    series = rand_series(r5, [ny] * K, 5, 1, 6, 0.15)
+    make_case(R, "factorial4x3", write("fact.net", text), ["Y%d" % i for i in range(K)], series,
+              ["X0", "X3", "W1", "Y2"], em_seed=21, likelihood_marked=["Y0", "Y1"])
+
     # 7. no time-slice interface at all: independent slices (scalar alpha)
     r4 = np.random.default_rng(14)
     text = net_text_generic(
