@@ -133,6 +133,11 @@ def cpu_reference(h, data, steps=1, warmup=0, budget_s=12.0):
 
 # ------------------------------------------------------------------- main ---
 def main():
+    # Everything that libraries print (NCCL's version banner, warnings) goes to stderr: stdout
+    # carries exactly one JSON line.
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -152,14 +157,14 @@ def main():
             return
         h, data = make_workload()
         val, cores, kind, what, ms = cpu_reference(h, data, steps=max(1, args.steps), warmup=args.warmup)
-        print(json.dumps({
+        print(file=json_out, flush=True, *[json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": "slice-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": WORKLOAD, "sample": what},
             "cpu_baseline": {"value": val, "unit": "slice-steps/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": val, "unit": "slice-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})])
         return
 
     import torch
@@ -290,7 +295,7 @@ def main():
     if not args.no_cpu_baseline:
         v, cores, kind, what, _ = cpu_reference(h, data)
         out["cpu_baseline"] = {"value": v, "unit": "slice-steps/s", "cores": cores, "kind": kind, "sample": what}
-    print(json.dumps(out))
+    print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
