@@ -37,30 +37,66 @@ int choose_launch(nipgpu_model* m) {
   int biggest = 1;
   for (int c = 0; c < hm.nc; c++) biggest = std::max(biggest, hm.csize[c]);
   JtLaunch& l = m->launch;
-  l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
-  const size_t bytes = jt_work_doubles(m->prog) * sizeof(double);
-  // NIPGPU_FORCE_HBM_WORKSPACE=1 exercises the large-clique path (tables in a per-CTA HBM
-  // workspace instead of shared memory) on small models; used by the tests only
+  l = JtLaunch{};
+  const size_t work = jt_work_doubles(m->prog);
+  const size_t bytes = work * sizeof(double);
+  // NIPGPU_JT_MODE = warp | cta | hbm | grid overrides the choice below; the tests use it to run
+  // every mode on small models (NIPGPU_FORCE_HBM_WORKSPACE=1 is the older spelling of "hbm")
+  const char* env = getenv("NIPGPU_JT_MODE");
+  std::string want = env ? env : "";
   const char* force = getenv("NIPGPU_FORCE_HBM_WORKSPACE");
-  if (bytes <= 200 * 1024 && !(force && force[0] == '1')) {
+  if (want.empty() && force && force[0] == '1') want = "hbm";
+  if (want.empty()) {
+    if (biggest <= 64 && bytes <= 8 * 1024) want = "warp";
+    else if (bytes <= 200 * 1024) want = "cta";
+    else if (biggest >= (1 << 18)) want = "grid";
+    else want = "hbm";
+  }
+  if ((want == "warp" && bytes > 24 * 1024) || (want == "cta" && bytes > 200 * 1024))
+    return fail(NIPGPU_EINVAL, "NIPGPU_JT_MODE: the tables of this model do not fit shared memory");
+  auto need_gwork = [&](size_t doubles) {
+    if (m->gwork_doubles >= doubles) return NIPGPU_OK;
+    cudaFree(m->d_gwork);
+    m->d_gwork = nullptr;
+    m->gwork_doubles = 0;
+    NIPGPU_CUDA(cudaMalloc((void**)&m->d_gwork, doubles * sizeof(double)));
+    m->gwork_doubles = doubles;
+    return NIPGPU_OK;
+  };
+  if (want == "warp") {
+    l.mode = JT_MODE_WARP;
+    int wpc = 8;
+    while (wpc > 1 && wpc * bytes > 64 * 1024) wpc /= 2;
+    l.threads = 32 * wpc;
+    l.smem_bytes = wpc * bytes;
+    const int by_smem = (int)std::max<size_t>(1, (200 * 1024) / (l.smem_bytes + 1024));
+    l.grid = m->sm_count * std::max(1, std::min({by_smem, 2048 / l.threads, 32}));
+  } else if (want == "cta") {
+    l.mode = JT_MODE_CTA;
+    l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
     l.smem_bytes = bytes;
-    l.gwork = nullptr;
     const int by_smem = (int)std::max<size_t>(1, (220 * 1024) / (bytes + 1024));
-    const int by_threads = 2048 / l.threads;
-    l.grid = m->sm_count * std::max(1, std::min({by_smem, by_threads, 16}));
+    l.grid = m->sm_count * std::max(1, std::min({by_smem, 2048 / l.threads, 16}));
+  } else if (want == "grid") {
+    l.mode = JT_MODE_GRID;
+    l.threads = 256;
+    l.grid = jt_grid_ctas(l.threads, m->sm_count);
+    const size_t part = 2 * (size_t)l.grid + 8, scratch = (size_t)l.grid * l.threads;
+    if (int e = need_gwork(work + part + scratch)) return e;
+    l.gwork = m->d_gwork;
+    l.part = m->d_gwork + work;
+    l.scratch = l.part + part;
   } else {
-    l.smem_bytes = 0;
+    l.mode = JT_MODE_CTA;
+    l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
     size_t ctas = (size_t)m->sm_count * 2;
     const size_t budget = (size_t)32 << 30;  // keep the workspace under 32 GB
     while (ctas > 1 && ctas * bytes > budget) ctas /= 2;
-    if (m->gwork_doubles < ctas * jt_work_doubles(m->prog)) {
-      cudaFree(m->d_gwork);
-      m->gwork_doubles = ctas * jt_work_doubles(m->prog);
-      NIPGPU_CUDA(cudaMalloc((void**)&m->d_gwork, m->gwork_doubles * sizeof(double)));
-    }
+    if (int e = need_gwork(ctas * work)) return e;
     l.gwork = m->d_gwork;
     l.grid = (int)ctas;
   }
+  l.slots = l.mode == JT_MODE_WARP ? l.grid * (l.threads / 32) : l.mode == JT_MODE_GRID ? 1 : l.grid;
   return NIPGPU_OK;
 }
 
@@ -86,9 +122,8 @@ int refresh_derived(nipgpu_model* m) {
   for (int k = 0; k < np; k++)
     if (hm.flags[hm.prior_vars[k]] & NIPGPU_IF_OLD_OUTGOING)
       if (int e = apply(m->d_base0, k)) return e;
-  JtLaunch one = m->launch;
-  if (one.gwork == nullptr && one.smem_bytes == 0) return fail(NIPGPU_EINVAL, "launch not configured");
-  if (int e = jt_calibrate(m->prog, one, m->d_R1, m->d_m10, st)) return e;
+  if (m->launch.gwork == nullptr && m->launch.smem_bytes == 0) return fail(NIPGPU_EINVAL, "launch not configured");
+  if (int e = jt_calibrate(m->prog, m->launch, m->d_R1, m->d_m10, st)) return e;
   if (m->chain.ok)
     if (int e = chain_refresh(hm, m->chain, m->d_base0, m->d_base1, m->tab_off, m->d_ipool, m->d_R1, m->d_m10, st)) return e;
   NIPGPU_CUDA(cudaStreamSynchronize(st));
@@ -197,8 +232,7 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
   if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;
   if (int e = ensure_alpha(m, b)) return e;
   const DBatch B = dev_batch(b, obs_proj);
-  JtLaunch l = m->launch;
-  l.grid = std::max(1, std::min(l.grid, b->n_series));
+  const JtLaunch l = jt_fit(m->launch, b->n_series);
   NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
   if (int e = jt_forward(m->prog, B, Q, l, want_ll, forward_only, b->d_alpha, forward_only ? post : nullptr,
                          b->d_ll, b->d_status, m->stream)) return e;
@@ -510,20 +544,19 @@ int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidenc
   if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;
   if (int e = ensure_alpha(m, b)) return e;
   const DBatch B = dev_batch(b, obs_proj);
-  JtLaunch l = m->launch;
-  l.grid = std::max(1, std::min(l.grid, std::max(b->n_series, 1)));
-  if (m->acc_groups < (size_t)l.grid) {
+  const JtLaunch l = jt_fit(m->launch, b->n_series);
+  if (m->acc_groups < (size_t)l.slots) {
     cudaFree(m->d_acc);
-    m->acc_groups = l.grid;
+    m->acc_groups = l.slots;
     NIPGPU_CUDA(cudaMalloc((void**)&m->d_acc, m->acc_groups * (size_t)n * sizeof(double)));
   }
-  NIPGPU_CUDA(cudaMemsetAsync(m->d_acc, 0, (size_t)l.grid * n * sizeof(double), m->stream));
+  NIPGPU_CUDA(cudaMemsetAsync(m->d_acc, 0, (size_t)l.slots * n * sizeof(double), m->stream));
   DQuery Q{};
   NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
   if (int e = jt_forward(m->prog, B, Q, l, 1, 0, b->d_alpha, nullptr, b->d_ll, b->d_status, m->stream)) return e;
   if (int e = jt_backward(m->prog, B, Q, l, b->d_alpha, nullptr, m->d_acc, n, m->stream)) return e;
   NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
-  if (int e = finish_estep(m->d_acc, l.grid, n, n, add_pseudocount ? 1.0 : 0.0, b->d_ll, b->d_status,
+  if (int e = finish_estep(m->d_acc, l.slots, n, n, add_pseudocount ? 1.0 : 0.0, b->d_ll, b->d_status,
                            b->n_series, m->d_counts, m->stream)) return e;
   double tail[2] = {0, 0};
   NIPGPU_CUDA(cudaMemcpyAsync(tail, m->d_counts + n, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -584,8 +617,7 @@ int nipgpu_likelihood(nipgpu_model* m, nipgpu_batch* b, const uint8_t* evidence_
   if (int e = upload_obs_proj(m, b, evidence_on, false, 2, &p_on)) return e;
   if (!b->d_like) NIPGPU_CUDA(cudaMalloc((void**)&b->d_like, std::max<size_t>((size_t)b->rows * 2, 1) * sizeof(double)));
   const DBatch B = dev_batch(b, nullptr);
-  JtLaunch l = m->launch;
-  l.grid = std::max(1, std::min(l.grid, std::max(b->n_series, 1)));
+  const JtLaunch l = jt_fit(m->launch, b->n_series);
   NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
   if (int e = jt_likelihood(m->prog, B, p_off, p_on, l, b->d_like, m->stream)) return e;
   NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));

@@ -17,9 +17,23 @@
 // The slice always restarts from the shared base tables (original_p x priors),
 // which is what reset_model + use_priors produce (src/nip.c:61-119), so
 // nip_retract_potential / nip_global_retraction never touch HBM.
+//
+// Every kernel is written once against a "team" — the set of threads that owns
+// one sequence at a time — and instantiated three ways:
+//   WarpTeam  one warp per sequence, tables in that warp's slice of shared
+//             memory (models whose cliques are a few dozen entries: C1/C5);
+//   CtaTeam   one CTA per sequence, tables in shared memory or, when they do
+//             not fit, in a per-CTA HBM workspace;
+//   GridTeam  the whole (cooperative) grid streams ONE sequence's tables
+//             through HBM — cliques of millions of entries (C3: 16^6).
 #include "jtree.cuh"
 
+#include <cooperative_groups.h>
+
+#include <algorithm>
 #include <cfloat>
+
+namespace cg = cooperative_groups;
 
 namespace nipgpu {
 
@@ -39,191 +53,304 @@ __device__ __forceinline__ Work carve(const DProgram& P, double* W) {
   return w;
 }
 
-__device__ __forceinline__ void load_tables(const DProgram& P, double* tab, const double* src) {
-  for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) tab[i] = src[i];
-  __syncthreads();
+struct WarpTeam {
+  static constexpr bool kGrid = false;
+  __device__ WarpTeam(double*, double*, double*) {}
+  __device__ int tid() const { return threadIdx.x & 31; }
+  __device__ int size() const { return 32; }
+  __device__ void sync() const { __syncwarp(); }
+  __device__ double sum(double v) { return warp_sum(v); }
+  __device__ int slot() const { return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); }
+  __device__ int first() const { return slot(); }
+  __device__ int step() const { return gridDim.x * (blockDim.x >> 5); }
+  __device__ double* work(double* gwork, double* smem, size_t wstride) const {
+    return smem + (size_t)(threadIdx.x >> 5) * wstride;
+  }
+};
+
+struct CtaTeam {
+  static constexpr bool kGrid = false;
+  double* red;
+  __device__ CtaTeam(double* r, double*, double*) : red(r) {}
+  __device__ int tid() const { return threadIdx.x; }
+  __device__ int size() const { return blockDim.x; }
+  __device__ void sync() const { __syncthreads(); }
+  __device__ double sum(double v) { return block_sum(v, red); }
+  __device__ int slot() const { return blockIdx.x; }
+  __device__ int first() const { return blockIdx.x; }
+  __device__ int step() const { return gridDim.x; }
+  __device__ double* work(double* gwork, double* smem, size_t wstride) const {
+    return gwork ? gwork + (size_t)blockIdx.x * wstride : smem;
+  }
+};
+
+// All CTAs of a cooperative launch.  `part` is 2 x gridDim doubles (alternating, so one
+// grid barrier per sum is enough), `scratch` holds size() doubles for two-stage marginals.
+struct GridTeam {
+  static constexpr bool kGrid = true;
+  double *red, *part, *scratch;
+  int flip = 0;
+  __device__ GridTeam(double* r, double* p, double* s) : red(r), part(p), scratch(s) {}
+  __device__ int tid() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+  __device__ int size() const { return gridDim.x * blockDim.x; }
+  __device__ void sync() const { cg::this_grid().sync(); }
+  __device__ double sum(double v) {
+    const double b = block_sum(v, red);
+    double* mine = part + flip * gridDim.x;
+    flip ^= 1;
+    if (threadIdx.x == 0) mine[blockIdx.x] = b;
+    sync();
+    double s = 0;  // every CTA adds the partials in the same order
+    if (threadIdx.x < 32) {
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) s += mine[i];
+      s = warp_sum(s);
+      if (threadIdx.x == 0) red[33] = s;
+    }
+    __syncthreads();
+    return red[33];
+  }
+  __device__ int slot() const { return 0; }
+  __device__ int first() const { return 0; }
+  __device__ int step() const { return 1; }
+  __device__ double* work(double* gwork, double*, size_t) const { return gwork; }
+};
+
+template <class Team>
+__device__ __forceinline__ void load_tables(Team& tm, const DProgram& P, double* tab, const double* src) {
+  for (int i = tm.tid(); i < P.tab_total; i += tm.size()) tab[i] = src[i];
+  tm.sync();
 }
 
 // dst[j] = sum_r T[base[j] + off[r]] — `lanes` threads share one destination
 // entry and combine with a fixed shuffle tree, so the result is deterministic.
-__device__ void op_marg(const DProgram& P, const double* tab, int pj, double* dst) {
+template <class Team>
+__device__ void op_marg(Team& tm, const DProgram& P, const double* tab, int pj, double* dst) {
   const DProj p = P.projs[pj];
   const double* T = tab + p.tab;
   const int* base = P.ipool + p.base;
   const int* off = P.ipool + p.off;
-  const int lanes = p.lanes, per_round = blockDim.x / lanes;
-  const int sub = threadIdx.x % lanes, jj = threadIdx.x / lanes;
-  for (int j0 = 0; j0 < p.m; j0 += per_round) {
-    const int j = j0 + jj;
-    double s = 0;
-    if (j < p.m) {
-      const int b = base[j];
-      for (int r = sub; r < p.R; r += lanes) s += T[b + off[r]];
+  const int lanes = p.lanes, sub = tm.tid() % lanes, grp = tm.tid() / lanes;
+  const int groups = tm.size() / lanes;
+  if constexpr (Team::kGrid) {
+    // The grid has far more threads than a small destination has entries: cut the free
+    // range into C chunks per destination entry (partials in scratch, chunk-major), then
+    // add the chunks of each entry in a fixed order.
+    const int per_lane_min = 8;
+    const int C = max(1, min(groups / max(p.m, 1), p.R / (lanes * per_lane_min)));
+    const int Rc = ((p.R + C - 1) / C + lanes - 1) / lanes * lanes;
+    const int total = p.m * C;
+    double* out = C == 1 ? dst : tm.scratch;
+    for (int g0 = 0; g0 < total; g0 += groups) {
+      const int g = g0 + grp;
+      double s = 0;
+      int c = 0, j = 0;
+      if (g < total) {
+        c = g / p.m;
+        j = g - c * p.m;
+        const int b = base[j], r1 = min(p.R, (c + 1) * Rc);
+        for (int r = c * Rc + sub; r < r1; r += lanes) s += T[b + off[r]];
+      }
+      for (int o = lanes >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (sub == 0 && g < total) out[c * p.m + j] = s;
     }
-    for (int o = lanes >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (sub == 0 && j < p.m) dst[j] = s;
+    if (C > 1) {
+      tm.sync();
+      const int lane = tm.tid() & 31, w = tm.tid() >> 5, nw = tm.size() >> 5;
+      for (int j = w; j < p.m; j += nw) {
+        double s = 0;
+        for (int c = lane; c < C; c += 32) s += tm.scratch[c * p.m + j];
+        s = warp_sum(s);
+        if (lane == 0) dst[j] = s;
+      }
+    }
+  } else {
+    for (int j0 = 0; j0 < p.m; j0 += groups) {
+      const int j = j0 + grp;
+      double s = 0;
+      if (j < p.m) {
+        const int b = base[j];
+        for (int r = sub; r < p.R; r += lanes) s += T[b + off[r]];
+      }
+      for (int o = lanes >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (sub == 0 && j < p.m) dst[j] = s;
+    }
   }
-  __syncthreads();
+  tm.sync();
+}
+
+// entry x of the projection's (j, r) enumeration, fastest index chosen so that
+// consecutive threads touch consecutive addresses
+__device__ __forceinline__ void decode(const DProj& p, int x, int& j, int& r) {
+  if (p.lanes == 1) { r = x / p.m; j = x - r * p.m; } else { j = x / p.R; r = x - j * p.R; }
 }
 
 // T[base[j] + off[r]] *= v[j]
-__device__ void op_absorb(const DProgram& P, double* tab, int pj, const double* v) {
+template <class Team>
+__device__ void op_absorb(Team& tm, const DProgram& P, double* tab, int pj, const double* v) {
   const DProj p = P.projs[pj];
   double* T = tab + p.tab;
   const int* base = P.ipool + p.base;
   const int* off = P.ipool + p.off;
   const int n = p.m * p.R;
-  if (p.lanes == 1) {  // destination holds the fastest dimension: j fastest
-    for (int x = threadIdx.x; x < n; x += blockDim.x) {
-      const int r = x / p.m, j = x - r * p.m;
-      T[base[j] + off[r]] *= v[j];
-    }
-  } else {
-    for (int x = threadIdx.x; x < n; x += blockDim.x) {
-      const int j = x / p.R, r = x - j * p.R;
-      T[base[j] + off[r]] *= v[j];
-    }
+  for (int x = tm.tid(); x < n; x += tm.size()) {
+    int j, r;
+    decode(p, x, j, r);
+    T[base[j] + off[r]] *= v[j];
   }
-  __syncthreads();
+  tm.sync();
 }
 
 // T[..] = T[..] * num[j] / den[j], and 0 where den[j] == 0
-__device__ void op_absorb_ratio(const DProgram& P, double* tab, int pj, const double* num,
+template <class Team>
+__device__ void op_absorb_ratio(Team& tm, const DProgram& P, double* tab, int pj, const double* num,
                                 const double* den) {
   const DProj p = P.projs[pj];
   double* T = tab + p.tab;
   const int* base = P.ipool + p.base;
   const int* off = P.ipool + p.off;
   const int n = p.m * p.R;
-  const bool jfast = p.lanes == 1;
-  for (int x = threadIdx.x; x < n; x += blockDim.x) {
+  for (int x = tm.tid(); x < n; x += tm.size()) {
     int j, r;
-    if (jfast) { r = x / p.m; j = x - r * p.m; } else { j = x / p.R; r = x - j * p.R; }
+    decode(p, x, j, r);
     const double d = den[j];
     double* e = T + base[j] + off[r];
     *e = (d != 0) ? (*e * num[j]) / d : 0.0;
   }
-  __syncthreads();
+  tm.sync();
 }
 
 // hard observation: keep only the entries whose state of the variable is `state`
-__device__ void op_evidence(const DProgram& P, double* tab, int pj, int state) {
+template <class Team>
+__device__ void op_evidence(Team& tm, const DProgram& P, double* tab, int pj, int state) {
   const DProj p = P.projs[pj];
   double* T = tab + p.tab;
   const int* base = P.ipool + p.base;
   const int* off = P.ipool + p.off;
   const int n = p.m * p.R;
-  const bool jfast = p.lanes == 1;
-  for (int x = threadIdx.x; x < n; x += blockDim.x) {
+  for (int x = tm.tid(); x < n; x += tm.size()) {
     int j, r;
-    if (jfast) { r = x / p.m; j = x - r * p.m; } else { j = x / p.R; r = x - j * p.R; }
+    decode(p, x, j, r);
     if (j != state) T[base[j] + off[r]] = 0.0;
   }
-  __syncthreads();
+  tm.sync();
 }
 
-__device__ double vec_sum(const double* v, int n, double* red) {
+template <class Team>
+__device__ double vec_sum(Team& tm, const double* v, int n) {
   double s = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
-  return block_sum(s, red);
+  for (int i = tm.tid(); i < n; i += tm.size()) s += v[i];
+  return tm.sum(s);
 }
 
-__device__ void vec_normalise(double* v, int n, double* red) {
-  const double s = vec_sum(v, n, red);
+template <class Team>
+__device__ void vec_normalise(Team& tm, double* v, int n) {
+  const double s = vec_sum(tm, v, n);
   if (s != 0)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] /= s;
-  __syncthreads();
+    for (int i = tm.tid(); i < n; i += tm.size()) v[i] /= s;
+  tm.sync();
 }
 
 // collect: child -> parent messages in post-order; sepsets start at 1 so the
 // absorbed ratio is the message itself.  Messages are kept for distribute.
-__device__ void do_collect(const DProgram& P, const Work& w) {
+template <class Team>
+__device__ void do_collect(Team& tm, const DProgram& P, const Work& w) {
   for (int i = 0; i < P.n_collect; i++) {
     const DMsg m = P.collect[i];
-    op_marg(P, w.tab, m.proj_src, w.msg + m.slot);
-    op_absorb(P, w.tab, m.proj_dst, w.msg + m.slot);
+    op_marg(tm, P, w.tab, m.proj_src, w.msg + m.slot);
+    op_absorb(tm, P, w.tab, m.proj_dst, w.msg + m.slot);
   }
 }
 
 // distribute: parent -> child; the child absorbs new/old where old is the
 // message it sent up during collect.
-__device__ void do_distribute(const DProgram& P, const Work& w, const DMsg* list, int n) {
+template <class Team>
+__device__ void do_distribute(Team& tm, const DProgram& P, const Work& w, const DMsg* list, int n) {
   for (int i = 0; i < n; i++) {
     const DMsg m = list[i];
-    op_marg(P, w.tab, m.proj_src, w.tmp);
-    op_absorb_ratio(P, w.tab, m.proj_dst, w.tmp, w.msg + m.slot);
-    for (int k = threadIdx.x; k < m.size; k += blockDim.x) w.msg[m.slot + k] = w.tmp[k];
-    __syncthreads();
+    op_marg(tm, P, w.tab, m.proj_src, w.tmp);
+    op_absorb_ratio(tm, P, w.tab, m.proj_dst, w.tmp, w.msg + m.slot);
+    for (int k = tm.tid(); k < m.size; k += tm.size()) w.msg[m.slot + k] = w.tmp[k];
+    tm.sync();
   }
 }
 
 // returns how many observations were entered
-__device__ int enter_row(const DProgram& P, const Work& w, const int* obs, int n_obs,
+template <class Team>
+__device__ int enter_row(Team& tm, const DProgram& P, const Work& w, const int* obs, int n_obs,
                          const int* obs_proj) {
   int n = 0;
   for (int k = 0; k < n_obs; k++) {
     const int pj = obs_proj[k], o = obs[k];
-    if (pj >= 0 && o >= 0) { op_evidence(P, w.tab, pj, o); n++; }
+    if (pj >= 0 && o >= 0) { op_evidence(tm, P, w.tab, pj, o); n++; }
   }
   return n;
 }
 
-__device__ void write_queries(const DProgram& P, const Work& w, const DQuery& Q, double* row,
-                              double* red) {
+template <class Team>
+__device__ void write_queries(Team& tm, const DProgram& P, const Work& w, const DQuery& Q, double* row) {
   for (int q = 0; q < Q.n_query; q++) {
     const int pj = Q.proj[q], m = P.projs[pj].m;
-    op_marg(P, w.tab, pj, w.scr);
-    vec_normalise(w.scr, m, red);
-    for (int i = threadIdx.x; i < m; i += blockDim.x) row[Q.off[q] + i] = w.scr[i];
-    __syncthreads();
+    op_marg(tm, P, w.tab, pj, w.scr);
+    vec_normalise(tm, w.scr, m);
+    for (int i = tm.tid(); i < m; i += tm.size()) row[Q.off[q] + i] = w.scr[i];
+    tm.sync();
   }
 }
 
-__global__ void k_jt_forward(DProgram P, DBatch B, DQuery Q, double* gwork, size_t wstride,
-                             int want_ll, int emit, double* alpha, double* post, double* ll_out,
-                             int* status_out) {
+// What a team needs besides the program: its workspace and the grid team's buffers.
+struct TeamMem {
+  double* gwork;
+  size_t wstride;
+  double* part;
+  double* scratch;
+};
+
+template <class Team>
+__global__ void k_jt_forward(DProgram P, DBatch B, DQuery Q, TeamMem M, int want_ll, int emit,
+                             double* alpha, double* post, double* ll_out, int* status_out) {
   extern __shared__ double smem[];
   __shared__ double red[40];
-  const Work w = carve(P, gwork ? gwork + (size_t)blockIdx.x * wstride : smem);
+  Team tm(red, M.part, M.scratch);
+  const Work w = carve(P, tm.work(M.gwork, smem, M.wstride));
   double* vprev = w.va;
   double* vcur = w.va + P.S;
-  for (int seq = blockIdx.x; seq < B.n_series; seq += gridDim.x) {
+  for (int seq = tm.first(); seq < B.n_series; seq += tm.step()) {
     const int T = B.len[seq];
     const long long row0 = B.row_off[seq];
     double ll = 0;
     int bad = 0;
     for (int t = 0; t < T; t++) {
-      load_tables(P, w.tab, t == 0 ? P.base0 : P.base1);
+      load_tables(tm, P, w.tab, t == 0 ? P.base0 : P.base1);
       double m1 = 0;
-      if (t > 0 && P.nif > 0) op_absorb(P, w.tab, P.proj_in, vprev);
+      if (t > 0 && P.nif > 0) op_absorb(tm, P, w.tab, P.proj_in, vprev);
       if (want_ll) {
         if (t == 0) m1 = *P.m1_0;
         else if (P.nif == 0) m1 = P.R1[0];
         else {
           double s = 0;
-          for (int i = threadIdx.x; i < P.S; i += blockDim.x) s += vprev[i] * P.R1[i];
-          m1 = block_sum(s, red);
+          for (int i = tm.tid(); i < P.S; i += tm.size()) s += vprev[i] * P.R1[i];
+          m1 = tm.sum(s);
         }
       }
-      const int entered = enter_row(P, w, B.obs + (row0 + t) * B.n_obs, B.n_obs, B.obs_proj);
-      do_collect(P, w);
+      const int entered = enter_row(tm, P, w, B.obs + (row0 + t) * B.n_obs, B.n_obs, B.obs_proj);
+      do_collect(tm, P, w);
       double m2 = 0;
-      if (want_ll) m2 = vec_sum(w.tab + P.root_tab, P.root_size, red);
+      if (want_ll) m2 = vec_sum(tm, w.tab + P.root_tab, P.root_size);
       // a slice without any evidence has m2 == m1 by definition; do not let rounding decide
       // whether the running log-likelihood is "> 0" (the reference's BAD_LUCK test)
       if (want_ll && entered == 0) m2 = m1;
       if (emit) {
-        do_distribute(P, w, P.distribute, P.n_distribute);
-        if (post) write_queries(P, w, Q, post + (row0 + t) * Q.row, red);
+        do_distribute(tm, P, w, P.distribute, P.n_distribute);
+        if (post) write_queries(tm, P, w, Q, post + (row0 + t) * Q.row);
       } else if (P.nif > 0)
-        do_distribute(P, w, P.path, P.n_path);
+        do_distribute(tm, P, w, P.path, P.n_path);
       if (P.nif > 0) {
-        op_marg(P, w.tab, P.proj_out, vcur);
-        vec_normalise(vcur, P.S, red);
+        op_marg(tm, P, w.tab, P.proj_out, vcur);
+        vec_normalise(tm, vcur, P.S);
         if (alpha)
-          for (int i = threadIdx.x; i < P.S; i += blockDim.x) alpha[(row0 + t) * P.S + i] = vcur[i];
+          for (int i = tm.tid(); i < P.S; i += tm.size()) alpha[(row0 + t) * P.S + i] = vcur[i];
         double* x = vprev; vprev = vcur; vcur = x;
-        __syncthreads();
+        tm.sync();
       }
       if (want_ll) {  // src/nip.c:1458-1474 and the BAD_LUCK test of e_step, :1827-1831
         if (m1 > 0 && m2 > 0) ll += log(m2) - log(m1);
@@ -231,174 +358,234 @@ __global__ void k_jt_forward(DProgram P, DBatch B, DQuery Q, double* gwork, size
         if (m1 <= 0 || m2 <= 0 || ll > 0) bad = 1;
       }
     }
-    if (threadIdx.x == 0) {
+    if (tm.tid() == 0) {
       if (ll_out) ll_out[seq] = ll;
       if (status_out) status_out[seq] = bad;
     }
   }
 }
 
-__global__ void k_jt_backward(DProgram P, DBatch B, DQuery Q, double* gwork, size_t wstride,
-                              const double* alpha, double* post, double* acc, long long acc_stride) {
+template <class Team>
+__global__ void k_jt_backward(DProgram P, DBatch B, DQuery Q, TeamMem M, const double* alpha,
+                              double* post, double* acc, long long acc_stride) {
   extern __shared__ double smem[];
   __shared__ double red[40];
-  const Work w = carve(P, gwork ? gwork + (size_t)blockIdx.x * wstride : smem);
+  Team tm(red, M.part, M.scratch);
+  const Work w = carve(P, tm.work(M.gwork, smem, M.wstride));
   double* a_prev = w.va;          // alpha_{t-1}
   double* a_cur = w.va + P.S;     // alpha_t
   double* gam = w.va + 2 * P.S;   // gamma_{t+1}
-  double* my_acc = acc ? acc + (size_t)blockIdx.x * acc_stride : nullptr;
-  for (int seq = blockIdx.x; seq < B.n_series; seq += gridDim.x) {
+  double* my_acc = acc ? acc + (size_t)tm.slot() * acc_stride : nullptr;
+  for (int seq = tm.first(); seq < B.n_series; seq += tm.step()) {
     const int T = B.len[seq];
     const long long row0 = B.row_off[seq];
     for (int t = T - 1; t >= 0; t--) {
-      load_tables(P, w.tab, t == 0 ? P.base0 : P.base1);
+      load_tables(tm, P, w.tab, t == 0 ? P.base0 : P.base1);
       if (t > 0 && P.nif > 0) {
-        for (int i = threadIdx.x; i < P.S; i += blockDim.x) a_prev[i] = alpha[(row0 + t - 1) * P.S + i];
-        __syncthreads();
-        op_absorb(P, w.tab, P.proj_in, a_prev);
+        for (int i = tm.tid(); i < P.S; i += tm.size()) a_prev[i] = alpha[(row0 + t - 1) * P.S + i];
+        tm.sync();
+        op_absorb(tm, P, w.tab, P.proj_in, a_prev);
       }
-      enter_row(P, w, B.obs + (row0 + t) * B.n_obs, B.n_obs, B.obs_proj);
-      if (t < T - 1 && P.nif > 0) op_absorb_ratio(P, w.tab, P.proj_out, gam, a_cur);
-      do_collect(P, w);
-      do_distribute(P, w, P.distribute, P.n_distribute);
-      if (post) write_queries(P, w, Q, post + (row0 + t) * Q.row, red);
+      enter_row(tm, P, w, B.obs + (row0 + t) * B.n_obs, B.n_obs, B.obs_proj);
+      if (t < T - 1 && P.nif > 0) op_absorb_ratio(tm, P, w.tab, P.proj_out, gam, a_cur);
+      do_collect(tm, P, w);
+      do_distribute(tm, P, w, P.distribute, P.n_distribute);
+      if (post) write_queries(tm, P, w, Q, post + (row0 + t) * Q.row);
       if (my_acc) {  // e_step "THE CORE", src/nip.c:1925-1967
         for (int v = 0; v < P.nv; v++) {
           if (t > 0 && (P.var_flags[v] & NIPGPU_IF_OLD_OUTGOING)) continue;
           const int pj = P.proj_fam[v], m = P.projs[pj].m;
-          op_marg(P, w.tab, pj, w.scr);
-          const double tot = vec_sum(w.scr, m, red);
+          op_marg(tm, P, w.tab, pj, w.scr);
+          const double tot = vec_sum(tm, w.scr, m);
           if (tot != 0)
-            for (int i = threadIdx.x; i < m; i += blockDim.x) my_acc[P.coff[v] + i] += w.scr[i] / tot;
-          __syncthreads();
+            for (int i = tm.tid(); i < m; i += tm.size()) my_acc[P.coff[v] + i] += w.scr[i] / tot;
+          tm.sync();
         }
       }
       if (t > 0 && P.nif > 0) {
-        op_marg(P, w.tab, P.proj_in, gam);
-        vec_normalise(gam, P.S, red);
+        op_marg(tm, P, w.tab, P.proj_in, gam);
+        vec_normalise(tm, gam, P.S);
       }
       double* x = a_prev; a_prev = a_cur; a_cur = x;
-      __syncthreads();
+      tm.sync();
     }
   }
 }
 
+template <class Team>
 __global__ void k_jt_likelihood(DProgram P, DBatch B, const int* proj_off, const int* proj_on,
-                                double* gwork, size_t wstride, double* out) {
+                                TeamMem M, double* out) {
   extern __shared__ double smem[];
   __shared__ double red[40];
-  const Work w = carve(P, gwork ? gwork + (size_t)blockIdx.x * wstride : smem);
-  for (int seq = blockIdx.x; seq < B.n_series; seq += gridDim.x) {
+  Team tm(red, M.part, M.scratch);
+  const Work w = carve(P, tm.work(M.gwork, smem, M.wstride));
+  for (int seq = tm.first(); seq < B.n_series; seq += tm.step()) {
     const int T = B.len[seq];
     const long long row0 = B.row_off[seq];
     for (int t = 0; t < T; t++) {
       const int* obs = B.obs + (row0 + t) * B.n_obs;
-      load_tables(P, w.tab, t == 0 ? P.base0 : P.base1);
-      enter_row(P, w, obs, B.n_obs, proj_off);
-      do_collect(P, w);
-      const double m1 = vec_sum(w.tab + P.root_tab, P.root_size, red);
-      load_tables(P, w.tab, t == 0 ? P.base0 : P.base1);
-      enter_row(P, w, obs, B.n_obs, proj_off);
-      const int extra = enter_row(P, w, obs, B.n_obs, proj_on);
-      do_collect(P, w);
-      double m2 = vec_sum(w.tab + P.root_tab, P.root_size, red);
+      load_tables(tm, P, w.tab, t == 0 ? P.base0 : P.base1);
+      enter_row(tm, P, w, obs, B.n_obs, proj_off);
+      do_collect(tm, P, w);
+      const double m1 = vec_sum(tm, w.tab + P.root_tab, P.root_size);
+      load_tables(tm, P, w.tab, t == 0 ? P.base0 : P.base1);
+      enter_row(tm, P, w, obs, B.n_obs, proj_off);
+      const int extra = enter_row(tm, P, w, obs, B.n_obs, proj_on);
+      do_collect(tm, P, w);
+      double m2 = vec_sum(tm, w.tab + P.root_tab, P.root_size);
       if (extra == 0) m2 = m1;
-      if (threadIdx.x == 0) { out[(row0 + t) * 2] = m1; out[(row0 + t) * 2 + 1] = m2; }
+      if (tm.tid() == 0) { out[(row0 + t) * 2] = m1; out[(row0 + t) * 2 + 1] = m2; }
     }
   }
 }
 
 // R1[i] = sum over everything but I_{t-1} of base1, m1_0 = total mass of base0
-__global__ void k_jt_calibrate(DProgram P, double* gwork, double* R1, double* m1_0) {
+template <class Team>
+__global__ void k_jt_calibrate(DProgram P, TeamMem M, double* R1, double* m1_0) {
   extern __shared__ double smem[];
   __shared__ double red[40];
-  const Work w = carve(P, gwork ? gwork : smem);
-  load_tables(P, w.tab, P.base1);
-  do_collect(P, w);
+  Team tm(red, M.part, M.scratch);
+  const Work w = carve(P, M.gwork ? M.gwork : smem);
+  load_tables(tm, P, w.tab, P.base1);
+  do_collect(tm, P, w);
   if (P.nif > 0) {
-    do_distribute(P, w, P.distribute, P.n_distribute);
-    op_marg(P, w.tab, P.proj_in, w.va);
-    for (int i = threadIdx.x; i < P.S; i += blockDim.x) R1[i] = w.va[i];
-    __syncthreads();
+    do_distribute(tm, P, w, P.distribute, P.n_distribute);
+    op_marg(tm, P, w.tab, P.proj_in, w.va);
+    for (int i = tm.tid(); i < P.S; i += tm.size()) R1[i] = w.va[i];
+    tm.sync();
   } else {
-    const double s = vec_sum(w.tab + P.root_tab, P.root_size, red);
-    if (threadIdx.x == 0) R1[0] = s;
+    const double s = vec_sum(tm, w.tab + P.root_tab, P.root_size);
+    if (tm.tid() == 0) R1[0] = s;
   }
-  load_tables(P, w.tab, P.base0);
-  do_collect(P, w);
-  const double s0 = vec_sum(w.tab + P.root_tab, P.root_size, red);
-  if (threadIdx.x == 0) *m1_0 = s0;
+  load_tables(tm, P, w.tab, P.base0);
+  do_collect(tm, P, w);
+  const double s0 = vec_sum(tm, w.tab + P.root_tab, P.root_size);
+  if (tm.tid() == 0) *m1_0 = s0;
 }
 
-__global__ void k_jt_slice(DProgram P, double* gwork, const double* start, double* out_tables,
+template <class Team>
+__global__ void k_jt_slice(DProgram P, TeamMem M, const double* start, double* out_tables,
                            double* out_msgs) {
   extern __shared__ double smem[];
-  const Work w = carve(P, gwork ? gwork : smem);
-  load_tables(P, w.tab, start);
-  do_collect(P, w);
-  do_distribute(P, w, P.distribute, P.n_distribute);
-  for (int i = threadIdx.x; i < P.tab_total; i += blockDim.x) out_tables[i] = w.tab[i];
-  for (int i = threadIdx.x; i < P.msg_total; i += blockDim.x) out_msgs[i] = w.msg[i];
+  __shared__ double red[40];
+  Team tm(red, M.part, M.scratch);
+  const Work w = carve(P, M.gwork ? M.gwork : smem);
+  load_tables(tm, P, w.tab, start);
+  do_collect(tm, P, w);
+  do_distribute(tm, P, w, P.distribute, P.n_distribute);
+  for (int i = tm.tid(); i < P.tab_total; i += tm.size()) out_tables[i] = w.tab[i];
+  for (int i = tm.tid(); i < P.msg_total; i += tm.size()) out_msgs[i] = w.msg[i];
 }
 
 // single-slice API: mass = sum of cliques - sum of sepsets (nip_probability_mass,
 // src/nipjointree.c:1156-1188) of the consistent tables left by k_jt_slice
 __global__ void k_jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out) {
   __shared__ double red[40];
-  const double a = vec_sum(tables, n_tab, red);
-  const double b = vec_sum(msgs, n_msg, red);
+  CtaTeam tm(red, nullptr, nullptr);
+  const double a = vec_sum(tm, tables, n_tab);
+  const double b = vec_sum(tm, msgs, n_msg);
   if (threadIdx.x == 0) *out = a - b;
 }
 
 // get_probability (src/nip.c:2261-2298): normalised one-variable marginal of the family clique
 __global__ void k_jt_marginal(DProgram P, const double* tables, int pj, double* out) {
   __shared__ double red[40];
+  CtaTeam tm(red, nullptr, nullptr);
   const int m = P.projs[pj].m;
-  op_marg(P, tables, pj, out);
-  vec_normalise(out, m, red);
+  op_marg(tm, P, tables, pj, out);
+  vec_normalise(tm, out, m);
 }
 
-template <class K>
-int prep_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024)
-    NIPGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+TeamMem team_mem(const DProgram& p, const JtLaunch& l) {
+  TeamMem M;
+  M.gwork = l.gwork;
+  M.wstride = jt_work_doubles(p);
+  M.part = l.part;
+  M.scratch = l.scratch;
+  return M;
+}
+
+// One launcher for the three instantiations of a kernel template.
+template <class KW, class KC, class KG, class... Args>
+int launch_team(KW kw, KC kc, KG kg, const JtLaunch& l, int grid, cudaStream_t st, Args... args) {
+  if (l.mode == JT_MODE_GRID) {
+    void* argv[] = {(void*)&args...};
+    NIPGPU_CUDA(cudaLaunchCooperativeKernel((const void*)kg, dim3(grid), dim3(l.threads), argv, 0, st));
+  } else if (l.mode == JT_MODE_WARP) {
+    if (l.smem_bytes > 48 * 1024)
+      NIPGPU_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
+    kw<<<grid, l.threads, l.smem_bytes, st>>>(args...);
+  } else {
+    if (l.smem_bytes > 48 * 1024)
+      NIPGPU_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
+    kc<<<grid, l.threads, l.smem_bytes, st>>>(args...);
+  }
+  NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
 
 }  // namespace
 
+int jt_grid_ctas(int threads, int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jt_backward<GridTeam>, threads, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  int f = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, k_jt_forward<GridTeam>, threads, 0) == cudaSuccess && f >= 1)
+    per_sm = std::min(per_sm, f);
+  return sm_count * std::min(per_sm, 2048 / threads);
+}
+
+JtLaunch jt_fit(const JtLaunch& l, int n_series) {
+  JtLaunch r = l;
+  const int n = std::max(n_series, 1);
+  if (l.mode == JT_MODE_WARP) {
+    const int wpc = l.threads / 32;
+    r.grid = std::max(1, std::min(l.grid, (n + wpc - 1) / wpc));
+    r.slots = r.grid * wpc;
+  } else if (l.mode == JT_MODE_GRID) {
+    r.slots = 1;
+  } else {
+    r.grid = std::max(1, std::min(l.grid, n));
+    r.slots = r.grid;
+  }
+  return r;
+}
+
 int jt_forward(const DProgram& p, const DBatch& b, const DQuery& q, const JtLaunch& l, int want_ll,
                int emit, double* alpha, double* post, double* ll, int* status, cudaStream_t st) {
-  if (int e = prep_smem(k_jt_forward, l.smem_bytes)) return e;
-  k_jt_forward<<<l.grid, l.threads, l.smem_bytes, st>>>(p, b, q, l.gwork, jt_work_doubles(p), want_ll,
-                                                        emit, alpha, post, ll, status);
-  NIPGPU_LAUNCHED();
-  return NIPGPU_OK;
+  return launch_team(k_jt_forward<WarpTeam>, k_jt_forward<CtaTeam>, k_jt_forward<GridTeam>, l, l.grid, st,
+                     p, b, q, team_mem(p, l), want_ll, emit, alpha, post, ll, status);
 }
 
 int jt_backward(const DProgram& p, const DBatch& b, const DQuery& q, const JtLaunch& l,
                 const double* alpha, double* post, double* acc, long long acc_stride, cudaStream_t st) {
-  if (int e = prep_smem(k_jt_backward, l.smem_bytes)) return e;
-  k_jt_backward<<<l.grid, l.threads, l.smem_bytes, st>>>(p, b, q, l.gwork, jt_work_doubles(p), alpha,
-                                                         post, acc, acc_stride);
-  NIPGPU_LAUNCHED();
-  return NIPGPU_OK;
+  return launch_team(k_jt_backward<WarpTeam>, k_jt_backward<CtaTeam>, k_jt_backward<GridTeam>, l, l.grid,
+                     st, p, b, q, team_mem(p, l), alpha, post, acc, acc_stride);
 }
 
 int jt_likelihood(const DProgram& p, const DBatch& b, const int* proj_off, const int* proj_on,
                   const JtLaunch& l, double* out, cudaStream_t st) {
-  if (int e = prep_smem(k_jt_likelihood, l.smem_bytes)) return e;
-  k_jt_likelihood<<<l.grid, l.threads, l.smem_bytes, st>>>(p, b, proj_off, proj_on, l.gwork,
-                                                           jt_work_doubles(p), out);
-  NIPGPU_LAUNCHED();
-  return NIPGPU_OK;
+  return launch_team(k_jt_likelihood<WarpTeam>, k_jt_likelihood<CtaTeam>, k_jt_likelihood<GridTeam>, l,
+                     l.grid, st, p, b, proj_off, proj_on, team_mem(p, l), out);
+}
+
+// single-sequence kernels run one team; in warp mode that is a CTA of one warp
+static JtLaunch single_team(const JtLaunch& l, const DProgram& p) {
+  JtLaunch one = l;
+  if (l.mode == JT_MODE_WARP) {
+    one.mode = JT_MODE_CTA;
+    one.threads = 32;
+    one.smem_bytes = jt_work_doubles(p) * sizeof(double);
+  }
+  return one;
 }
 
 int jt_calibrate(const DProgram& p, const JtLaunch& l, double* R1, double* m1_0, cudaStream_t st) {
-  if (int e = prep_smem(k_jt_calibrate, l.smem_bytes)) return e;
-  k_jt_calibrate<<<1, l.threads, l.smem_bytes, st>>>(p, l.gwork, R1, m1_0);
-  NIPGPU_LAUNCHED();
-  return NIPGPU_OK;
+  const JtLaunch one = single_team(l, p);
+  return launch_team(k_jt_calibrate<CtaTeam>, k_jt_calibrate<CtaTeam>, k_jt_calibrate<GridTeam>, one,
+                     one.mode == JT_MODE_GRID ? one.grid : 1, st, p, team_mem(p, one), R1, m1_0);
 }
 
 int jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out, cudaStream_t st) {
@@ -415,10 +602,10 @@ int jt_marginal(const DProgram& p, const double* tables, int proj, double* out, 
 
 int jt_slice(const DProgram& p, const JtLaunch& l, const double* start, double* out_tables,
              double* out_msgs, cudaStream_t st) {
-  if (int e = prep_smem(k_jt_slice, l.smem_bytes)) return e;
-  k_jt_slice<<<1, l.threads, l.smem_bytes, st>>>(p, l.gwork, start, out_tables, out_msgs);
-  NIPGPU_LAUNCHED();
-  return NIPGPU_OK;
+  const JtLaunch one = single_team(l, p);
+  return launch_team(k_jt_slice<CtaTeam>, k_jt_slice<CtaTeam>, k_jt_slice<GridTeam>, one,
+                     one.mode == JT_MODE_GRID ? one.grid : 1, st, p, team_mem(p, one), start, out_tables,
+                     out_msgs);
 }
 
 }  // namespace nipgpu

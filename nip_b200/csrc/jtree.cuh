@@ -2,7 +2,8 @@
 // layout and launchers.  One CTA owns one sequence at a time and walks the
 // compiled collect/distribute schedule for every slice with the sequence's
 // clique tables staged in shared memory (or in a per-CTA HBM workspace when
-// they do not fit).
+// they do not fit); small models run one warp per sequence, huge cliques are
+// streamed through HBM by the whole grid.
 #pragma once
 
 #include "common.cuh"
@@ -60,11 +61,23 @@ inline size_t jt_work_doubles(const DProgram& p) {
   return (size_t)p.tab_total + p.msg_total + p.msg_max + 3 * (size_t)p.S + p.scratch + 40;
 }
 
+// Which set of threads owns one sequence (see jtree.cu).
+enum { JT_MODE_CTA = 0, JT_MODE_WARP = 1, JT_MODE_GRID = 2 };
+
 struct JtLaunch {
   int threads, grid;
   size_t smem_bytes;     // 0 when the work area lives in HBM
-  double* gwork;         // per-CTA workspace (grid x work doubles) or nullptr
+  double* gwork;         // per-CTA workspace (grid x work doubles), the grid team's single one, or nullptr
+  int mode;              // JT_MODE_*
+  int slots;             // teams running concurrently = accumulator groups of the E-step
+  double* part;          // grid mode: 2 x grid doubles for grid-wide sums
+  double* scratch;       // grid mode: grid x threads doubles for two-stage marginals
 };
+
+// co-resident CTAs for the cooperative (grid-team) kernels
+int jt_grid_ctas(int threads, int sm_count);
+// launch geometry for a batch of n_series sequences (never more teams than sequences)
+JtLaunch jt_fit(const JtLaunch& l, int n_series);
 
 int jt_forward(const DProgram& p, const DBatch& b, const DQuery& q, const JtLaunch& l,
                int want_ll, int emit_filtered, double* alpha, double* post, double* ll,

@@ -127,6 +127,50 @@ def test_hbm_workspace_path(gpu_lib, name, monkeypatch):
     assert_close(counts, unhex(it["counts"]), "%s expected counts (HBM workspace)" % name)
 
 
+@pytest.mark.parametrize("mode", ["warp", "cta", "hbm", "grid"])
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_generic_engine_team_modes(gpu_lib, name, mode, monkeypatch):
+    """the generic engine's kernels are instantiated for three teams (warp / CTA / whole grid) and
+    two table homes (shared memory / HBM); every combination must reproduce every golden: smoothing,
+    filtering, E-step counts, the likelihood loop and the single-slice API"""
+    monkeypatch.setenv("NIPGPU_JT_MODE", mode)
+    c = Case(name)
+    try:
+        m = gpu_lib.Model(c.fm, engine=1)
+    except Exception as e:          # tables larger than shared memory in a shared-memory mode
+        assert mode in ("warp", "cta") and "do not fit" in str(e)
+        pytest.skip("model does not fit shared memory in mode " + mode)
+    b = m.batch(c.obs_vars, c.series)
+    for kind, fwd in (("smooth", False), ("filter", True)):
+        posts, lls = c.expected(kind)
+        post, ll = b.infer(c.query, forward_only=fwd)
+        for i, got in enumerate(b.split(post)):
+            assert_close(got, posts[i], "%s series %d %s (%s)" % (name, i, kind, mode))
+        assert_close(ll, lls, "%s loglik %s (%s)" % (name, kind, mode))
+    if "likelihood" in c.j and name in LIKELIHOOD_CASES:
+        on = np.zeros(c.fm.n_vars, dtype=np.uint8)
+        on[c.j["likelihood"]["marked"]] = 1
+        out = b.likelihood(1 - on, on)
+        for i, got in enumerate(b.split(out)):
+            assert_close(got.reshape(-1), unhex(c.j["likelihood"]["out"][i]), "%s likelihood (%s)" % (name, mode))
+    if name in EM_CASES:
+        it = c.j["em"]["iters"][0]
+        m.mstep(unhex(c.j["em"]["init"]))
+        counts, L, st = b.estep()
+        assert st == 0
+        assert_close(counts, unhex(it["counts"]), "%s expected counts (%s)" % (name, mode))
+        assert_close(L, float.fromhex(it["ll"]), "%s EM loglik (%s)" % (name, mode))
+    if name in SLICE_CASES:
+        m2 = gpu_lib.Model(c.fm, engine=1)
+        step = c.j["slice"][-1]
+        m2.slice_reset()
+        m2.slice_use_priors(step["has_history"])
+        for var, lik in step["evidence"]:
+            m2.slice_enter_evidence(var, unhex(lik))
+        m2.slice_make_consistent()
+        assert_close(m2.slice_mass(), float.fromhex(step["mass"]), "mass (%s)" % mode)
+
+
 def test_empty_and_single_slice(gpu_lib):
     c = Case("hmm5")
     m = gpu_lib.Model(c.fm)
