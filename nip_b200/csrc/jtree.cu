@@ -55,6 +55,7 @@ __device__ __forceinline__ Work carve(const DProgram& P, double* W) {
 
 struct WarpTeam {
   static constexpr bool kGrid = false;
+  static constexpr int kUnroll = 2;
   __device__ WarpTeam(double*, double*, double*) {}
   __device__ int tid() const { return threadIdx.x & 31; }
   __device__ int size() const { return 32; }
@@ -70,6 +71,7 @@ struct WarpTeam {
 
 struct CtaTeam {
   static constexpr bool kGrid = false;
+  static constexpr int kUnroll = 4;
   double* red;
   __device__ CtaTeam(double* r, double*, double*) : red(r) {}
   __device__ int tid() const { return threadIdx.x; }
@@ -88,6 +90,7 @@ struct CtaTeam {
 // grid barrier per sum is enough), `scratch` holds size() doubles for two-stage marginals.
 struct GridTeam {
   static constexpr bool kGrid = true;
+  static constexpr int kUnroll = 8;
   double *red, *part, *scratch;
   int flip = 0;
   __device__ GridTeam(double* r, double* p, double* s) : red(r), part(p), scratch(s) {}
@@ -116,8 +119,19 @@ struct GridTeam {
 };
 
 template <class Team>
-__device__ __forceinline__ void load_tables(Team& tm, const DProgram& P, double* tab, const double* src) {
-  for (int i = tm.tid(); i < P.tab_total; i += tm.size()) tab[i] = src[i];
+__device__ __forceinline__ void load_tables(Team& tm, const DProgram& P, double* __restrict__ tab,
+                                            const double* __restrict__ src) {
+  constexpr int U = Team::kUnroll;
+  const int n = P.tab_total, stride = tm.size();
+  int i = tm.tid();
+  for (; i + (U - 1) * stride < n; i += U * stride) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = src[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < U; u++) tab[i + u * stride] = v[u];
+  }
+  for (; i < n; i += stride) tab[i] = src[i];
   tm.sync();
 }
 
@@ -126,9 +140,9 @@ __device__ __forceinline__ void load_tables(Team& tm, const DProgram& P, double*
 template <class Team>
 __device__ void op_marg(Team& tm, const DProgram& P, const double* tab, int pj, double* dst) {
   const DProj p = P.projs[pj];
-  const double* T = tab + p.tab;
-  const int* base = P.ipool + p.base;
-  const int* off = P.ipool + p.off;
+  const double* __restrict__ T = tab + p.tab;
+  const int* __restrict__ base = P.ipool + p.base;
+  const int* __restrict__ off = P.ipool + p.off;
   const int lanes = p.lanes, sub = tm.tid() % lanes, grp = tm.tid() / lanes;
   const int groups = tm.size() / lanes;
   if constexpr (Team::kGrid) {
@@ -148,6 +162,7 @@ __device__ void op_marg(Team& tm, const DProgram& P, const double* tab, int pj, 
         c = g / p.m;
         j = g - c * p.m;
         const int b = base[j], r1 = min(p.R, (c + 1) * Rc);
+#pragma unroll 8
         for (int r = c * Rc + sub; r < r1; r += lanes) s += T[b + off[r]];
       }
       for (int o = lanes >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -179,60 +194,80 @@ __device__ void op_marg(Team& tm, const DProgram& P, const double* tab, int pj, 
 }
 
 // entry x of the projection's (j, r) enumeration, fastest index chosen so that
-// consecutive threads touch consecutive addresses
-__device__ __forceinline__ void decode(const DProj& p, int x, int& j, int& r) {
-  if (p.lanes == 1) { r = x / p.m; j = x - r * p.m; } else { j = x / p.R; r = x - j * p.R; }
+// consecutive threads touch consecutive addresses; shifts when the divisor is a power of two
+struct Decoder {
+  int div, shift;
+  bool jfast;
+  __device__ explicit Decoder(const DProj& p) {
+    jfast = p.lanes == 1;
+    div = jfast ? p.m : p.R;
+    shift = (div & (div - 1)) == 0 ? __ffs(div) - 1 : -1;
+  }
+  __device__ __forceinline__ void operator()(int x, int& j, int& r) const {
+    const int q = shift >= 0 ? x >> shift : x / div;
+    const int rem = x - q * div;
+    if (jfast) { r = q; j = rem; } else { j = q; r = rem; }
+  }
+};
+
+// T[e] = f(T[e], coef(j)) for every entry e = base[j] + off[r] of a projection.  U entries per
+// thread are loaded before any is stored, so that a thread keeps U independent HBM requests in
+// flight (the tables of the grid team are far larger than L2).
+template <int U, class Team, class Coef, class F>
+__device__ __forceinline__ void for_entries(Team& tm, const DProgram& P, double* tab, int pj, Coef coef, F f) {
+  const DProj p = P.projs[pj];
+  double* __restrict__ T = tab + p.tab;
+  const int* __restrict__ base = P.ipool + p.base;
+  const int* __restrict__ off = P.ipool + p.off;
+  const Decoder dec(p);
+  const int n = p.m * p.R, stride = tm.size();
+  int x = tm.tid();
+  for (; x + (U - 1) * stride < n; x += U * stride) {
+    int a[U];
+    double v[U];
+    decltype(coef(0)) c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int j, r;
+      dec(x + u * stride, j, r);
+      a[u] = base[j] + off[r];
+      c[u] = coef(j);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = T[a[u]];
+#pragma unroll
+    for (int u = 0; u < U; u++) T[a[u]] = f(v[u], c[u]);
+  }
+  for (; x < n; x += stride) {
+    int j, r;
+    dec(x, j, r);
+    double* e = T + base[j] + off[r];
+    *e = f(*e, coef(j));
+  }
+  tm.sync();
 }
 
 // T[base[j] + off[r]] *= v[j]
 template <class Team>
 __device__ void op_absorb(Team& tm, const DProgram& P, double* tab, int pj, const double* v) {
-  const DProj p = P.projs[pj];
-  double* T = tab + p.tab;
-  const int* base = P.ipool + p.base;
-  const int* off = P.ipool + p.off;
-  const int n = p.m * p.R;
-  for (int x = tm.tid(); x < n; x += tm.size()) {
-    int j, r;
-    decode(p, x, j, r);
-    T[base[j] + off[r]] *= v[j];
-  }
-  tm.sync();
+  for_entries<Team::kUnroll>(tm, P, tab, pj, [=](int j) { return v[j]; },
+                             [](double t, double c) { return t * c; });
 }
 
 // T[..] = T[..] * num[j] / den[j], and 0 where den[j] == 0
+struct Ratio { double num, den; };
 template <class Team>
 __device__ void op_absorb_ratio(Team& tm, const DProgram& P, double* tab, int pj, const double* num,
                                 const double* den) {
-  const DProj p = P.projs[pj];
-  double* T = tab + p.tab;
-  const int* base = P.ipool + p.base;
-  const int* off = P.ipool + p.off;
-  const int n = p.m * p.R;
-  for (int x = tm.tid(); x < n; x += tm.size()) {
-    int j, r;
-    decode(p, x, j, r);
-    const double d = den[j];
-    double* e = T + base[j] + off[r];
-    *e = (d != 0) ? (*e * num[j]) / d : 0.0;
-  }
-  tm.sync();
+  for_entries<Team::kUnroll>(tm, P, tab, pj, [=](int j) { return Ratio{num[j], den[j]}; },
+                             [](double t, Ratio c) { return c.den != 0 ? (t * c.num) / c.den : 0.0; });
 }
 
 // hard observation: keep only the entries whose state of the variable is `state`
 template <class Team>
 __device__ void op_evidence(Team& tm, const DProgram& P, double* tab, int pj, int state) {
-  const DProj p = P.projs[pj];
-  double* T = tab + p.tab;
-  const int* base = P.ipool + p.base;
-  const int* off = P.ipool + p.off;
-  const int n = p.m * p.R;
-  for (int x = tm.tid(); x < n; x += tm.size()) {
-    int j, r;
-    decode(p, x, j, r);
-    if (j != state) T[base[j] + off[r]] = 0.0;
-  }
-  tm.sync();
+  for_entries<Team::kUnroll>(tm, P, tab, pj, [=](int j) { return j == state; },
+                             [](double t, bool keep) { return keep ? t : 0.0; });
 }
 
 template <class Team>

@@ -138,3 +138,125 @@ def net_text_generic(nodes, potentials) -> str:
         flat = arr.reshape(-1, arr.shape[-1])
         lines.append("%s { data = (\n  %s ); }" % (head, _fmt_rows(flat)))
     return "\n".join(lines) + "\n"
+
+
+# ---------------------------------------------------------------------------
+# factorial DBN (config C3 of SURVEY §8): 4 ring-coupled chains
+#   X^i_t | X^i_{t-1}, X^{i-1}_{t-1}   and   Y^i_t | X^i_t
+# ---------------------------------------------------------------------------
+class FactorialSpec:
+    """K = 4 chains of `ns` states with one `ny`-symbol observation each.  Node order in the
+    .net text: Y0..Y3, X0..X3, W0..W3 (W^i = X^i of the previous slice, NIP_next = X^i).
+
+    flat() states the join tree the reference's parser + triangulation build for this text
+    (verified for ns = 3 against the golden fixture factorial4x3.json, which was generated from
+    the reference itself; the tree depends on the graph only, not on the cardinalities):
+    four {Y^i, X^i} cliques and three 6-variable cliques chained by two 5-variable sepsets,
+    interface |I| = ns^4."""
+
+    K = 4
+    _CLIQUES = [["Y0", "X0"], ["Y1", "X1"], ["Y3", "X3"], ["Y2", "X2"],
+                ["X2", "X3", "W0", "W1", "W2", "W3"],
+                ["X1", "X2", "X3", "W0", "W1", "W3"],
+                ["X0", "X1", "X2", "X3", "W0", "W3"]]
+    _SEPSETS = [(0, 6, ["X0"]), (1, 5, ["X1"]), (2, 6, ["X3"]), (3, 4, ["X2"]),
+                (4, 5, ["X2", "X3", "W0", "W1", "W3"]), (5, 6, ["X1", "X2", "X3", "W0", "W3"])]
+    _FAMILY = [0, 1, 3, 2, 6, 5, 4, 4, 4, 4, 4, 4]
+    _ADJ = [[0], [1], [2], [3], [3, 4], [1, 5, 4], [0, 2, 5]]   # sepsets of each clique, reference order
+
+    def __init__(self, ns: int = 16, ny: int = 4, seed: int = 1):
+        K = self.K
+        rng = np.random.default_rng(seed)
+        self.ns, self.ny = ns, ny
+        # unnormalised, as written to the .net text: the parser normalises (and so does flat())
+        self.E = [rng.random((ns, ny)) + 0.05 for _ in range(K)]            # [x][y]
+        self.A = [rng.random((ns, ns, ns)) + 0.05 for _ in range(K)]        # [w_{i-1}][w_i][x]
+        self.pi = [rng.random(ns) + 0.1 for _ in range(K)]
+        self.names = ["Y%d" % i for i in range(K)] + ["X%d" % i for i in range(K)] + ["W%d" % i for i in range(K)]
+
+    def net_text(self) -> str:
+        K, ns, ny = self.K, self.ns, self.ny
+        nodes = [("Y%d" % i, ny, None) for i in range(K)] + [("X%d" % i, ns, None) for i in range(K)] + \
+                [("W%d" % i, ns, "X%d" % i) for i in range(K)]
+        pots = [("Y%d" % i, ["X%d" % i], self.E[i]) for i in range(K)]
+        pots += [("X%d" % i, ["W%d" % ((i - 1) % K), "W%d" % i], self.A[i]) for i in range(K)]
+        pots += [("W%d" % i, [], self.pi[i][None, :]) for i in range(K)]
+        return net_text_generic(nodes, pots)
+
+    def flat(self) -> FlatModel:
+        K, ns, ny = self.K, self.ns, self.ny
+        idx = {n: i for i, n in enumerate(self.names)}
+        card = np.array([ny] * K + [ns] * (2 * K))
+        flags = np.array([0] * K + [IF_INCOMING | IF_OUTGOING] * K + [IF_OLD_OUTGOING] * K)
+        parents, poff = [], [0]
+        for v in range(3 * K):
+            if v < K:
+                parents += [idx["X%d" % v]]
+            elif v < 2 * K:
+                i = v - K
+                parents += [idx["W%d" % i], idx["W%d" % ((i - 1) % K)]]   # last written parent first
+            poff.append(len(parents))
+        # CPTs as the parser sees them (child fastest, blocks normalised left to right)
+        cpt = {}
+        for i in range(K):
+            cpt[i] = _seq_normalise_blocks(self.E[i].reshape(-1), ny).reshape(ns, ny)
+            cpt[K + i] = _seq_normalise_blocks(self.A[i].reshape(-1), ns).reshape(ns, ns, ns)
+        cvars = [[idx[n] for n in c] for c in self._CLIQUES]
+        tables, toff = [], [0]
+        for c, vs in enumerate(cvars):
+            shape = [int(card[v]) for v in reversed(vs)]           # numpy C order: last variable slowest
+            t = np.ones(shape)
+            for v in range(2 * K):
+                if self._FAMILY[v] != c:
+                    continue
+                fam = [v] + parents[poff[v]:poff[v + 1]]          # child fastest in the CPT
+                src = cpt[v]                                       # axes: reversed(fam)
+                axes_in_t = [len(vs) - 1 - vs.index(u) for u in reversed(fam)]
+                order = np.argsort(axes_in_t)
+                shp = [1] * len(vs)
+                for a in axes_in_t:
+                    shp[a] = int(card[vs[len(vs) - 1 - a]])
+                t = t * np.transpose(src, order).reshape(shp)
+            tables.append(t.reshape(-1))
+            toff.append(toff[-1] + t.size)
+        prior, proff = [], [0]
+        for v in range(3 * K):
+            if v >= 2 * K:
+                p = np.array(self.pi[v - 2 * K], dtype=np.float64)
+                s = np.cumsum(p)[-1]
+                prior.append(p / s if s != 0 else p)
+            proff.append(proff[-1] + (ns if v >= 2 * K else 0))
+        adj = self._ADJ
+        return FlatModel(
+            var_card=card, var_flags=flags, var_parent_off=np.array(poff), var_parents=np.array(parents),
+            var_family=np.array(self._FAMILY), var_prior_off=np.array(proff), var_prior=np.concatenate(prior),
+            clique_var_off=np.cumsum([0] + [len(c) for c in cvars]), clique_vars=np.concatenate(cvars),
+            clique_tab_off=np.array(toff, dtype=np.int64), clique_tables=np.concatenate(tables),
+            sepset_cliques=np.array([x for a, b, _ in self._SEPSETS for x in (a, b)]),
+            sepset_var_off=np.cumsum([0] + [len(v) for _, _, v in self._SEPSETS]),
+            sepset_vars=np.array([idx[n] for _, _, v in self._SEPSETS for n in v]),
+            clique_adj_off=np.cumsum([0] + [len(a) for a in adj]), clique_adj=np.concatenate(adj),
+            outgoing=np.arange(K, 2 * K), prev_outgoing=np.arange(2 * K, 3 * K), in_clique=4, out_clique=6,
+            var_names=list(self.names),
+        ).normalise_dtypes()
+
+    obs_vars = [0, 1, 2, 3]
+
+    def sample(self, n_series: int, T: int, seed: int = 2, missing: float = 0.0) -> np.ndarray:
+        """[n_series, T, 4] int32 observations of Y0..Y3 (-1 = missing)."""
+        K = self.K
+        rng = np.random.default_rng(seed)
+        nrm = lambda a: a / a.sum(-1, keepdims=True)
+        pi, A, E = [nrm(a) for a in self.pi], [nrm(a) for a in self.A], [nrm(a) for a in self.E]
+        draw = lambda p: np.minimum((np.cumsum(p, axis=-1) < rng.random(p.shape[:-1])[..., None]).sum(-1),
+                                    p.shape[-1] - 1)
+        w = [draw(np.broadcast_to(pi[i], (n_series, self.ns))) for i in range(K)]
+        out = np.empty((n_series, T, K), dtype=np.int32)
+        for t in range(T):
+            x = [draw(A[i][w[(i - 1) % K], w[i]]) for i in range(K)]
+            for i in range(K):
+                out[:, t, i] = draw(E[i][x[i]])
+            w = x
+        if missing > 0:
+            out[rng.random(out.shape) < missing] = -1
+        return out
