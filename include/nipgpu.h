@@ -208,6 +208,12 @@ int64_t nipgpu_launch_count(int reset);
  * nipgpu_infer / nipgpu_em_estep call, measured with CUDA events on the library's
  * stream; n receives the number of launches summed. */
 int nipgpu_last_kernel_ms(nipgpu_model* m, double* ms, int32_t* n);
+/* Diagnostics of the generic engine's grid team (models whose cliques are streamed through
+ * HBM; recording is on when the model was created with NIPGPU_JT_TRACE=1 in the environment):
+ * copies up to cap_records (tag, device-timer ns) pairs, one per grid-wide barrier, into
+ * out[2 * cap_records]; tag = operation code << 16 | projection.  Returns the number of records
+ * (0 when recording is off), -1 on error. */
+int nipgpu_jt_trace(nipgpu_model* m, uint64_t* out, int cap_records, int reset);
 /* Measures, with CUDA events, what this device sustains on the two resources the
  * hot path is bound by (MEASURED_PEAKS.json has no FP64 figure): a dependent-free
  * stream of DMMA m8n8k4 instructions, the same with scalar DFMA, and a plain

@@ -80,12 +80,18 @@ int choose_launch(nipgpu_model* m) {
   } else if (want == "grid") {
     l.mode = JT_MODE_GRID;
     l.threads = 256;
-    l.grid = jt_grid_ctas(l.threads, m->sm_count);
+    l.grid = jt_grid_ctas(l.threads, m->sm_count, &l.smem_bytes);
     const size_t part = 2 * (size_t)l.grid + 8, scratch = (size_t)l.grid * l.threads;
     if (int e = need_gwork(work + part + scratch)) return e;
     l.gwork = m->d_gwork;
     l.part = m->d_gwork + work;
     l.scratch = l.part + part;
+    const char* tr = getenv("NIPGPU_JT_TRACE");
+    if (tr && tr[0] == '1' && !m->d_trace) {
+      NIPGPU_CUDA(cudaMalloc((void**)&m->d_trace, JT_TRACE_WORDS * sizeof(unsigned long long)));
+      NIPGPU_CUDA(cudaMemset(m->d_trace, 0, JT_TRACE_WORDS * sizeof(unsigned long long)));
+    }
+    l.trace = m->d_trace;
   } else {
     l.mode = JT_MODE_CTA;
     l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
@@ -122,7 +128,7 @@ int refresh_derived(nipgpu_model* m) {
   for (int k = 0; k < np; k++)
     if (hm.flags[hm.prior_vars[k]] & NIPGPU_IF_OLD_OUTGOING)
       if (int e = apply(m->d_base0, k)) return e;
-  if (m->launch.gwork == nullptr && m->launch.smem_bytes == 0) return fail(NIPGPU_EINVAL, "launch not configured");
+  if (m->launch.threads == 0) return fail(NIPGPU_EINVAL, "launch not configured");
   if (int e = jt_calibrate(m->prog, m->launch, m->d_R1, m->d_m10, st)) return e;
   if (m->chain.ok)
     if (int e = chain_refresh(hm, m->chain, m->d_base0, m->d_base1, m->tab_off, m->d_ipool, m->d_R1, m->d_m10, st)) return e;
@@ -308,6 +314,11 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
     pool.insert(pool.end(), p.off.begin(), p.off.end());
     dp[i].tab = m->tab_off[p.clique]; dp[i].m = p.m; dp[i].R = p.R; dp[i].lanes = p.lanes;
     dp[i].base = p.base_pos; dp[i].off = p.off_pos;
+    p.jlo_pos = (int)pool.size();
+    pool.insert(pool.end(), p.jlo.begin(), p.jlo.end());
+    p.jhi_pos = (int)pool.size();
+    pool.insert(pool.end(), p.jhi.begin(), p.jhi.end());
+    dp[i].clq = p.clique; dp[i].F = p.F; dp[i].jlo = p.jlo_pos; dp[i].jhi = p.jhi_pos;
   }
   auto to_dmsg = [&](const std::vector<Msg>& v) {
     std::vector<DMsg> r(v.size());
@@ -345,7 +356,7 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
   P.n_collect = (int)hm.collect.size(); P.n_distribute = (int)hm.distribute.size();
   P.n_path = (int)hm.path_to_out.size();
   P.nif = hm.nif; P.S = hm.S; P.proj_in = hm.proj_in; P.proj_out = hm.proj_out;
-  P.root_tab = m->tab_off[0]; P.root_size = hm.csize[0]; P.nv = hm.nv;
+  P.root_tab = m->tab_off[0]; P.root_size = hm.csize[0]; P.nv = hm.nv; P.n_cliques = hm.nc;
   P.projs = m->d_projs; P.ipool = m->d_ipool; P.collect = m->d_collect; P.distribute = m->d_distribute;
   P.path = m->d_path; P.base0 = m->d_base0; P.base1 = m->d_base1; P.R1 = m->d_R1; P.m1_0 = m->d_m10;
   P.proj_var = m->d_proj_var; P.proj_fam = m->d_proj_fam; P.coff = m->d_coff; P.var_flags = m->d_var_flags;
@@ -365,7 +376,7 @@ void nipgpu_model_destroy(nipgpu_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  cudaFree(m->d_ipool); cudaFree(m->d_projs); cudaFree(m->d_collect); cudaFree(m->d_distribute);
+  cudaFree(m->d_trace); cudaFree(m->d_ipool); cudaFree(m->d_projs); cudaFree(m->d_collect); cudaFree(m->d_distribute);
   cudaFree(m->d_path); cudaFree(m->d_proj_var); cudaFree(m->d_proj_fam); cudaFree(m->d_var_flags);
   cudaFree(m->d_coff); cudaFree(m->d_prior_off); cudaFree(m->d_prior_vars); cudaFree(m->d_prior_flags);
   cudaFree(m->d_orig); cudaFree(m->d_prior); cudaFree(m->d_base0); cudaFree(m->d_base1);
@@ -734,6 +745,19 @@ int nipgpu_slice_marginal(nipgpu_model* m, int32_t var, double* out) {
   NIPGPU_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m->hm.card[var] * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
   return NIPGPU_OK;
+}
+
+int nipgpu_jt_trace(nipgpu_model* m, uint64_t* out, int cap_records, int reset) {
+  if (!m || !out || cap_records < 0) return fail(NIPGPU_EINVAL, "bad arguments") , -1;
+  if (!m->d_trace) return 0;
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  std::vector<unsigned long long> h(JT_TRACE_WORDS);
+  NIPGPU_CUDA(cudaMemcpy(h.data(), m->d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  const int n = (int)std::min<unsigned long long>(h[0], (unsigned long long)cap_records);
+  for (int i = 0; i < 2 * n; i++) out[i] = h[1 + i];
+  if (reset) NIPGPU_CUDA(cudaMemset(m->d_trace, 0, sizeof(unsigned long long)));
+  return n;
 }
 
 int64_t nipgpu_launch_count(int reset) {

@@ -36,6 +36,7 @@ struct nipgpu_model {
   size_t acc_groups = 0;
   double* d_gwork = nullptr;   // HBM workspace when tables do not fit shared memory
   size_t gwork_doubles = 0;
+  unsigned long long* d_trace = nullptr;  // NIPGPU_JT_TRACE=1 (grid team diagnostics)
 
   nipgpu::DProgram prog{};
   nipgpu::JtLaunch launch{};

@@ -14,6 +14,8 @@ struct DProj {
   int tab;    // offset of the clique's table inside the work area
   int m, R, lanes;
   int base, off;  // positions in the int pool
+  int clq;        // clique index
+  int F, jlo, jhi;  // table-order map: j(e) = ipool[jhi + e / F] + ipool[jlo + e % F]
 };
 
 struct DMsg {
@@ -23,6 +25,7 @@ struct DMsg {
 // Everything a slice kernel needs about the model; passed by value.
 struct DProgram {
   int tab_total, msg_total, msg_max, scratch;
+  int n_cliques;
   int n_collect, n_distribute, n_path;
   int nif, S, proj_in, proj_out;
   int root_tab, root_size;
@@ -58,7 +61,8 @@ struct DQuery {
 
 // work-area size in doubles for one CTA
 inline size_t jt_work_doubles(const DProgram& p) {
-  return (size_t)p.tab_total + p.msg_total + p.msg_max + 3 * (size_t)p.S + p.scratch + 40;
+  const size_t quo = p.msg_max > p.S ? p.msg_max : p.S;  // quotient vector of the grid team
+  return (size_t)p.tab_total + p.msg_total + p.msg_max + 3 * (size_t)p.S + p.scratch + quo + 40;
 }
 
 // Which set of threads owns one sequence (see jtree.cu).
@@ -72,10 +76,13 @@ struct JtLaunch {
   int slots;             // teams running concurrently = accumulator groups of the E-step
   double* part;          // grid mode: 2 x grid doubles for grid-wide sums
   double* scratch;       // grid mode: grid x threads doubles for two-stage marginals
+  unsigned long long* trace;  // grid mode, NIPGPU_JT_TRACE=1: per-barrier (tag, ns) records
 };
 
+constexpr int JT_TRACE_WORDS = 1 + 2 * 8192;
+
 // co-resident CTAs for the cooperative (grid-team) kernels
-int jt_grid_ctas(int threads, int sm_count);
+int jt_grid_ctas(int threads, int sm_count, size_t* smem_bytes);
 // launch geometry for a batch of n_series sequences (never more teams than sequences)
 JtLaunch jt_fit(const JtLaunch& l, int n_series);
 

@@ -65,6 +65,27 @@ int HostModel::add_proj(int clique, const std::vector<int>& vars) {
   // up to a warp cooperates on one destination entry (shuffle reduction).
   const bool dest_has_dim0 = std::find(dpos.begin(), dpos.end(), 0) != dpos.end();
   p.lanes = dest_has_dim0 ? 1 : std::min(32, pow2_floor(std::max(1, p.R)));
+  // table-order map, split after the leading dimensions whose product reaches 1024
+  std::vector<int64_t> dstride(nd, 0);  // weight of clique dimension k inside j (0: summed out)
+  {
+    int64_t w = 1;
+    for (size_t k = 0; k < vars.size(); k++) { dstride[dpos[k]] = w; w *= card[vars[k]]; }
+  }
+  int split = 0;
+  p.F = 1;
+  while (split < nd && p.F < 1024) p.F *= card[cv[split++]];
+  auto fill = [&](std::vector<int>& out, int from, int to) {
+    int64_t count = 1;
+    for (int k = from; k < to; k++) count *= card[cv[k]];
+    out.resize((size_t)count);
+    for (int64_t x = 0; x < count; x++) {
+      int64_t rem = x, j = 0;
+      for (int k = from; k < to; k++) { j += (rem % card[cv[k]]) * dstride[k]; rem /= card[cv[k]]; }
+      out[(size_t)x] = (int)j;
+    }
+  };
+  fill(p.jlo, 0, split);
+  fill(p.jhi, split, nd);
   projs.push_back(p);
   return (int)projs.size() - 1;
 }

@@ -31,6 +31,11 @@ struct Proj {
   int lanes = 1;           // threads cooperating on one destination entry (pow2 <= 32)
   std::vector<int> base, off;
   int base_pos = 0, off_pos = 0;  // positions inside the device int pool
+  // the same map in table order, for kernels that stream the table linearly:
+  // destination index of entry e = jhi[e / F] + jlo[e % F], F = product of leading dimensions
+  int F = 1;
+  std::vector<int> jlo, jhi;
+  int jlo_pos = 0, jhi_pos = 0;
 };
 
 struct Msg {

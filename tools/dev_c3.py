@@ -36,6 +36,22 @@ def run(mode):
         ms = m.last_kernel_ms()[0]
         print("[%s] E-step: kernels %.2f ms -> %.3e slice-steps/s, ll %.6f status %d" % (mode or "auto", ms, N * T / (ms * 1e-3), L, st), flush=True)
     res["counts"], res["L"] = counts, L
+    if os.environ.get("NIPGPU_JT_TRACE") and mode is None:
+        m.jt_trace()
+        b.infer(q)
+        tr = m.jt_trace()
+        names = {1: "marg", 2: "marg2", 3: "update", 4: "quot", 5: "sum", 6: "norm", 0: "other"}
+        agg = {}
+        for k in range(1, len(tr)):
+            tag, dt = int(tr[k, 0]), (int(tr[k, 1]) - int(tr[k - 1, 1])) / 1e3
+            if dt > 1e5:       # gap between the two kernels
+                continue
+            key = (names.get(tag >> 16, "?"), tag & 0xffff)
+            a = agg.setdefault(key, [0, 0.0]); a[0] += 1; a[1] += dt
+        tot = sum(v[1] for v in agg.values())
+        print("trace: %d barriers, %.1f us total" % (len(tr), tot))
+        for key, (cnt, us) in sorted(agg.items(), key=lambda z: -z[1][1])[:40]:
+            print("   %-7s proj %3d: %4d x %8.1f us = %9.1f us (%.1f%%)" % (key[0], key[1], cnt, us / cnt, us, 100 * us / tot))
     b.close(); m.close()
     return res
 
