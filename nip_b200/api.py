@@ -161,6 +161,12 @@ class Model:
     def counts_size(self):
         return int(self.L.nipgpu_model_counts_size(self.h))
 
+    def counts_offsets(self):
+        """[n_vars + 1] offsets of every variable's family counts inside the E-step vector"""
+        off = np.zeros(self.fm.n_vars + 1, dtype=np.int64)
+        _check(self.L.nipgpu_model_counts_offsets(self.h, _p(off)))
+        return off
+
     def mstep(self, counts=None):
         c = None if counts is None else np.ascontiguousarray(counts, dtype=np.float64)
         _check(self.L.nipgpu_em_mstep(self.h, _p(c)))

@@ -291,3 +291,60 @@ def test_launches_are_counted(gpu_lib):
     gpu_lib.launch_count(reset=True)
     b.infer(c.query)
     assert gpu_lib.launch_count() >= 2
+
+
+# ---- factorial DBN (config C3): cliques too large for shared memory ------------------------
+@pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None)])
+def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, monkeypatch):
+    """4 ring-coupled chains (C3's topology); ns = 8 gives 8^6-entry cliques, which the engine
+    streams through HBM with the whole grid on its own (no override): smoothing, filtering and
+    the E-step against the oracle"""
+    from nip_b200.synth import FactorialSpec
+    if mode:
+        monkeypatch.setenv("NIPGPU_JT_MODE", mode)
+    sp = FactorialSpec(ns, 3, seed=4)
+    fm = sp.flat()
+    data = sp.sample(3, 4, seed=5, missing=0.2)
+    data[:, 0, :] = np.abs(data[:, 0, :])          # observed first slices (DESIGN.md section 7)
+    series = [data[0], data[1][:2], data[2][:1]]
+    query = [4, 7, 9, 2]                            # X0, X3, W1, Y2
+    om = oracle_lib.model(fm)
+    m = gpu_lib.Model(fm, engine=1)
+    b = m.batch(sp.obs_vars, series)
+    for fwd in (False, True):
+        post, ll = b.infer(query, forward_only=fwd)
+        for i, got in enumerate(b.split(post)):
+            want, llw = om.infer(sp.obs_vars, series[i], query, forward_only=fwd)
+            assert_close(got, want, "factorial ns=%d series %d posterior (fwd=%s)" % (ns, i, fwd))
+            assert_close(ll[i], llw, "factorial ns=%d series %d loglik" % (ns, i))
+    want, ll_want, st_want = om.estep(sp.obs_vars, series)
+    counts, L, st = b.estep()
+    assert st == st_want == 0
+    assert_close(counts, want, "factorial ns=%d expected counts" % ns)
+    assert_close(L, ll_want, "factorial ns=%d EM loglik" % ns)
+
+
+def test_c3_full_size_vs_oracle(gpu_lib, oracle_lib):
+    """config C3 at its real size — 16 states per chain, three 16^6-entry cliques (403 MB of
+    tables), interface of 65 536 states — one short series against the oracle (which needs
+    about ten seconds per slice), plus the size-independent checks"""
+    from nip_b200.synth import FactorialSpec
+    sp = FactorialSpec(16, 4, seed=1)
+    fm = sp.flat()
+    series = [sp.sample(1, 2, seed=2)[0]]
+    query = [4, 6, 9]                               # X0, X2, W1
+    m = gpu_lib.Model(fm, engine=1)
+    b = m.batch(sp.obs_vars, series)
+    post, ll = b.infer(query)
+    want, llw = oracle_lib.model(fm).infer(sp.obs_vars, series[0], query)
+    assert_close(post, want, "C3 posterior")
+    assert_close(ll[0], llw, "C3 loglik")
+    assert np.allclose(post.reshape(2, 3, 16).sum(-1), 1.0, rtol=0, atol=1e-12)
+    counts, L, st = b.estep(add_pseudocount=False)
+    assert st == 0
+    assert_close(L, llw, "C3 EM loglik")
+    # every variable's expected family counts sum to the number of slices it is counted in
+    off = m.counts_offsets()
+    for v in range(fm.n_vars):
+        slices = 1 if v >= 8 else 2                 # W^i (previous slice) only at t = 0
+        assert abs(counts[off[v]:off[v + 1]].sum() - slices) < 1e-9

@@ -195,3 +195,18 @@ def test_against_reference_side_by_side(oracle_lib, ref_lib, tmp_path):
             pr, lr = rm.infer(ts, [1, 2, 0])
             po, lo = om.infer(h.obs_vars, s, [1, 2, 0])
             assert np.array_equal(pr, po) and lr == lo
+
+
+def test_factorial_generator_matches_reference_parse():
+    """nip_b200.synth.FactorialSpec states the join tree the reference builds for the factorial
+    family; for ns = 3 it must reproduce the golden fixture (generated from the reference's own
+    parser + triangulation) bit for bit, tables included"""
+    from nip_b200.synth import FactorialSpec
+    g = Case("factorial4x3").fm
+    f = FactorialSpec(3, 2, seed=15).flat()
+    for k in ("var_card", "var_flags", "var_parent_off", "var_parents", "var_family", "var_prior_off",
+              "var_prior", "clique_var_off", "clique_vars", "clique_tab_off", "clique_tables",
+              "sepset_cliques", "sepset_var_off", "sepset_vars", "clique_adj_off", "clique_adj",
+              "outgoing", "prev_outgoing"):
+        assert np.array_equal(np.asarray(getattr(f, k)), np.asarray(getattr(g, k))), k
+    assert (f.in_clique, f.out_clique) == (g.in_clique, g.out_clique)
