@@ -448,17 +448,20 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
 // beta_{t-1} (1 / sum of the sweep's result) is obtained during the sweep as
 // 1 / (r . colsum(A)), and the posterior of slice t, the alpha / evidence
 // prefetches and the stores all sit in the sweep's issue gaps.
-// EM variant: additionally stores, per slice, the row  rt[t] = r_t / Z_t  with
-// Z_t = own_{t-1} . (A . r_t) the mass of the slice's joint, so that the expected
-// transition counts become one GEMM  sum_t own_{t-1}^T rt[t]  (k_chain_counts), and
-// r0[series] = r_0 / (phi0 . r_0) for the first slice.
+// EM variant: stores, per slice, only the scaled beta_t it carries (rt[t]) and the scale h_t
+// with beta_{t-1} = h_t A r_t (hvec[t]); it neither reads the forward store nor forms
+// posteriors.  Everything the E-step needs follows from (own_t, beta_t, h_t, evidence index)
+// row by row in k_chain_stats: posterior_t = own_t beta_t / N_t with N_t = own_t . beta_t, and
+// the slice's joint mass Z_t = own_{t-1} . (A r_t) = N_{t-1} / h_t.  r0[series] =
+// r_0 / (phi0 . r_0) is still written here for the first slice.
 template <int NT, bool VEC, bool EM>
 __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatchDev B,
                                                            const double* __restrict__ alpha,
                                                            double* __restrict__ post,
                                                            int post_stride, int post_off,
                                                            double* __restrict__ rt,
-                                                           double* __restrict__ r0) {
+                                                           double* __restrict__ r0,
+                                                           double* __restrict__ hvec) {
   constexpr int SP = 8 * NT;
   extern __shared__ double sB[];
   double* s_cs = sB + SP * SP;
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   // prologue: the longest rows start at slice Tw-1 with beta = 1, r = lambda
   const bool has_last = Tw >= 1 && Tw - 1 < T;
   load_row(C.lam_comb + (long long)(has_last ? cfg[Tw - 1] : 0) * SP, has_last, r);
-  load_row(alpha + (row0 + Tw - 1) * SP, has_last, a);
+  if (!EM) load_row(alpha + (row0 + Tw - 1) * SP, has_last, a);
 #pragma unroll
   for (int n = 0; n < NT; n++) beta[n][0] = beta[n][1] = 1.0;
   int c_pre = (Tw >= 2 && Tw - 2 < T) ? cfg[Tw - 2] : 0;
@@ -513,21 +516,29 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   auto item = [&](auto wc) {
     constexpr int w = decltype(wc)::value;
     if constexpr (w >= I_MUL && w < I_RED) {
-      constexpr int i = w - I_MUL;
-      a[i >> 1][i & 1] *= beta[i >> 1][i & 1];
-      if constexpr (i < 4) ps[i & 3] = a[i >> 1][i & 1];
-      else ps[i & 3] += a[i >> 1][i & 1];
+      if constexpr (!EM) {
+        constexpr int i = w - I_MUL;
+        a[i >> 1][i & 1] *= beta[i >> 1][i & 1];
+        if constexpr (i < 4) ps[i & 3] = a[i >> 1][i & 1];
+        else ps[i & 3] += a[i >> 1][i & 1];
+      }
     } else if constexpr (w == I_RED) {
-      if constexpr (E >= 4) psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-      else psum = ps[0] + ps[1];
+      if constexpr (!EM) {
+        if constexpr (E >= 4) psum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+        else psum = ps[0] + ps[1];
+      }
     } else if constexpr (w == I_RED + 1) {
-      psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+      if constexpr (!EM) psum += __shfl_xor_sync(0xffffffffu, psum, 1);
     } else if constexpr (w == I_RED + 2) {
-      psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+      if constexpr (!EM) psum += __shfl_xor_sync(0xffffffffu, psum, 2);
     } else if constexpr (w == I_INV) {
-      pinv = safe_rcp(psum);
+      if constexpr (!EM) pinv = safe_rcp(psum);
     } else if constexpr (w >= I_ST && w < I_LD) {   // posterior of slice t: normalise(alpha_t * beta_t)
       constexpr int n = w - I_ST;
+      if constexpr (EM) {  // E-step: the carried beta_t itself
+        if (on) reinterpret_cast<double2*>(rt + (row0 + t_cur) * SP)[4 * n + q] = make_double2(beta[n][0], beta[n][1]);
+        return;
+      }
       double* prow = post + (row0 + t_cur) * post_stride + post_off;
       if (VEC) {
         if (on) reinterpret_cast<double2*>(prow)[4 * n + q] = make_double2(a[n][0] * pinv, a[n][1] * pinv);
@@ -537,9 +548,11 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
         if (on && col + 1 < C.S) prow[col + 1] = a[n][1] * pinv;
       }
     } else if constexpr (w >= I_LD && w < I_DOT) {
-      constexpr int n = w - I_LD;
-      a[n][0] = an[n][0];
-      a[n][1] = an[n][1];
+      if constexpr (!EM) {
+        constexpr int n = w - I_LD;
+        a[n][0] = an[n][0];
+        a[n][1] = an[n][1];
+      }
     } else if constexpr (w >= I_DOT && w < I_DRED) {
       constexpr int n = w - I_DOT;
       const double2 v = csv[4 * n + q];
@@ -554,6 +567,9 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
     } else if constexpr (w == I_H) {
       h = safe_rcp(dsum);
       hs = first_next ? 1.0 : h;
+      if constexpr (EM) {
+        if (on && q == 0) hvec[row0 + t_cur] = h;
+      }
     } else if constexpr (w >= I_LAM && w < W_ITEMS) {
       constexpr int n = w - I_LAM;
       lam[n][0] *= hs;
@@ -567,7 +583,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   {
     const bool p0 = Tw >= 2 && Tw - 2 < T;
     load_row(C.lam_comb + (long long)c_pre * SP, p0, lam);
-    load_row(alpha + (row0 + Tw - 2) * SP, p0, an);
+    if (!EM) load_row(alpha + (row0 + Tw - 2) * SP, p0, an);
     if (Tw >= 3 && Tw - 3 < T) c_pre = __ldg(cfg + Tw - 3);
   }
   for (int t = Tw - 1; t >= 1; t--) {
@@ -577,16 +593,6 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
     t_cur = t;
     // u = r . A^T  (k = current state, n = previous state)
     mma_sweep<NT>(u, r, frag, [&](auto sc) { run_items<2 * NT * NT, W_ITEMS, decltype(sc)::value>(item); });
-    if (EM) {  // a = own_{t-1} (loaded in the sweep), u = A . r_t
-      double z0 = 0, z1 = 0;
-#pragma unroll
-      for (int n = 0; n < NT; n++) { z0 += a[n][0] * u[n][0]; z1 += a[n][1] * u[n][1]; }
-      const double zinv = safe_rcp(quad_sum_full(z0 + z1));
-      double2* rrow = reinterpret_cast<double2*>(rt + (row0 + t) * SP);
-#pragma unroll
-      for (int n = 0; n < NT; n++)
-        if (on) rrow[4 * n + q] = make_double2(r[n][0] * zinv, r[n][1] * zinv);
-    }
 #pragma unroll
     for (int n = 0; n < NT; n++) {
       beta[n][0] = first_next ? 1.0 : u[n][0] * h;
@@ -597,7 +603,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
     {  // requests for iteration t-1: lambda_{t-2}, alpha_{t-2}, evidence index of slice t-3
       const bool p2 = t >= 2 && t - 2 < T;
       load_row(C.lam_comb + (long long)c_pre * SP, p2, lam);
-      load_row(alpha + (row0 + t - 2) * SP, p2, an);
+      if (!EM) load_row(alpha + (row0 + t - 2) * SP, p2, an);
       if (t >= 3 && t - 3 < T) c_pre = __ldg(cfg + t - 3);
     }
   }
@@ -616,61 +622,211 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
     const double zinv = safe_rcp(quad_sum_full(z0 + z1));
     if (0 < T) {
       double2* out0 = reinterpret_cast<double2*>(r0 + (long long)orig * SP);
-      double2* rrow = reinterpret_cast<double2*>(rt + row0 * SP);
 #pragma unroll
-      for (int n = 0; n < NT; n++) {
-        out0[4 * n + q] = make_double2(r[n][0] * zinv, r[n][1] * zinv);
-        rrow[4 * n + q] = make_double2(0.0, 0.0);
-      }
+      for (int n = 0; n < NT; n++) out0[4 * n + q] = make_double2(r[n][0] * zinv, r[n][1] * zinv);
     }
   }
 }
 
 // ----------------------------------------------------------------- EM ----
-// G[i_prev][i_cur] = sum over data rows k >= 1 of own[k-1][i_prev] * rt[k][i_cur]
-// (rt is zero on every series' first row, so the shifted product never pairs two
-// series).  Split-K over CTAs, partial tiles reduced afterwards in a fixed order.
+// Sufficient statistics of the whole batch in one pass over the two row stores
+// (own[k] from the forward kernel, bt[k] = beta_k and hv[k] = h_k from the backward kernel):
+//   N_k      = own_k . beta_k
+//   G[i][j] += own_{k-1}[i] (h_k / N_{k-1}) * lambda_{c_k}[j] beta_k[j]   (rows that do not open a series)
+//   Cc[c_k][j] += own_k[j] beta_k[j] / N_k                                (posterior of the row)
+// G is a DMMA GEMM over the rows (split-K over CTAs, warp w owns the 8 previous states
+// 8w..8w+7); the row-wise scalars and the evidence row are folded into its operands while the
+// tile sits in shared memory, and the posterior rows are added into `phases` private tables
+// (thread = column x phase, rows in ascending order: deterministic).  Tiles of 32 rows arrive
+// through a two-stage cp.async pipeline; partial results are reduced afterwards in a fixed order.
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
 template <int NT>
-__global__ void __launch_bounds__(32 * NT) k_chain_counts(const double* __restrict__ own,
-                                                          const double* __restrict__ rt,
-                                                          long long rows, double* __restrict__ part) {
-  constexpr int SP = 8 * NT, KC = 32, LD = SP + 2;
+__global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
+    k_chain_stats(const double* __restrict__ own, const double* __restrict__ bt, const double* __restrict__ hv,
+                  const int* __restrict__ cfg, const unsigned char* __restrict__ first,
+                  const double* __restrict__ lam_comb, long long rows, int n_comb, int phases,
+                  double* __restrict__ partG, double* __restrict__ partC) {
+  // NT m-tiles x GR halves of the n-tiles: 2 NT warps keep four warps on every scheduler
+  constexpr int SP = 8 * NT, KC = 32, LD = SP + 4, GR = NT >= 2 ? 2 : 1, NW = NT * GR, NTH = 32 * NW;
+  constexpr int TR = KC + 1, NH = NT / GR, STG = 2 * TR * LD;
   extern __shared__ double sm[];
-  double* sA = sm;
-  double* sR = sm + KC * LD;
+  constexpr int NS = 3;                     // tile stages in flight (cp.async)
+  double* s_post = sm + NS * STG;           // [TR][LD] normalised posterior rows of the tile
+  double* s_h = s_post + TR * LD;           // [NS][TR + 1] h of the tile's rows, per stage
+  double* s_lam = s_h + NS * (TR + 1);      // [n_comb][SP] evidence rows
+  const int tab = n_comb * SP;
+  double* s_tab = s_lam + tab;              // [phases][n_comb][SP]
+  int* s_c = reinterpret_cast<int*>(s_tab + (long long)phases * tab);  // [NS][TR + 1] evidence index, -1 - c: opens a series
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, w = threadIdx.x >> 5;
+  const int mt = w % NT, nh = w / NT;
+  for (int x = threadIdx.x; x < phases * tab; x += NTH) s_tab[x] = 0.0;
+  for (int x = threadIdx.x; x < tab; x += NTH) s_lam[x] = lam_comb[x];
+
   long long chunk = (rows + gridDim.x - 1) / gridDim.x;
   chunk = (chunk + KC - 1) / KC * KC;
   const long long k_begin = (long long)blockIdx.x * chunk;
   const long long k_end = k_begin + chunk < rows ? k_begin + chunk : rows;
-  double acc[NT][2];
-#pragma unroll
-  for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
-  for (long long k0 = k_begin; k0 < k_end; k0 += KC) {
-    for (int x = threadIdx.x; x < KC * (SP / 2); x += blockDim.x) {
+
+  // stage s: own rows at sm + s * STG, beta rows TR * LD further; tile row i of a tile starting
+  // at k0 holds data row k0 - 1 + i
+  auto fetch = [&](int stage, long long k0) {
+    double* so = sm + stage * STG;
+    double* sb = so + TR * LD;
+    for (int x = threadIdx.x; x < TR * (SP / 2); x += NTH) {
       const int i = x / (SP / 2), c = 2 * (x - i * (SP / 2));
-      const long long k = k0 + i;
-      const double2 vr = k < k_end ? __ldg(reinterpret_cast<const double2*>(rt + k * SP + c)) : make_double2(0.0, 0.0);
-      const double2 va = (k < k_end && k >= 1) ? __ldg(reinterpret_cast<const double2*>(own + (k - 1) * SP + c))
-                                               : make_double2(0.0, 0.0);
-      *reinterpret_cast<double2*>(sR + i * LD + c) = vr;
-      *reinterpret_cast<double2*>(sA + i * LD + c) = va;
+      const long long k = k0 - 1 + i;
+      const bool ok = k >= 0 && k < k_end;
+      const long long ks = ok ? k : 0;
+      cp_async16_zfill(so + i * LD + c, own + ks * SP + c, ok);
+      cp_async16_zfill(sb + i * LD + c, bt + ks * SP + c, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // per-row scalars of a tile travel one tile ahead through registers (thread i <-> tile row i)
+  constexpr int MS = (TR + NTH - 1) / NTH;  // tile rows per thread (2 only for the one-warp CTA)
+  int m_c[MS];
+  unsigned char m_f[MS];
+  double m_h[MS];
+  auto meta_load = [&](long long k0) {  // only requests: nothing here waits for the values
+#pragma unroll
+    for (int u = 0; u < MS; u++) {
+      const int i = threadIdx.x + u * NTH;
+      const long long k = k0 - 1 + i;
+      const bool ok = i < TR && k >= 0 && k < k_end;
+      m_f[u] = ok ? __ldg(first + k) : 0;
+      m_c[u] = ok ? __ldg(cfg + k) : 0;
+      m_h[u] = ok ? __ldg(hv + k) : 0.0;
+    }
+  };
+  auto meta_store = [&](int stage) {
+#pragma unroll
+    for (int u = 0; u < MS; u++) {
+      const int i = threadIdx.x + u * NTH;
+      if (i < TR) {
+        s_c[stage * (TR + 1) + i] = m_f[u] ? -1 - m_c[u] : m_c[u];
+        s_h[stage * (TR + 1) + i] = m_h[u];
+      }
+    }
+  };
+
+  double acc[NH > 0 ? NH : 1][2];
+#pragma unroll
+  for (int n = 0; n < NH; n++) acc[n][0] = acc[n][1] = 0.0;
+  // tiles k0, k0 + KC are in flight when tile k0 is consumed; the per-row scalars run one tile ahead
+  if (k_begin < k_end) {
+    fetch(0, k_begin);
+    meta_load(k_begin);
+    meta_store(0);
+  }
+  if (k_begin + KC < k_end) fetch(1, k_begin + KC);
+  int stage = 0;
+  for (long long k0 = k_begin; k0 < k_end; k0 += KC, stage = stage + 1 == NS ? 0 : stage + 1) {
+    const int st1 = stage + 1 >= NS ? stage + 1 - NS : stage + 1, st2 = stage + 2 >= NS ? stage + 2 - NS : stage + 2;
+    const bool more = k0 + KC < k_end;
+    if (more) meta_load(k0 + KC);
+    if (k0 + 2 * KC < k_end) {
+      fetch(st2, k0 + 2 * KC);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+    } else if (more) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    double* so = sm + stage * STG;
+    double* sb = so + TR * LD;
+    const int* sc = s_c + stage * (TR + 1);
+    const double* sh = s_h + stage * (TR + 1);
+    // ---- row pass: one warp per tile row, the rows of a warp interleaved for ILP ----
+    constexpr int RW = (TR + NW - 1) / NW, CW = (SP + 31) / 32;
+    {
+      double o[RW][CW], b[RW][CW], N[RW];
+#pragma unroll
+      for (int u = 0; u < RW; u++) {
+        const int i = w + u * NW;
+        double part = 0;
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+          const int col = lane + 32 * c;
+          const bool ok = i < TR && col < SP;
+          o[u][c] = ok ? so[i * LD + col] : 0.0;
+          b[u][c] = ok ? sb[i * LD + col] : 0.0;
+          part += o[u][c] * b[u][c];
+        }
+        N[u] = part;
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+        for (int u = 0; u < RW; u++) N[u] += __shfl_xor_sync(0xffffffffu, N[u], sft);
+#pragma unroll
+      for (int u = 0; u < RW; u++) {
+        const int i = w + u * NW;
+        if (i < TR) {
+          const double rn = N[u] != 0 ? 1.0 / N[u] : 0.0;
+          // the pair (this row, next row) counts unless the next row opens a series or lies outside
+          const bool pair = i < KC && k0 + i < k_end && sc[i + 1] >= 0;
+          const double wk = pair ? sh[i + 1] * rn : 0.0;
+          const int cc = sc[i] >= 0 ? sc[i] : -1 - sc[i];
+          const double* lam = s_lam + cc * SP;
+#pragma unroll
+          for (int c = 0; c < CW; c++) {
+            const int col = lane + 32 * c;
+            if (col < SP) {
+              s_post[i * LD + col] = o[u][c] * b[u][c] * rn;
+              so[i * LD + col] = o[u][c] * wk;
+              sb[i * LD + col] = b[u][c] * lam[col];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- G += Aop^T Bop (rows k0 .. k0+KC-1: A from tile row i-1, B from tile row i) ----
 #pragma unroll
     for (int kk = 0; kk < KC / 4; kk++) {
-      const double a = sA[(4 * kk + q) * LD + 8 * w + g];
+      const double a = so[(4 * kk + q) * LD + 8 * mt + g];
 #pragma unroll
-      for (int n = 0; n < NT; n++) dmma(acc[n][0], acc[n][1], a, sR[(4 * kk + q) * LD + 8 * n + g]);
+      for (int n = 0; n < NH; n++)
+        dmma(acc[n][0], acc[n][1], a, sb[(4 * kk + q + 1) * LD + 8 * (nh * NH + n) + g]);
     }
+    // ---- posterior rows into the evidence-indexed tables ----
+    {
+      const int col = threadIdx.x % SP, ph = threadIdx.x / SP;
+      if (ph < phases) {
+        double* mine = s_tab + (long long)ph * tab + col;
+        for (int i = 1 + ph; i < TR; i += phases) {
+          const int cc = sc[i] >= 0 ? sc[i] : -1 - sc[i];
+          mine[cc * SP] += s_post[i * LD + col];
+        }
+      }
+    }
+    if (more) meta_store(st1);
     __syncthreads();
   }
-  double* out = part + (long long)blockIdx.x * SP * SP;
+  double* outG = partG + (long long)blockIdx.x * SP * SP;
 #pragma unroll
-  for (int n = 0; n < NT; n++) {
-    out[(8 * w + g) * SP + 8 * n + 2 * q] = acc[n][0];
-    out[(8 * w + g) * SP + 8 * n + 2 * q + 1] = acc[n][1];
+  for (int n = 0; n < NH; n++) {
+    outG[(8 * mt + g) * SP + 8 * (nh * NH + n) + 2 * q] = acc[n][0];
+    outG[(8 * mt + g) * SP + 8 * (nh * NH + n) + 2 * q + 1] = acc[n][1];
   }
+  double* outC = partC + (long long)blockIdx.x * tab;
+  for (int x = threadIdx.x; x < tab; x += NTH) {
+    double s = 0;
+    for (int ph = 0; ph < phases; ph++) s += s_tab[(long long)ph * tab + x];
+    outC[x] = s;
+  }
+}
+
+// first[k] = 1 on the rows that open a series
+__global__ void k_chain_first(const long long* row_off, int n_series, long long rows, unsigned char* first) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_series && row_off[s] < rows) first[row_off[s]] = 1;
 }
 
 // out[x] = sum_p part[p][x] in a fixed order
@@ -691,41 +847,6 @@ __global__ void k_chain_g0(const double* r0, int n_series, int SP, double* g0) {
   for (int b = threadIdx.x; b < n_series; b += blockDim.x) s += r0[(long long)b * SP + ip];
   s = block_sum(s, red);
   if (threadIdx.x == 0) g0[ip] = s;
-}
-
-// Cc[c][ip] += posterior rows grouped by their combined evidence index; every warp owns a
-// private table in shared memory and a contiguous range of rows (deterministic).
-__global__ void k_chain_leafcount(const double* __restrict__ postj, const int* __restrict__ cfg,
-                                  long long rows, int n_comb, int SP, double* __restrict__ part) {
-  extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int tab = n_comb * SP;
-  double* mine = sm + (long long)w * tab;
-  for (int x = lane; x < tab; x += 32) mine[x] = 0.0;
-  __syncwarp();
-  const long long nwarps = (long long)gridDim.x * nw, me = (long long)blockIdx.x * nw + w;
-  const long long per = (rows + nwarps - 1) / nwarps;
-  const long long k_end = (me + 1) * per < rows ? (me + 1) * per : rows;
-  constexpr int U = 8;                       // rows in flight: the loads are issued before any is used
-  for (long long k0 = me * per; k0 < k_end; k0 += U) {
-    int c[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) c[u] = k0 + u < k_end ? __ldg(cfg + k0 + u) : 0;
-    for (int col = lane; col < SP; col += 32) {
-      double v[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) v[u] = k0 + u < k_end ? __ldg(postj + (k0 + u) * SP + col) : 0.0;
-#pragma unroll
-      for (int u = 0; u < U; u++) mine[c[u] * SP + col] += v[u];   // in row order: deterministic
-    }
-  }
-  __syncthreads();
-  double* out = part + (long long)blockIdx.x * tab;
-  for (int x = threadIdx.x; x < tab; x += blockDim.x) {
-    double s = 0;
-    for (int k = 0; k < nw; k++) s += sm[(long long)k * tab + x];
-    out[x] = s;
-  }
 }
 
 // expected table of the interface clique over all slices (E) and over first slices (E0)
@@ -833,28 +954,37 @@ int launch_backward(const ChainDev& C, const ChainBatchDev& B, const ChainInferA
   if (vec) {
     if (int e = set_smem(k_chain_backward<NT, true, false>, smem)) return e;
     k_chain_backward<NT, true, false><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride,
-                                                                a.post_off, nullptr, nullptr);
+                                                                a.post_off, nullptr, nullptr, nullptr);
   } else {
     if (int e = set_smem(k_chain_backward<NT, false, false>, smem)) return e;
     k_chain_backward<NT, false, false><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride,
-                                                                 a.post_off, nullptr, nullptr);
+                                                                 a.post_off, nullptr, nullptr, nullptr);
   }
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
 
+struct ChainStatsArgs {
+  double *bt, *hv, *r0;
+  const unsigned char* first;
+  long long rows;
+  int n_comb, phases, parts;
+  size_t smem;
+  double *partG, *partC;
+};
+
 template <int NT>
 int launch_em(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
-              double* postj, double* rt, double* r0, long long rows, int parts, double* part,
-              cudaStream_t st) {
+              const ChainStatsArgs& s, cudaStream_t st) {
   if (int e = launch_forward_v<NT, false, true>(C, B, a, alpha, st)) return e;
   const int grid = (B.n_series + 31) / 32;
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
   if (int e = set_smem(k_chain_backward<NT, true, true>, smem)) return e;
-  k_chain_backward<NT, true, true><<<grid, 128, smem, st>>>(C, B, alpha, postj, C.SP, 0, rt, r0);
+  k_chain_backward<NT, true, true><<<grid, 128, smem, st>>>(C, B, alpha, nullptr, C.SP, 0, s.bt, s.r0, s.hv);
   NIPGPU_LAUNCHED();
-  const size_t smem2 = sizeof(double) * 2 * 32 * (8 * NT + 2);
-  k_chain_counts<NT><<<parts, 32 * NT, smem2, st>>>(alpha, rt, rows, part);
+  if (int e = set_smem(k_chain_stats<NT>, s.smem)) return e;
+  k_chain_stats<NT><<<s.parts, 32 * NT * (NT >= 2 ? 2 : 1), s.smem, st>>>(alpha, s.bt, s.hv, B.cfg, s.first, C.lam_comb, s.rows,
+                                                      s.n_comb, s.phases, s.partG, s.partC);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
@@ -1125,7 +1255,7 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
 void chain_batch_free(ChainBatch& cb) {
   cudaFree(cb.d_order); cudaFree(cb.d_len_sorted); cudaFree(cb.d_cfg); cudaFree(cb.d_alpha);
   cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_rows); cudaFree(cb.d_comb);
-  cudaFree(cb.d_postj); cudaFree(cb.d_rt); cudaFree(cb.d_r0); cudaFree(cb.d_em_scratch);
+  cudaFree(cb.d_rt); cudaFree(cb.d_hvec); cudaFree(cb.d_first); cudaFree(cb.d_r0); cudaFree(cb.d_em_scratch);
   cudaFree(cb.d_dense); cudaFree(cb.d_dense_i);
   cb = ChainBatch();
 }
@@ -1236,19 +1366,28 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   const int SP = cm.SP, S = cm.S;
   if (cm.dense) return NIPGPU_EUNSUPPORTED;   // EM for |I| > 64 goes through the generic engine
   const size_t tab = (size_t)plan.n_comb * SP;
-  int lc_warps = 8;
-  while (lc_warps > 1 && lc_warps * tab * sizeof(double) > 200 * 1024) lc_warps /= 2;
-  if (lc_warps * tab * sizeof(double) > 200 * 1024) return NIPGPU_EUNSUPPORTED;
+  // k_chain_stats: two (own, beta) tile stages + posterior tile + `phases` evidence-indexed tables
+  const size_t stats_fixed = sizeof(double) * (7 * 33 * (SP + 4) + 3 * 34 + tab) + 3 * 34 * sizeof(int) + 16;
+  int phases = 4;
+  while (phases > 1 && stats_fixed + phases * tab * sizeof(double) > 220 * 1024) phases /= 2;
+  if (stats_fixed + phases * tab * sizeof(double) > 220 * 1024) return NIPGPU_EUNSUPPORTED;
   for (int l = 0; l < cm.n_real; l++)
     if (cm.leaves[l].free_vars.size() > 8) return NIPGPU_EUNSUPPORTED;
   if (int e = chain_prepare_evidence(cm, cb, plan, a, st)) return e;
 
   const long long rows = std::max<long long>(a.rows, 1);
-  const int parts = std::max(1, x.sm_count) * 4;   // CTAs of the split-K count GEMM (4 per SM)
-  if (!cb.d_postj) {
-    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_postj, rows * SP * sizeof(double)));
+  const int parts = std::max(1, x.sm_count);   // CTAs of the statistics kernel (one per SM, split-K)
+  if (!cb.d_rt) {
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_rt, rows * SP * sizeof(double)));
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_hvec, rows * sizeof(double)));
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_first, rows));
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_r0, (size_t)std::max(a.n_series, 1) * SP * sizeof(double)));
+    NIPGPU_CUDA(cudaMemsetAsync(cb.d_first, 0, rows, st));
+    NIPGPU_CUDA(cudaMemsetAsync(cb.d_hvec, 0, rows * sizeof(double), st));
+    if (a.n_series > 0) {
+      k_chain_first<<<(a.n_series + 255) / 256, 256, 0, st>>>(a.d_row_off, a.n_series, a.rows, cb.d_first);
+      NIPGPU_LAUNCHED();
+    }
   }
   // scratch: part_G | G | g0 | part_C | Cc | E | E0
   const size_t n_partG = (size_t)parts * SP * SP, n_G = (size_t)SP * SP, n_partC = (size_t)parts * tab;
@@ -1278,30 +1417,29 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   NIPGPU_CUDA(cudaMemsetAsync(cb.d_r0, 0, (size_t)std::max(a.n_series, 1) * SP * sizeof(double), st));
   if (ev0) NIPGPU_CUDA(cudaEventRecord(ev0, st));
   int e = NIPGPU_OK;
+  ChainStatsArgs sa;
+  sa.bt = cb.d_rt; sa.hv = cb.d_hvec; sa.r0 = cb.d_r0; sa.first = cb.d_first; sa.rows = a.rows;
+  sa.n_comb = plan.n_comb; sa.phases = phases; sa.parts = parts;
+  sa.smem = stats_fixed + phases * tab * sizeof(double);
+  sa.partG = partG; sa.partC = partC;
   if (a.n_series > 0) {
     switch (cm.NT) {
-      case 1: e = launch_em<1>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
-      case 2: e = launch_em<2>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
-      case 4: e = launch_em<4>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
-      case 8: e = launch_em<8>(C, B, a, cb.d_alpha, cb.d_postj, cb.d_rt, cb.d_r0, a.rows, parts, partG, st); break;
+      case 1: e = launch_em<1>(C, B, a, cb.d_alpha, sa, st); break;
+      case 2: e = launch_em<2>(C, B, a, cb.d_alpha, sa, st); break;
+      case 4: e = launch_em<4>(C, B, a, cb.d_alpha, sa, st); break;
+      case 8: e = launch_em<8>(C, B, a, cb.d_alpha, sa, st); break;
       default: return NIPGPU_EUNSUPPORTED;
     }
     if (e) return e;
   } else {
-    NIPGPU_CUDA(cudaMemsetAsync(partG, 0, n_partG * sizeof(double), st));
+    NIPGPU_CUDA(cudaMemsetAsync(partG, 0, (n_partG + n_G + SP + n_partC) * sizeof(double), st));
   }
   k_chain_sum_parts<<<(unsigned)((n_G + 255) / 256), 256, 0, st>>>(partG, parts, (long long)n_G, G);
   NIPGPU_LAUNCHED();
   k_chain_g0<<<SP, 256, 0, st>>>(cb.d_r0, a.n_series, SP, g0);
   NIPGPU_LAUNCHED();
-  {
-    const size_t smem = (size_t)lc_warps * tab * sizeof(double);
-    if (int e2 = set_smem(k_chain_leafcount, smem)) return e2;
-    k_chain_leafcount<<<x.sm_count, 32 * lc_warps, smem, st>>>(cb.d_postj, cb.d_cfg, a.rows, plan.n_comb, SP, partC);
-    NIPGPU_LAUNCHED();
-    k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, x.sm_count, (long long)tab, Cc);
-    NIPGPU_LAUNCHED();
-  }
+  k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, parts, (long long)tab, Cc);
+  NIPGPU_LAUNCHED();
   if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
   // ---- expected clique tables ----
   const int n0 = hm.csize[cm.c0];

@@ -73,7 +73,8 @@ struct ChainBatch {
   double* d_dense = nullptr;
   int* d_dense_i = nullptr;
   // EM (chain_estep)
-  double *d_postj = nullptr, *d_rt = nullptr, *d_r0 = nullptr, *d_em_scratch = nullptr;
+  double *d_rt = nullptr, *d_hvec = nullptr, *d_r0 = nullptr, *d_em_scratch = nullptr;  // beta rows, h_t, r_0 rows
+  unsigned char* d_first = nullptr;  // [rows] 1 on the first row of every series
   size_t em_scratch_cap = 0;
 };
 
