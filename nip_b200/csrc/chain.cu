@@ -653,15 +653,16 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
                   double* __restrict__ partG, double* __restrict__ partC) {
   // NT m-tiles x GR halves of the n-tiles: 2 NT warps keep four warps on every scheduler
   constexpr int SP = 8 * NT, KC = 32, LD = SP + 4, GR = NT >= 2 ? 2 : 1, NW = NT * GR, NTH = 32 * NW;
-  constexpr int TR = KC + 1, NH = NT / GR, STG = 2 * TR * LD;
+  constexpr int TR = KC + 1, NH = NT / GR, STG = 3 * TR * LD;
+  constexpr int RW = (TR + NW - 1) / NW, CW = (SP + 31) / 32;   // tile rows per warp, columns per lane
   extern __shared__ double sm[];
-  constexpr int NS = 3;                     // tile stages in flight (cp.async)
-  double* s_post = sm + NS * STG;           // [TR][LD] normalised posterior rows of the tile
-  double* s_h = s_post + TR * LD;           // [NS][TR + 1] h of the tile's rows, per stage
-  double* s_lam = s_h + NS * (TR + 1);      // [n_comb][SP] evidence rows
+  // stage s (2): Aop rows at sm + s * STG, Bop rows TR * LD further, posterior rows 2 TR LD further;
+  // tile row i of the tile starting at k0 holds data row k0 - 1 + i
+  double* s_h = sm + 2 * STG;               // [3][TR + 1] h of the tile's rows (tile t in slot t % 3)
+  double* s_lam = s_h + 3 * (TR + 1) + 1;   // [n_comb][SP] evidence rows
   const int tab = n_comb * SP;
   double* s_tab = s_lam + tab;              // [phases][n_comb][SP]
-  int* s_c = reinterpret_cast<int*>(s_tab + (long long)phases * tab);  // [NS][TR + 1] evidence index, -1 - c: opens a series
+  int* s_c = reinterpret_cast<int*>(s_tab + (long long)phases * tab);  // [3][TR + 1] evidence index, -1 - c: opens a series
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, w = threadIdx.x >> 5;
   const int mt = w % NT, nh = w / NT;
   for (int x = threadIdx.x; x < phases * tab; x += NTH) s_tab[x] = 0.0;
@@ -672,23 +673,26 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
   const long long k_begin = (long long)blockIdx.x * chunk;
   const long long k_end = k_begin + chunk < rows ? k_begin + chunk : rows;
 
-  // stage s: own rows at sm + s * STG, beta rows TR * LD further; tile row i of a tile starting
-  // at k0 holds data row k0 - 1 + i
-  auto fetch = [&](int stage, long long k0) {
-    double* so = sm + stage * STG;
-    double* sb = so + TR * LD;
-    for (int x = threadIdx.x; x < TR * (SP / 2); x += NTH) {
-      const int i = x / (SP / 2), c = 2 * (x - i * (SP / 2));
+  // The rows of the next tile travel through registers: requested before the tensor work of
+  // the current tile, turned into operands after it (no staging copy in shared memory).
+  double ro[RW][CW], rb[RW][CW];
+  auto rows_load = [&](long long k0) {
+#pragma unroll
+    for (int u = 0; u < RW; u++) {
+      const int i = w + u * NW;
       const long long k = k0 - 1 + i;
-      const bool ok = k >= 0 && k < k_end;
-      const long long ks = ok ? k : 0;
-      cp_async16_zfill(so + i * LD + c, own + ks * SP + c, ok);
-      cp_async16_zfill(sb + i * LD + c, bt + ks * SP + c, ok);
+      const bool okr = i < TR && k >= 0 && k < k_end;
+#pragma unroll
+      for (int c = 0; c < CW; c++) {
+        const int col = lane + 32 * c;
+        const bool ok = okr && col < SP;
+        ro[u][c] = ok ? __ldg(own + k * SP + col) : 0.0;
+        rb[u][c] = ok ? __ldg(bt + k * SP + col) : 0.0;
+      }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  // per-row scalars of a tile travel one tile ahead through registers (thread i <-> tile row i)
-  constexpr int MS = (TR + NTH - 1) / NTH;  // tile rows per thread (2 only for the one-warp CTA)
+  // per-row scalars run one tile further ahead (thread i <-> tile row i): row i needs row i+1's
+  constexpr int MS = (TR + NTH - 1) / NTH;
   int m_c[MS];
   unsigned char m_f[MS];
   double m_h[MS];
@@ -703,13 +707,54 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
       m_h[u] = ok ? __ldg(hv + k) : 0.0;
     }
   };
-  auto meta_store = [&](int stage) {
+  auto meta_store = [&](int slot) {
 #pragma unroll
     for (int u = 0; u < MS; u++) {
       const int i = threadIdx.x + u * NTH;
       if (i < TR) {
-        s_c[stage * (TR + 1) + i] = m_f[u] ? -1 - m_c[u] : m_c[u];
-        s_h[stage * (TR + 1) + i] = m_h[u];
+        s_c[slot * (TR + 1) + i] = m_f[u] ? -1 - m_c[u] : m_c[u];
+        s_h[slot * (TR + 1) + i] = m_h[u];
+      }
+    }
+  };
+  // registers -> operands of the tile starting at k0, in stage `stage`; its scalars sit in `slot`
+  auto rows_pass = [&](int stage, int slot, long long k0) {
+    double* so = sm + stage * STG;
+    double* sb = so + TR * LD;
+    double* sp = sb + TR * LD;
+    const int* sc = s_c + slot * (TR + 1);
+    const double* sh = s_h + slot * (TR + 1);
+    double N[RW];
+#pragma unroll
+    for (int u = 0; u < RW; u++) {
+      double part = 0;
+#pragma unroll
+      for (int c = 0; c < CW; c++) part += ro[u][c] * rb[u][c];
+      N[u] = part;
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+      for (int u = 0; u < RW; u++) N[u] += __shfl_xor_sync(0xffffffffu, N[u], sft);
+#pragma unroll
+    for (int u = 0; u < RW; u++) {
+      const int i = w + u * NW;
+      if (i < TR) {
+        const double rn = N[u] != 0 ? 1.0 / N[u] : 0.0;
+        // the pair (this row, next row) counts unless the next row opens a series or lies outside
+        const bool pair = i < KC && k0 + i < k_end && sc[i + 1] >= 0;
+        const double wk = pair ? sh[i + 1] * rn : 0.0;
+        const int cc = sc[i] >= 0 ? sc[i] : -1 - sc[i];
+        const double* lam = s_lam + cc * SP;
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+          const int col = lane + 32 * c;
+          if (col < SP) {
+            sp[i * LD + col] = ro[u][c] * rb[u][c] * rn;
+            so[i * LD + col] = ro[u][c] * wk;
+            sb[i * LD + col] = rb[u][c] * lam[col];
+          }
+        }
       }
     }
   };
@@ -717,76 +762,28 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
   double acc[NH > 0 ? NH : 1][2];
 #pragma unroll
   for (int n = 0; n < NH; n++) acc[n][0] = acc[n][1] = 0.0;
-  // tiles k0, k0 + KC are in flight when tile k0 is consumed; the per-row scalars run one tile ahead
-  if (k_begin < k_end) {
-    fetch(0, k_begin);
+  if (k_begin < k_end) {  // prologue: tile 0 becomes operands, the scalars of tile 1 are parked
     meta_load(k_begin);
     meta_store(0);
+    rows_load(k_begin);
+    __syncthreads();
+    rows_pass(0, 0, k_begin);
+    if (k_begin + KC < k_end) {
+      meta_load(k_begin + KC);
+      meta_store(1);
+    }
   }
-  if (k_begin + KC < k_end) fetch(1, k_begin + KC);
-  int stage = 0;
-  for (long long k0 = k_begin; k0 < k_end; k0 += KC, stage = stage + 1 == NS ? 0 : stage + 1) {
-    const int st1 = stage + 1 >= NS ? stage + 1 - NS : stage + 1, st2 = stage + 2 >= NS ? stage + 2 - NS : stage + 2;
-    const bool more = k0 + KC < k_end;
-    if (more) meta_load(k0 + KC);
-    if (k0 + 2 * KC < k_end) {
-      fetch(st2, k0 + 2 * KC);
-      asm volatile("cp.async.wait_group 2;" ::: "memory");
-    } else if (more) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    double* so = sm + stage * STG;
-    double* sb = so + TR * LD;
-    const int* sc = s_c + stage * (TR + 1);
-    const double* sh = s_h + stage * (TR + 1);
-    // ---- row pass: one warp per tile row, the rows of a warp interleaved for ILP ----
-    constexpr int RW = (TR + NW - 1) / NW, CW = (SP + 31) / 32;
-    {
-      double o[RW][CW], b[RW][CW], N[RW];
-#pragma unroll
-      for (int u = 0; u < RW; u++) {
-        const int i = w + u * NW;
-        double part = 0;
-#pragma unroll
-        for (int c = 0; c < CW; c++) {
-          const int col = lane + 32 * c;
-          const bool ok = i < TR && col < SP;
-          o[u][c] = ok ? so[i * LD + col] : 0.0;
-          b[u][c] = ok ? sb[i * LD + col] : 0.0;
-          part += o[u][c] * b[u][c];
-        }
-        N[u] = part;
-      }
-#pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1)
-#pragma unroll
-        for (int u = 0; u < RW; u++) N[u] += __shfl_xor_sync(0xffffffffu, N[u], sft);
-#pragma unroll
-      for (int u = 0; u < RW; u++) {
-        const int i = w + u * NW;
-        if (i < TR) {
-          const double rn = N[u] != 0 ? 1.0 / N[u] : 0.0;
-          // the pair (this row, next row) counts unless the next row opens a series or lies outside
-          const bool pair = i < KC && k0 + i < k_end && sc[i + 1] >= 0;
-          const double wk = pair ? sh[i + 1] * rn : 0.0;
-          const int cc = sc[i] >= 0 ? sc[i] : -1 - sc[i];
-          const double* lam = s_lam + cc * SP;
-#pragma unroll
-          for (int c = 0; c < CW; c++) {
-            const int col = lane + 32 * c;
-            if (col < SP) {
-              s_post[i * LD + col] = o[u][c] * b[u][c] * rn;
-              so[i * LD + col] = o[u][c] * wk;
-              sb[i * LD + col] = b[u][c] * lam[col];
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
+  __syncthreads();
+  int stage = 0, slot = 0;
+  for (long long k0 = k_begin; k0 < k_end; k0 += KC, stage ^= 1, slot = slot == 2 ? 0 : slot + 1) {
+    const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
+    const bool more = k0 + KC < k_end, more2 = k0 + 2 * KC < k_end;
+    if (more) rows_load(k0 + KC);
+    if (more2) meta_load(k0 + 2 * KC);
+    const double* so = sm + stage * STG;
+    const double* sb = so + TR * LD;
+    const double* sp = sb + TR * LD;
+    const int* sc = s_c + slot * (TR + 1);
     // ---- G += Aop^T Bop (rows k0 .. k0+KC-1: A from tile row i-1, B from tile row i) ----
 #pragma unroll
     for (int kk = 0; kk < KC / 4; kk++) {
@@ -802,11 +799,13 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
         double* mine = s_tab + (long long)ph * tab + col;
         for (int i = 1 + ph; i < TR; i += phases) {
           const int cc = sc[i] >= 0 ? sc[i] : -1 - sc[i];
-          mine[cc * SP] += s_post[i * LD + col];
+          mine[cc * SP] += sp[i * LD + col];
         }
       }
     }
-    if (more) meta_store(st1);
+    // ---- the next tile: registers -> operands in the other stage ----
+    if (more) rows_pass(stage ^ 1, slot1, k0 + KC);
+    if (more2) meta_store(slot2);  // scalars of tile k0 + 2 KC: a slot nobody reads in this iteration
     __syncthreads();
   }
   double* outG = partG + (long long)blockIdx.x * SP * SP;
@@ -1367,7 +1366,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   if (cm.dense) return NIPGPU_EUNSUPPORTED;   // EM for |I| > 64 goes through the generic engine
   const size_t tab = (size_t)plan.n_comb * SP;
   // k_chain_stats: two (own, beta) tile stages + posterior tile + `phases` evidence-indexed tables
-  const size_t stats_fixed = sizeof(double) * (7 * 33 * (SP + 4) + 3 * 34 + tab) + 3 * 34 * sizeof(int) + 16;
+  const size_t stats_fixed = sizeof(double) * (6 * 33 * (SP + 4) + 3 * 34 + 1 + tab) + 3 * 34 * sizeof(int) + 16;
   int phases = 4;
   while (phases > 1 && stats_fixed + phases * tab * sizeof(double) > 220 * 1024) phases /= 2;
   if (stats_fixed + phases * tab * sizeof(double) > 220 * 1024) return NIPGPU_EUNSUPPORTED;
