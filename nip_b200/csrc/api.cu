@@ -471,7 +471,7 @@ void nipgpu_batch_destroy(nipgpu_batch* b) {
   if (b->m) { cudaSetDevice(b->m->device); cudaStreamSynchronize(b->m->stream); }
   cudaFree(b->d_len); cudaFree(b->d_row_off); cudaFree(b->d_obs); cudaFree(b->d_obs_proj);
   cudaFree(b->d_qproj); cudaFree(b->d_qoff); cudaFree(b->d_alpha); cudaFree(b->d_post);
-  cudaFree(b->d_ll); cudaFree(b->d_like); cudaFree(b->d_status);
+  cudaFree(b->d_ll); cudaFree(b->d_like); cudaFree(b->d_status); cudaFree(b->d_first);
   chain_batch_free(b->chain);
   delete b;
 }
@@ -629,6 +629,65 @@ int nipgpu_likelihood(nipgpu_model* m, nipgpu_batch* b, const uint8_t* evidence_
   if (!b->d_like) NIPGPU_CUDA(cudaMalloc((void**)&b->d_like, std::max<size_t>((size_t)b->rows * 2, 1) * sizeof(double)));
   const DBatch B = dev_batch(b, nullptr);
   const JtLaunch l = jt_fit(m->launch, b->n_series);
+
+  // ---- few evidence configurations: evaluate each once, the records gather ----
+  const HostModel& hm = m->hm;
+  std::vector<int> col_stride(std::max(b->n_obs, 1), 0), col_card(std::max(b->n_obs, 1), 1);
+  long long n_cfg = 1;
+  for (int k = 0; k < b->n_obs && n_cfg <= (1 << 16); k++) {
+    const int v = b->obs_vars[k];
+    if ((evidence_off && evidence_off[v]) || (evidence_on && evidence_on[v])) {
+      col_stride[k] = (int)n_cfg;
+      col_card[k] = hm.card[v];
+      n_cfg *= hm.card[v] + 2;  // missing, every state, out of range
+    }
+  }
+  const char* no_memo = getenv("NIPGPU_NO_LIKELIHOOD_MEMO");
+  if (n_cfg <= (1 << 16) && b->rows >= 4 * n_cfg && !(no_memo && no_memo[0] == '1')) {
+    const int nc = (int)n_cfg, no = std::max(b->n_obs, 1);
+    std::vector<int> len(nc, 2), obs((size_t)nc * 2 * no, -1);
+    std::vector<long long> off(nc);
+    for (int c = 0; c < nc; c++) {
+      off[c] = 2LL * c;
+      for (int k = 0; k < b->n_obs; k++) {
+        if (!col_stride[k]) continue;
+        const int d = (c / col_stride[k]) % (col_card[k] + 2);  // 0 missing, 1..card states, card+1 out of range
+        const int o = d == 0 ? -1 : (d <= col_card[k] ? d - 1 : col_card[k]);
+        obs[(size_t)(2 * c) * no + k] = o;
+        obs[(size_t)(2 * c + 1) * no + k] = o;
+      }
+    }
+    int *d_len = nullptr, *d_obs = nullptr, *d_cs = nullptr, *d_cc = nullptr;
+    long long* d_off = nullptr;
+    double* d_table = nullptr;
+    auto cleanup = [&]() { cudaFree(d_len); cudaFree(d_obs); cudaFree(d_cs); cudaFree(d_cc); cudaFree(d_off); cudaFree(d_table); };
+    int e = 0;
+    if ((e = dev_upload(&d_len, len, m->stream)) || (e = dev_upload(&d_obs, obs, m->stream)) ||
+        (e = dev_upload(&d_off, off, m->stream)) || (e = dev_upload(&d_cs, col_stride, m->stream)) ||
+        (e = dev_upload(&d_cc, col_card, m->stream))) { cleanup(); return e; }
+    if (cudaMalloc((void**)&d_table, (size_t)nc * 4 * sizeof(double)) != cudaSuccess) { cleanup(); return fail(NIPGPU_ENOMEM, "likelihood table"); }
+    if (!b->d_first) {
+      NIPGPU_CUDA(cudaMalloc((void**)&b->d_first, std::max<long long>(b->rows, 1)));
+      NIPGPU_CUDA(cudaMemsetAsync(b->d_first, 0, std::max<long long>(b->rows, 1), m->stream));
+      if ((e = jt_first_rows(b->d_row_off, b->n_series, b->rows, b->d_first, m->stream))) { cleanup(); return e; }
+    }
+    DBatch S;
+    S.n_series = nc; S.n_obs = b->n_obs; S.len = d_len; S.row_off = d_off; S.obs = d_obs; S.obs_proj = nullptr;
+    NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if ((e = jt_likelihood(m->prog, S, p_off, p_on, jt_fit(m->launch, nc), d_table, m->stream)) ||
+        (e = jt_like_gather(b->d_obs, b->n_obs, b->rows, b->d_first, d_cs, d_cc, d_table, b->d_like, m->sm_count, m->stream))) {
+      cleanup();
+      return e;
+    }
+    NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+    NIPGPU_CUDA(cudaMemcpyAsync(out, b->d_like, (size_t)b->rows * 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+    cleanup();
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 2; }
+    return NIPGPU_OK;
+  }
+
   NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
   if (int e = jt_likelihood(m->prog, B, p_off, p_on, l, b->d_like, m->stream)) return e;
   NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));

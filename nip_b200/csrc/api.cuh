@@ -65,5 +65,6 @@ struct nipgpu_batch {
   double *d_alpha = nullptr, *d_post = nullptr, *d_ll = nullptr, *d_like = nullptr;
   size_t post_cap = 0;
   int* d_status = nullptr;
+  unsigned char* d_first = nullptr;  // [rows] 1 on the first row of every series (memoised likelihood)
   nipgpu::ChainBatch chain;
 };

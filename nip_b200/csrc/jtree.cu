@@ -886,6 +886,50 @@ int jt_calibrate(const DProgram& p, const JtLaunch& l, double* R1, double* m1_0,
                      one.mode == JT_MODE_GRID ? one.grid : 1, st, p, team_mem(p, one), R1, m1_0);
 }
 
+// ---- memoised likelihood loop -------------------------------------------------------------
+// The slices of the likelihood loop are independent, so (m1, m2) of a record depends only on
+// its evidence configuration and on whether it opens a series.  When the configurations are
+// few, k_jt_likelihood runs once per configuration and the records only gather.
+__global__ void k_jt_first_rows(const long long* row_off, int n_series, long long rows, unsigned char* first) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_series && row_off[s] < rows) first[row_off[s]] = 1;
+}
+
+__global__ void k_jt_like_gather(const int* __restrict__ obs, int n_obs, long long rows,
+                                 const unsigned char* __restrict__ first, const int* __restrict__ col_stride,
+                                 const int* __restrict__ col_card, const double2* __restrict__ table,
+                                 double2* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    int cfg = 0;
+    for (int k = 0; k < n_obs; k++) {
+      const int st = col_stride[k];
+      if (st == 0) continue;  // column outside both evidence sets
+      const int o = obs[r * n_obs + k], card = col_card[k];
+      cfg += st * (o < 0 ? 0 : (o < card ? o + 1 : card + 1));  // missing / state / out of range
+    }
+    out[r] = table[2 * cfg + (first[r] ? 0 : 1)];
+  }
+}
+
+int jt_first_rows(const long long* row_off, int n_series, long long rows, unsigned char* first, cudaStream_t st) {
+  if (n_series <= 0) return NIPGPU_OK;
+  k_jt_first_rows<<<(n_series + 255) / 256, 256, 0, st>>>(row_off, n_series, rows, first);
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
+int jt_like_gather(const int* obs, int n_obs, long long rows, const unsigned char* first, const int* col_stride,
+                   const int* col_card, const double* table, double* out, int sm_count, cudaStream_t st) {
+  if (rows <= 0) return NIPGPU_OK;
+  const long long want = (rows + 255) / 256;
+  const int grid = (int)std::min<long long>(want, (long long)sm_count * 16);
+  k_jt_like_gather<<<grid, 256, 0, st>>>(obs, n_obs, rows, first, col_stride, col_card,
+                                         reinterpret_cast<const double2*>(table), reinterpret_cast<double2*>(out));
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
 int jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out, cudaStream_t st) {
   k_jt_mass<<<1, 256, 0, st>>>(tables, n_tab, msgs, n_msg, out);
   NIPGPU_LAUNCHED();

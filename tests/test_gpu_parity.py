@@ -348,3 +348,21 @@ def test_c3_full_size_vs_oracle(gpu_lib, oracle_lib):
     for v in range(fm.n_vars):
         slices = 1 if v >= 8 else 2                 # W^i (previous slice) only at t = 0
         assert abs(counts[off[v]:off[v + 1]].sum() - slices) < 1e-9
+
+
+@pytest.mark.parametrize("name", LIKELIHOOD_CASES)
+def test_likelihood_memo_equals_direct(gpu_lib, name, monkeypatch):
+    """with few evidence configurations the likelihood loop evaluates each configuration once
+    and the records gather; that path must give the same bits as evaluating every record"""
+    c = Case(name)
+    rng = np.random.default_rng(7)
+    cards = [int(c.fm.var_card[v]) for v in c.obs_vars]
+    series = [np.stack([rng.integers(-1, k, size=int(T)) for k in cards], axis=1).astype(np.int32)
+              for T in rng.integers(1, 40, size=60)]
+    on = np.zeros(c.fm.n_vars, dtype=np.uint8)
+    on[c.j["likelihood"]["marked"]] = 1
+    m = gpu_lib.Model(c.fm)
+    memo = m.batch(c.obs_vars, series).likelihood(1 - on, on)
+    monkeypatch.setenv("NIPGPU_NO_LIKELIHOOD_MEMO", "1")
+    direct = m.batch(c.obs_vars, series).likelihood(1 - on, on)
+    assert np.array_equal(memo, direct)
