@@ -19,7 +19,10 @@
  *
  * Beyond nip.h it exports nip_gpu_smooth_set(), a batched variant for callers
  * that hold a whole `time_series` set (util/nipinference.c:125-132 loops over
- * one): same results, one device pass.
+ * one): same results, one device pass; and transparent batching for callers
+ * that do NOT change: once a set is known (nip_gpu_register_set(), or the
+ * read_timeseries wrapper below), the first per-series call smooths the whole
+ * set in one pass and the following calls are served from that pass.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -46,6 +49,7 @@ typedef struct {
   double* tables; /* host parameters the device copy was built from */
   double* prior;
   long n_tables, n_prior;
+  long version;   /* bumped whenever the parameters on the device change */
 } backend_entry;
 
 #define MAX_BACKENDS 16
@@ -109,6 +113,7 @@ static backend_entry* backend_for(nip_model model) {
       }
       memcpy(e->tables, t, sizeof(double) * (size_t)e->n_tables);
       memcpy(e->prior, p, sizeof(double) * (size_t)e->n_prior);
+      e->version++;
     }
     free(t); free(p);
   }
@@ -116,8 +121,11 @@ static backend_entry* backend_for(nip_model model) {
 }
 
 /* Forget the device copy of a model (call before free_model()). */
+static void forget_sets_of(nip_model model);
+
 void nip_gpu_release(nip_model model) {
   int i;
+  forget_sets_of(model);
   for (i = 0; i < n_backends; i++)
     if (backends[i].model == model) {
       nipgpu_model_destroy(backends[i].gm);
@@ -235,19 +243,150 @@ int nip_gpu_smooth_set(time_series* set, int n, nip_variable vars[], int nvars, 
   return rc == NIPGPU_OK ? NIP_NO_ERROR : NIP_ERROR_GENERAL;
 }
 
+/* ---- transparent batching -----------------------------
+ * util/nipinference.c:125-129 and util/nipmap.c:139-145 call the smoother once per
+ * series of a set they read with read_timeseries().  A registered set is smoothed
+ * in ONE device pass on the first such call; the per-series results are parked
+ * here and handed over (ownership included) as the caller asks for them.  A
+ * parked pass is dropped when the query, the marked variables, the direction or
+ * the model parameters differ from what it was computed for. */
+typedef struct {
+  time_series* set;        /* the caller's array (not owned) */
+  int n;
+  uncertain_series* res;   /* parked results, NULL once handed over */
+  double* ll;
+  int valid, forward_only, nvars;
+  nip_variable* vars;
+  unsigned char* mask;
+  long version;
+  nip_model model;
+} set_entry;
+
+#define MAX_SETS 16
+static set_entry sets[MAX_SETS];
+static int n_sets = 0;
+
+static void drop_parked(set_entry* se) {
+  int i;
+  if (se->res)
+    for (i = 0; i < se->n; i++)
+      if (se->res[i]) { free_uncertainseries(se->res[i]); se->res[i] = NULL; }
+  free(se->vars); free(se->mask);
+  se->vars = NULL; se->mask = NULL;
+  se->valid = 0;
+}
+
+/* Tell the backend that set[0..n-1] belong together (the array must stay alive until
+ * nip_gpu_forget_set).  Hosts built with NIP_GPU_WRAP_SETS never call this: their
+ * read_timeseries() does. */
+void nip_gpu_register_set(time_series* set, int n) {
+  set_entry* se;
+  if (!set || n <= 1 || n_sets == MAX_SETS) return;
+  se = &sets[n_sets];
+  memset(se, 0, sizeof(*se));
+  se->res = (uncertain_series*)calloc((size_t)n, sizeof(uncertain_series));
+  se->ll = (double*)calloc((size_t)n, sizeof(double));
+  if (!se->res || !se->ll) { free(se->res); free(se->ll); return; }
+  se->set = set;
+  se->n = n;
+  n_sets++;
+}
+
+void nip_gpu_forget_set(time_series* set) {
+  int i;
+  for (i = 0; i < n_sets; i++)
+    if (sets[i].set == set) {
+      drop_parked(&sets[i]);
+      free(sets[i].res); free(sets[i].ll);
+      sets[i] = sets[--n_sets];
+      return;
+    }
+}
+
+/* a series is going away: the set it belongs to cannot be batched any more */
+static void forget_series(time_series ts) {
+  int i, k;
+  for (i = 0; i < n_sets; i++)
+    for (k = 0; k < sets[i].n; k++)
+      if (sets[i].set[k] == ts) { nip_gpu_forget_set(sets[i].set); return; }
+}
+
+static uncertain_series batched_or_single(time_series ts, nip_variable vars[], int nvars, int forward_only,
+                                          double* loglikelihood) {
+  uncertain_series r = NULL;
+  set_entry* se = NULL;
+  int i, k, idx = -1;
+  for (i = 0; i < n_sets && !se; i++)
+    for (k = 0; k < sets[i].n; k++)
+      if (sets[i].set[k] == ts) { se = &sets[i]; idx = k; break; }
+  if (se && ts && ts->model) {
+    backend_entry* e = backend_for(ts->model);
+    unsigned char* mask = e ? marked_mask(e->model) : NULL;
+    int same = e && mask && se->valid && se->model == ts->model && se->version == e->version &&
+               se->forward_only == forward_only && se->nvars == nvars &&
+               (nvars == 0 || memcmp(se->vars, vars, sizeof(nip_variable) * (size_t)nvars) == 0) &&
+               memcmp(se->mask, mask, (size_t)e->model->num_of_vars) == 0;
+    if (e && mask && !(same && se->res[idx])) {   /* nothing parked for this request: one pass over the set */
+      drop_parked(se);
+      se->vars = (nip_variable*)calloc((size_t)(nvars > 0 ? nvars : 1), sizeof(nip_variable));
+      if (se->vars && nip_gpu_smooth_set(se->set, se->n, vars, nvars, forward_only, se->res, se->ll) == NIP_NO_ERROR) {
+        memcpy(se->vars, vars, sizeof(nip_variable) * (size_t)nvars);
+        se->mask = mask;
+        mask = NULL;
+        se->nvars = nvars; se->forward_only = forward_only; se->model = ts->model; se->version = e->version;
+        se->valid = 1;
+      } else {
+        drop_parked(se);
+      }
+    }
+    free(mask);
+    if (se->valid && se->res[idx]) {
+      r = se->res[idx];
+      se->res[idx] = NULL;
+      if (loglikelihood) *loglikelihood = se->ll[idx];
+      return r;
+    }
+  }
+  if (nip_gpu_smooth_set(&ts, 1, vars, nvars, forward_only, &r, loglikelihood) != NIP_NO_ERROR) return NULL;
+  return r;
+}
+
 uncertain_series forward_backward_inference(time_series ts, nip_variable vars[], int nvars,
                                             double* loglikelihood) {
-  uncertain_series r = NULL;
-  if (nip_gpu_smooth_set(&ts, 1, vars, nvars, 0, &r, loglikelihood) != NIP_NO_ERROR) return NULL;
-  return r;
+  return batched_or_single(ts, vars, nvars, 0, loglikelihood);
 }
 
 uncertain_series forward_inference(time_series ts, nip_variable vars[], int nvars,
                                    double* loglikelihood) {
-  uncertain_series r = NULL;
-  if (nip_gpu_smooth_set(&ts, 1, vars, nvars, 1, &r, loglikelihood) != NIP_NO_ERROR) return NULL;
-  return r;
+  return batched_or_single(ts, vars, nvars, 1, loglikelihood);
 }
+
+static void forget_sets_of(nip_model model) {
+  int i = 0;
+  while (i < n_sets)
+    if (sets[i].n > 0 && sets[i].set[0] && sets[i].set[0]->model == model) nip_gpu_forget_set(sets[i].set);
+    else i++;
+}
+
+#ifdef NIP_GPU_WRAP_SETS
+/* Built inside the reference tree, where src/nip.c is compiled with
+ *   -Dread_timeseries=ref_read_timeseries -Dfree_timeseries=ref_free_timeseries
+ * (INTEGRATION.md): every set the tools read is registered, every series they free is
+ * forgotten, and the unchanged per-series loops run at batch throughput. */
+int ref_read_timeseries(nip_model model, char* datafile, time_series** results);
+void ref_free_timeseries(time_series ts);
+
+int read_timeseries(nip_model model, char* datafile, time_series** results) {
+  const int n = ref_read_timeseries(model, datafile, results);
+  if (n > 1 && results && *results) nip_gpu_register_set(*results, n);
+  return n;
+}
+
+void free_timeseries(time_series ts) {
+  forget_series(ts);
+  ref_free_timeseries(ts);
+}
+#endif
 
 /* ---- EM ---------------------------------------------------------------------
  * Control flow of em_learn (src/nip.c:2076-2250) with E- and M-steps on the

@@ -132,3 +132,45 @@ def test_make_consistent_dropin(libs, tmp_path):
     for v in range(3):
         assert_close(m_gpu.marginal(v), m_ref.marginal(v), "get_probability on the mirrored tree")
     gpu.nip_gpu_release(m_gpu.h)
+
+
+def test_transparent_batching_of_per_series_calls(libs, tmp_path):
+    """util/nipinference.c:125-129 calls forward_backward_inference once per series of a set;
+    once the set is registered the first call smooths the whole set in one device pass and the
+    others are served from it — same results as the reference, a fraction of the launches"""
+    import nip_b200.api as api
+    ref, gpu = libs
+    gpu.nip_gpu_register_set.argtypes = [vp, i32]
+    gpu.nip_gpu_forget_set.argtypes = [vp]
+    h = HmmSpec(16, 5, seed=8)
+    p = tmp_path / "b.net"
+    p.write_text(h.net_text())
+    model = ref.parse(p)
+    data = h.sample(12, 25, seed=4, missing=0.1)
+    series = [data[i, :10 + i] for i in range(12)]            # ragged
+    ts = [model.timeseries(h.obs_vars, s) for s in series]
+    arr = (vp * len(ts))(*ts)
+    q = _vars(ref, model, [1])
+    gpu.nip_gpu_register_set(arr, len(ts))
+    api.launch_count(reset=True)
+    launches = []
+    for k, t in enumerate(ts):
+        ll = f64()
+        got = _flat(ref, gpu.forward_backward_inference(t, q, 1, C.byref(ll)), 16)
+        want, ll_want = model.infer(t, [1])
+        assert_close(got, want, "batched series %d posterior" % k)
+        assert_close(ll.value, ll_want, "batched series %d loglikelihood" % k)
+        launches.append(api.launch_count())
+    assert launches[-1] == launches[0], "series 2..n must be served from the first pass"
+    # a different query invalidates the parked pass; a repeated request is computed again
+    got = _flat(ref, gpu.forward_backward_inference(ts[3], _vars(ref, model, [1, 0]), 2, None), 16 + 5)
+    assert_close(got, model.infer(ts[3], [1, 0])[0], "new query after a parked pass")
+    got = _flat(ref, gpu.forward_inference(ts[3], q, 1, None), 16)
+    assert_close(got, model.infer(ts[3], [1], forward_only=True)[0], "filtering after smoothing")
+    # changed marks change the evidence: no stale result may be served
+    model.mark(0, False)
+    got = _flat(ref, gpu.forward_backward_inference(ts[5], q, 1, None), 16)
+    assert_close(got, model.infer(ts[5], [1])[0], "marks changed")
+    model.mark(0, True)
+    gpu.nip_gpu_forget_set(arr)
+    gpu.nip_gpu_release(model.h)
