@@ -294,11 +294,11 @@ def test_launches_are_counted(gpu_lib):
 
 
 # ---- factorial DBN (config C3): cliques too large for shared memory ------------------------
-@pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None)])
+@pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None), (8, "grid")])
 def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, monkeypatch):
-    """4 ring-coupled chains (C3's topology); ns = 8 gives 8^6-entry cliques, which the engine
-    streams through HBM with the whole grid on its own (no override): smoothing, filtering and
-    the E-step against the oracle"""
+    """4 ring-coupled chains (C3's topology) with cliques too large for shared memory, in the
+    per-CTA HBM workspace and with the whole grid streaming one sequence: smoothing, filtering
+    and the E-step against the oracle"""
     from nip_b200.synth import FactorialSpec
     if mode:
         monkeypatch.setenv("NIPGPU_JT_MODE", mode)
