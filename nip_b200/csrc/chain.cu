@@ -1363,19 +1363,23 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
                 const ChainEmArgs& x, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
   const ChainInferArgs& a = x.base;
   const int SP = cm.SP, S = cm.S;
-  if (cm.dense) return NIPGPU_EUNSUPPORTED;   // EM for |I| > 64 goes through the generic engine
+  const bool dense = cm.dense;   // |I| > 64: per-slice GEMMs (dense.cu) + dense_stats
   const size_t tab = (size_t)plan.n_comb * SP;
   // k_chain_stats: two (own, beta) tile stages + posterior tile + `phases` evidence-indexed tables
   const size_t stats_fixed = sizeof(double) * (6 * 33 * (SP + 4) + 3 * 34 + 1 + tab) + 3 * 34 * sizeof(int) + 16;
   int phases = 4;
   while (phases > 1 && stats_fixed + phases * tab * sizeof(double) > 220 * 1024) phases /= 2;
-  if (stats_fixed + phases * tab * sizeof(double) > 220 * 1024) return NIPGPU_EUNSUPPORTED;
+  if (!dense && stats_fixed + phases * tab * sizeof(double) > 220 * 1024) return NIPGPU_EUNSUPPORTED;
+  if (dense && (size_t)plan.n_comb * 128 * sizeof(double) > 200 * 1024) return NIPGPU_EUNSUPPORTED;
   for (int l = 0; l < cm.n_real; l++)
     if (cm.leaves[l].free_vars.size() > 8) return NIPGPU_EUNSUPPORTED;
   if (int e = chain_prepare_evidence(cm, cb, plan, a, st)) return e;
 
   const long long rows = std::max<long long>(a.rows, 1);
-  const int parts = std::max(1, x.sm_count);   // CTAs of the statistics kernel (one per SM, split-K)
+  // CTAs of the statistics kernel (one per SM, split-K); dense: split-K of the count GEMM, the
+  // leaf pass uses row ranges so that its grid fills the machine
+  const int parts = dense ? 8 : std::max(1, x.sm_count);
+  const int partsC = dense ? std::max(1, 2 * x.sm_count / (SP / 128)) : parts;
   if (!cb.d_rt) {
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_rt, rows * SP * sizeof(double)));
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_hvec, rows * sizeof(double)));
@@ -1389,9 +1393,10 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
     }
   }
   // scratch: part_G | G | g0 | part_C | Cc | E | E0
-  const size_t n_partG = (size_t)parts * SP * SP, n_G = (size_t)SP * SP, n_partC = (size_t)parts * tab;
+  const size_t n_partG = (size_t)parts * SP * SP, n_G = (size_t)SP * SP, n_partC = (size_t)partsC * tab;
   const size_t n_E = (size_t)hm.toff[hm.nc], n_E0 = (size_t)hm.csize[cm.c0];
-  const size_t need = n_partG + n_G + SP + n_partC + tab + n_E + n_E0;
+  const size_t n_work = dense ? 2 * (size_t)rows : 0;   // dense_stats: N_k and pair weights
+  const size_t need = n_partG + n_G + SP + n_partC + tab + n_E + n_E0 + n_work;
   if (cb.em_scratch_cap < need) {
     cudaFree(cb.d_em_scratch);
     cb.d_em_scratch = nullptr;
@@ -1405,6 +1410,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   double* Cc = partC + n_partC;
   double* E = Cc + tab;
   double* E0 = E + n_E;
+  double* work = E0 + n_E0;
 
   ChainBatchDev B;
   B.n_series = a.n_series; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
@@ -1421,7 +1427,15 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   sa.n_comb = plan.n_comb; sa.phases = phases; sa.parts = parts;
   sa.smem = stats_fixed + phases * tab * sizeof(double);
   sa.partG = partG; sa.partC = partC;
-  if (a.n_series > 0) {
+  if (a.n_series > 0 && dense) {
+    DenseEm em;
+    em.bt = cb.d_rt; em.hvec = cb.d_hvec; em.r0 = cb.d_r0;
+    ChainInferArgs fa = a;
+    fa.want_ll = 1; fa.forward_only = 0; fa.d_post = nullptr;
+    if ((e = dense_infer(cm, cb, plan, fa, st, &em)) ||
+        (e = dense_stats(cm, cb, plan, em, cb.d_first, a.rows, work, parts, partG, partsC, partC, st)))
+      return e;
+  } else if (a.n_series > 0) {
     switch (cm.NT) {
       case 1: e = launch_em<1>(C, B, a, cb.d_alpha, sa, st); break;
       case 2: e = launch_em<2>(C, B, a, cb.d_alpha, sa, st); break;
@@ -1437,7 +1451,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   NIPGPU_LAUNCHED();
   k_chain_g0<<<SP, 256, 0, st>>>(cb.d_r0, a.n_series, SP, g0);
   NIPGPU_LAUNCHED();
-  k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, parts, (long long)tab, Cc);
+  k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, partsC, (long long)tab, Cc);
   NIPGPU_LAUNCHED();
   if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
   // ---- expected clique tables ----

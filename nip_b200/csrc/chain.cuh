@@ -120,8 +120,20 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
 void chain_batch_free(ChainBatch& cb);
 // dense.cu
 int dense_refresh_mats(const ChainModel& cm, const double* d_base1_c0, cudaStream_t st);
+// E-step outputs of the dense backward pass (see k_chain_stats in chain.cu for what they mean)
+struct DenseEm {
+  double* bt;     // [rows][SP] scaled beta_t
+  double* hvec;   // [rows] h_t with beta_{t-1} = h_t A r_t
+  double* r0;     // [n_series][SP] r_0 / (phi0 . r_0)
+};
 int dense_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan, const ChainInferArgs& a,
-                cudaStream_t st);
+                cudaStream_t st, const DenseEm* em = nullptr);
+// Statistics of the E-step for |I| > 64: per-row norms, posterior rows into evidence-indexed
+// tables (partC: partsC x [n_comb][SP]) and the transition counts as a split-K TN DMMA GEMM
+// (partG: partsG x [SP][SP]); `work` holds 2 x rows doubles.
+int dense_stats(const ChainModel& cm, const ChainBatch& cb, const ChainPlan& plan, const DenseEm& em,
+                const unsigned char* first, long long rows, double* work, int partsG, double* partG,
+                int partsC, double* partC, cudaStream_t st);
 
 struct ChainEmArgs {
   ChainInferArgs base;           // d_post / forward_only unused

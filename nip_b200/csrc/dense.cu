@@ -244,7 +244,8 @@ __global__ void k_dense_ll(DenseBatch B, DenseState st, double* ll_out, int* sta
 // posterior of slice t = normalise(alpha_t * beta_t); h = 1 / (R_t . colsum) for the next GEMM.
 __global__ void k_dense_bsettle(DenseBatch B, int t, int S, int SP, const double* colsum,
                                 const double* lam_comb, const double* alpha, double* beta, double* R,
-                                double* h, double* post, int post_stride, int post_off) {
+                                double* h, double* post, int post_stride, int post_off,
+                                double* em_bt, double* em_h, double* em_r0, const double* phi0) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B.n_series || B.len_sorted[b] <= t) return;
   const long long r0 = B.row_off[B.order[b]];
@@ -266,6 +267,150 @@ __global__ void k_dense_bsettle(DenseBatch B, int t, int S, int SP, const double
     for (int j = lane; j < S; j += 32) prow[j] = a[j] * be[j] * pinv;
   }
   if (lane == 0) h[b] = rcp_or_one(d);
+  if (em_bt) {  // E-step: the carried beta_t, the scale of beta_{t-1}, and r_0 / (phi0 . r_0)
+    for (int j = lane; j < SP; j += 32) em_bt[(r0 + t) * SP + j] = be[j];
+    if (lane == 0) em_h[r0 + t] = rcp_or_one(d);
+    if (t == 0) {
+      double z = 0;
+      for (int j = lane; j < SP; j += 32) z += phi0[j] * rr[j];
+      const double zinv = rcp_or_one(warp_sum_d(z));
+      for (int j = lane; j < SP; j += 32) em_r0[(long long)B.order[b] * SP + j] = rr[j] * zinv;
+    }
+  }
+}
+
+// ---- E-step statistics for large interfaces ---------------------------------------------
+// N[k] = own_k . beta_k; one warp per data row
+__global__ void k_dense_rownorm(const double* __restrict__ own, const double* __restrict__ bt, long long rows,
+                                int SP, double* __restrict__ N) {
+  const long long k = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= rows) return;
+  double s = 0;
+  for (int j = lane; j < SP; j += 32) s += own[k * SP + j] * bt[k * SP + j];
+  s = warp_sum_d(s);
+  if (lane == 0) N[k] = s;
+}
+
+// w[k] = h_k / N_{k-1}: weight of the pair (k-1, k); 0 on the rows that open a series
+__global__ void k_dense_pairw(const double* __restrict__ N, const double* __restrict__ hv,
+                              const unsigned char* __restrict__ first, long long rows, double* __restrict__ w) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= rows) return;
+  const double n = k >= 1 ? N[k - 1] : 0.0;
+  w[k] = (k >= 1 && !first[k] && n != 0) ? hv[k] / n : 0.0;
+}
+
+// posterior rows own_k beta_k / N_k added into evidence-indexed tables: CTA (x = 128-column
+// slice, y = contiguous range of rows) keeps [n_comb][128] in shared memory, thread = column,
+// rows in ascending order (deterministic); U rows are in flight per thread.
+__global__ void __launch_bounds__(128) k_dense_leaf(const double* __restrict__ own, const double* __restrict__ bt,
+                                                    const double* __restrict__ N, const int* __restrict__ cfg,
+                                                    long long rows, int SP, int n_comb, double* __restrict__ part) {
+  extern __shared__ double tabs[];
+  for (int x = threadIdx.x; x < n_comb * 128; x += 128) tabs[x] = 0.0;
+  __syncthreads();
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long k_begin = blockIdx.y * per, k_end = k_begin + per < rows ? k_begin + per : rows;
+  constexpr int U = 8;
+  for (long long k0 = k_begin; k0 < k_end; k0 += U) {
+    double o[U], b[U], n[U];
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long k = k0 + u;
+      const bool ok = k < k_end;
+      o[u] = ok ? own[k * SP + col] : 0.0;
+      b[u] = ok ? bt[k * SP + col] : 0.0;
+      n[u] = ok ? N[k] : 0.0;
+      c[u] = ok ? cfg[k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) tabs[c[u] * 128 + threadIdx.x] += n[u] != 0 ? (o[u] * b[u]) / n[u] : 0.0;
+  }
+  double* out = part + ((long long)blockIdx.y * n_comb) * SP + col;
+  for (int c = 0; c < n_comb; c++) out[(long long)c * SP] = tabs[c * 128 + threadIdx.x];
+}
+
+// bt[k][j] <- beta_k[j] lambda_{c_k}[j] w[k]: the B operand of the count GEMM
+__global__ void k_dense_bop(double* __restrict__ bt, const double* __restrict__ lam_comb,
+                            const int* __restrict__ cfg, const double* __restrict__ w, long long rows, int SP) {
+  const long long total = rows * (SP / 2);
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const long long k = x / (SP / 2);
+    const int j = 2 * (int)(x - k * (SP / 2));
+    double2 v = *reinterpret_cast<double2*>(bt + k * SP + j);
+    const double2 l = *reinterpret_cast<const double2*>(lam_comb + (long long)cfg[k] * SP + j);
+    const double wk = w[k];
+    v.x *= l.x * wk;
+    v.y *= l.y * wk;
+    *reinterpret_cast<double2*>(bt + k * SP + j) = v;
+  }
+}
+
+// G-part[z][i][j] = sum over the rows k of split z of A[k-1][i] * Bop[k][j]  (A = own rows):
+// TN GEMM, 128 x 128 tile of G per CTA, 16 rows per step, cp.async double buffering, DMMA.
+constexpr int CM = 128, CK = 16, CLD = CM + 4;
+__global__ void __launch_bounds__(256) k_dense_counts(const double* __restrict__ own, const double* __restrict__ bop,
+                                                      long long rows, int SP, double* __restrict__ part) {
+  extern __shared__ double sm[];
+  double* sA = sm;                    // [2][CK][CLD]
+  double* sB = sm + 2 * CK * CLD;     // [2][CK][CLD]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int wm = w & 3, wn = w >> 2;  // warp tile: i 32*wm.., j 64*wn..
+  const int i0 = blockIdx.y * CM, j0 = blockIdx.x * CM;
+  long long chunk = (rows + gridDim.z - 1) / gridDim.z;
+  chunk = (chunk + CK - 1) / CK * CK;
+  const long long k_begin = (long long)blockIdx.z * chunk;
+  const long long k_end = k_begin + chunk < rows ? k_begin + chunk : rows;
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  auto load_tiles = [&](int buf, long long k0) {
+#pragma unroll
+    for (int x = tid; x < CK * (CM / 2); x += 256) {
+      const int r = x / (CM / 2), c = 2 * (x % (CM / 2));
+      const long long k = k0 + r;
+      const bool okb = k < k_end, oka = okb && k >= 1;
+      cp_async16(sA + (buf * CK + r) * CLD + c, own + (oka ? (k - 1) * SP + i0 + c : 0), oka);
+      cp_async16(sB + (buf * CK + r) * CLD + c, bop + (okb ? k * SP + j0 + c : 0), okb);
+    }
+    cp_async_commit();
+  };
+  if (k_begin < k_end) load_tiles(0, k_begin);
+  int buf = 0;
+  for (long long k0 = k_begin; k0 < k_end; k0 += CK, buf ^= 1) {
+    if (k0 + CK < k_end) { load_tiles(buf ^ 1, k0 + CK); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const double* a_s = sA + buf * CK * CLD + 32 * wm;
+    const double* b_s = sB + buf * CK * CLD + 64 * wn;
+#pragma unroll
+    for (int kk = 0; kk < CK / 4; kk++) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int i = 0; i < 4; i++) af[i] = a_s[(4 * kk + q) * CLD + 8 * i + g];
+#pragma unroll
+      for (int j = 0; j < 8; j++) bf[j] = b_s[(4 * kk + q) * CLD + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+  double* out = part + (long long)blockIdx.z * SP * SP;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const long long o = (long long)(i0 + 32 * wm + 8 * i + g) * SP + j0 + 64 * wn + 8 * j + 2 * q;
+      *reinterpret_cast<double2*>(out + o) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
 }
 
 __global__ void k_dense_mats(const double* base1, const int* ent_of, int S, int SP, double* A, double* AT) {
@@ -290,7 +435,7 @@ int dense_refresh_mats(const ChainModel& cm, const double* d_base1_c0, cudaStrea
 }
 
 int dense_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan, const ChainInferArgs& a,
-                cudaStream_t st) {
+                cudaStream_t st, const DenseEm* em) {
   const int S = cm.S, SP = cm.SP, n = a.n_series;
   if (n == 0) return NIPGPU_OK;
   // ---- per-batch buffers (sorted order) ----
@@ -339,13 +484,14 @@ int dense_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan, con
   }
   k_dense_ll<<<(n + 255) / 256, 256, 0, st>>>(B, stt, a.want_ll ? a.d_ll : nullptr, a.d_status);
   NIPGPU_LAUNCHED();
-  if (a.forward_only || !a.d_post) return NIPGPU_OK;
+  if (a.forward_only || (!a.d_post && !em)) return NIPGPU_OK;
 
   double* Rcur = R0;
   double* Rnext = R1b;
   for (int t = a.t_max - 1; t >= 0; t--) {
     k_dense_bsettle<<<wgrid, 256, 0, st>>>(B, t, S, SP, cm.d_colsum, cb.d_comb, cb.d_alpha, beta, Rcur, h, a.d_post,
-                                           a.post_stride, a.post_off);
+                                           a.post_stride, a.post_off, em ? em->bt : nullptr,
+                                           em ? em->hvec : nullptr, em ? em->r0 : nullptr, cm.d_phi0);
     NIPGPU_LAUNCHED();
     const int rows = n_longer(t);
     if (t >= 1 && rows > 0) {
@@ -354,6 +500,39 @@ int dense_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan, con
       NIPGPU_LAUNCHED();
       std::swap(Rcur, Rnext);
     }
+  }
+  return NIPGPU_OK;
+}
+
+int dense_stats(const ChainModel& cm, const ChainBatch& cb, const ChainPlan& plan, const DenseEm& em,
+                const unsigned char* first, long long rows, double* work, int partsG, double* partG,
+                int partsC, double* partC, cudaStream_t st) {
+  const int SP = cm.SP;
+  double* N = work;
+  double* w = work + rows;
+  if (rows <= 0) {
+    NIPGPU_CUDA(cudaMemsetAsync(partG, 0, (size_t)partsG * SP * SP * sizeof(double), st));
+    NIPGPU_CUDA(cudaMemsetAsync(partC, 0, (size_t)partsC * plan.n_comb * SP * sizeof(double), st));
+    return NIPGPU_OK;
+  }
+  k_dense_rownorm<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cb.d_alpha, em.bt, rows, SP, N);
+  NIPGPU_LAUNCHED();
+  k_dense_pairw<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(N, em.hvec, first, rows, w);
+  NIPGPU_LAUNCHED();
+  {
+    const size_t smem = (size_t)plan.n_comb * 128 * sizeof(double);
+    if (smem > 200 * 1024) return NIPGPU_EUNSUPPORTED;
+    NIPGPU_CUDA(cudaFuncSetAttribute(k_dense_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dense_leaf<<<dim3(SP / 128, partsC), 128, smem, st>>>(cb.d_alpha, em.bt, N, cb.d_cfg, rows, SP, plan.n_comb, partC);
+    NIPGPU_LAUNCHED();
+  }
+  k_dense_bop<<<148 * 8, 256, 0, st>>>(em.bt, cb.d_comb, cb.d_cfg, w, rows, SP);
+  NIPGPU_LAUNCHED();
+  {
+    const size_t smem = (size_t)4 * CK * CLD * sizeof(double);
+    NIPGPU_CUDA(cudaFuncSetAttribute(k_dense_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dense_counts<<<dim3(SP / CM, SP / CM, partsG), 256, smem, st>>>(cb.d_alpha, em.bt, rows, SP, partG);
+    NIPGPU_LAUNCHED();
   }
   return NIPGPU_OK;
 }
