@@ -215,17 +215,45 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
   m->last_kernel_n = 0;
 
   // ---- engine 2 when the model, the evidence columns and the query allow it ----
+  // The chain engines produce the posterior of the JOINT interface state.  A query for the single
+  // interface variable is that vector itself; queries for variables of a composite interface
+  // (coupled chains) are its marginals, formed by a small projection kernel afterwards.
   ChainPlan plan;
-  const bool query_is_interface = nq == 0 || (nq == 1 && hm.nif == 1 && query[0] == hm.outg[0]);
-  if (m->engine == NIPGPU_ENGINE_CHAIN && m->chain.ok && query_is_interface &&
+  const bool direct = nq == 0 || (nq == 1 && hm.nif == 1 && query[0] == hm.outg[0]);
+  bool all_interface = nq > 0 && hm.nif > 0;
+  std::vector<int> q_stride(std::max(nq, 1), 1), q_card(std::max(nq, 1), 1), q_off(std::max(nq, 1), 0);
+  for (int i = 0, off = 0; i < nq; i++) {
+    int k = 0, stride = 1;
+    while (k < hm.nif && hm.outg[k] != query[i]) stride *= hm.card[hm.outg[k++]];
+    if (k == hm.nif) { all_interface = false; break; }
+    q_stride[i] = stride; q_card[i] = hm.card[query[i]]; q_off[i] = off;
+    off += hm.card[query[i]];
+  }
+  if (m->engine == NIPGPU_ENGINE_CHAIN && m->chain.ok && (direct || all_interface) &&
       chain_plan(hm, m->chain, b->n_obs, b->obs_vars.data(), use_evidence, plan)) {
     if (int e = chain_batch_prepare(m->chain, b->chain, b->n_series, b->len.data(), b->rows, b->t_max, m->stream)) return e;
+    const bool project = !direct && post != nullptr;
+    const int SPc = m->chain.SP;
+    if (project && !b->d_joint)
+      NIPGPU_CUDA(cudaMalloc((void**)&b->d_joint, std::max<size_t>((size_t)b->rows * SPc, 1) * sizeof(double)));
     ChainInferArgs a;
     a.n_series = b->n_series; a.n_obs = b->n_obs; a.t_max = b->t_max; a.rows = b->rows;
     a.d_obs = b->d_obs; a.d_row_off = b->d_row_off; a.want_ll = want_ll; a.forward_only = forward_only;
-    a.d_post = post; a.post_stride = Q.row; a.post_off = 0;
+    a.d_post = project ? b->d_joint : post; a.post_stride = project ? SPc : Q.row; a.post_off = 0;
     a.d_ll = b->d_ll; a.d_status = b->d_status;
     if (int e = chain_infer(hm, m->chain, b->chain, plan, a, m->stream, m->ev0, m->ev1)) return e;
+    if (project) {
+      int* d_q = nullptr;   // [3][nq]: stride, cardinality, offset of every queried variable
+      std::vector<int> packed;
+      packed.insert(packed.end(), q_stride.begin(), q_stride.begin() + nq);
+      packed.insert(packed.end(), q_card.begin(), q_card.begin() + nq);
+      packed.insert(packed.end(), q_off.begin(), q_off.begin() + nq);
+      if (int e = dev_upload(&d_q, packed, m->stream)) return e;
+      const int e2 = project_interface(b->d_joint, b->rows, SPc, hm.S, nq, d_q, Q.row, post, m->stream);
+      NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+      cudaFree(d_q);
+      if (e2) return e2;
+    }
     NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
     float ms = 0;
     if (b->n_series > 0 && cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) {
@@ -473,7 +501,7 @@ void nipgpu_batch_destroy(nipgpu_batch* b) {
   if (b->m) { cudaSetDevice(b->m->device); cudaStreamSynchronize(b->m->stream); }
   cudaFree(b->d_len); cudaFree(b->d_row_off); cudaFree(b->d_obs); cudaFree(b->d_obs_proj);
   cudaFree(b->d_qproj); cudaFree(b->d_qoff); cudaFree(b->d_alpha); cudaFree(b->d_post);
-  cudaFree(b->d_ll); cudaFree(b->d_like); cudaFree(b->d_status); cudaFree(b->d_first);
+  cudaFree(b->d_ll); cudaFree(b->d_like); cudaFree(b->d_status); cudaFree(b->d_first); cudaFree(b->d_joint);
   chain_batch_free(b->chain);
   delete b;
 }

@@ -66,5 +66,6 @@ struct nipgpu_batch {
   size_t post_cap = 0;
   int* d_status = nullptr;
   unsigned char* d_first = nullptr;  // [rows] 1 on the first row of every series (memoised likelihood)
+  double* d_joint = nullptr;         // [rows][SP] posterior of the joint interface state (composite interfaces)
   nipgpu::ChainBatch chain;
 };

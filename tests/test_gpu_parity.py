@@ -367,3 +367,22 @@ def test_likelihood_memo_equals_direct(gpu_lib, name, monkeypatch):
     monkeypatch.setenv("NIPGPU_NO_LIKELIHOOD_MEMO", "1")
     direct = m.batch(c.obs_vars, series).likelihood(1 - on, on)
     assert np.array_equal(memo, direct)
+
+
+@pytest.mark.parametrize("order", [[0], [1], [0, 1], [1, 0]])
+def test_composite_interface_queries_on_the_chain_engine(gpu_lib, order):
+    """two coupled chains: the interface is the pair (A1, B1); the chain engine smooths the joint
+    state and the queried interface variables are its marginals"""
+    c = Case("coupled2x3")
+    iface = [int(v) for v in c.fm.outgoing]                 # A1, B1
+    q = [iface[k] for k in order]
+    cols = {v: (int(sum(c.fm.var_card[u] for u in c.query[:c.query.index(v)])), int(c.fm.var_card[v])) for v in iface}
+    m = gpu_lib.Model(c.fm, engine=0)
+    b = m.batch(c.obs_vars, c.series)
+    for kind, fwd in (("smooth", False), ("filter", True)):
+        posts, lls = c.expected(kind)
+        post, ll = b.infer(q, forward_only=fwd)
+        for i, got in enumerate(b.split(post)):
+            want = np.concatenate([posts[i][:, cols[v][0]:cols[v][0] + cols[v][1]] for v in q], axis=1)
+            assert_close(got, want, "coupled2x3 %s series %d, interface query %r" % (kind, i, order))
+        assert_close(ll, lls, "coupled2x3 %s loglik" % kind)
