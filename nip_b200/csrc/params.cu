@@ -58,13 +58,17 @@ __global__ void k_finish_estep(const double* acc, int groups, long long stride, 
     for (int g = 0; g < groups; g++) s += acc[g * stride + j];
     counts[j] = s;
   }
-  if (tid == 0) {
-    double L = 0;
-    int bad = 0;
-    for (int s = 0; s < n_series; s++) { L += ll[s]; bad |= status[s]; }
-    counts[n] = L;
-    counts[n + 1] = bad ? 1.0 : 0.0;
-  }
+}
+
+// tail of the accumulator: [n] = sum of the per-series log-likelihoods, [n+1] = any BAD_LUCK flag
+// (one CTA, fixed order: the sum does not depend on how many series there are per thread block)
+__global__ void k_estep_tail(const double* ll, const int* status, int n_series, double* tail) {
+  __shared__ double red[40];
+  double L = 0, bad = 0;
+  for (int i = threadIdx.x; i < n_series; i += blockDim.x) { L += ll[i]; bad += status[i] ? 1.0 : 0.0; }
+  L = block_sum(L, red);
+  bad = block_sum(bad, red);
+  if (threadIdx.x == 0) { tail[0] = L; tail[1] = bad != 0 ? 1.0 : 0.0; }
 }
 
 int blocks_for(long long n, int threads) {
@@ -141,6 +145,8 @@ int finish_estep(const double* acc, int groups, long long stride, long long n, d
                  const double* ll, const int* status, int n_series, double* counts, cudaStream_t st) {
   k_finish_estep<<<blocks_for(n, 256), 256, 0, st>>>(acc, groups, stride, n, pseudo, ll, status,
                                                     n_series, counts);
+  NIPGPU_LAUNCHED();
+  k_estep_tail<<<1, 512, 0, st>>>(ll, status, n_series, counts + n);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }

@@ -174,3 +174,49 @@ def test_transparent_batching_of_per_series_calls(libs, tmp_path):
     model.mark(0, True)
     gpu.nip_gpu_forget_set(arr)
     gpu.nip_gpu_release(model.h)
+
+
+# ---- the reference's unchanged command-line tools, relinked -------------------------------
+TOOLS = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _run(tool, *args):
+    import subprocess
+    exe = os.path.join(TOOLS, tool)
+    if not os.path.exists(exe):
+        pytest.skip("needs the prebuilt oracle/_ref/%s (make -C oracle, where /root/reference is present)" % tool)
+    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def _observed_only(src, dst, name):
+    lines = open(src).read().split("\n")
+    k = lines[0].split(",").index(name)
+    open(dst, "w").write("\n".join([name] + [l.split(",")[k] if l.strip() else "" for l in lines[1:]]))
+
+
+def test_unchanged_cli_tools_on_the_gpu_backend(gpu_lib, tmp_path):
+    """util/nipinference.c and util/niptrain.c, compiled from the reference's sources without a
+    single edit and linked as INTEGRATION.md says, against the same tools linked with the
+    reference's own code: same files in, same files out"""
+    h = HmmSpec(12, 5, seed=3)
+    net = tmp_path / "h.net"
+    net.write_text(h.net_text())
+    _run("nipsample_cpu", net, 40, 15, tmp_path / "all.txt")
+    _observed_only(tmp_path / "all.txt", tmp_path / "m1.txt", "M1")
+    out_cpu = _run("nipinference_cpu", net, tmp_path / "m1.txt", "P1", tmp_path / "post_cpu.txt")
+    out_gpu = _run("nipinference_gpu", net, tmp_path / "m1.txt", "P1", tmp_path / "post_gpu.txt")
+    a = np.genfromtxt(tmp_path / "post_cpu.txt", delimiter=",", skip_header=1)
+    b = np.genfromtxt(tmp_path / "post_gpu.txt", delimiter=",", skip_header=1)
+    assert a.shape == b.shape and a.shape[1] == 12 and np.isfinite(a).sum() == 40 * 15 * 12
+    assert np.nanmax(np.abs(a - b)) <= 1.01e-6           # the tool prints six decimals
+    ll = lambda s: float(s.split("Average log. likelihood =")[1].split()[0])
+    assert abs(ll(out_cpu) - ll(out_gpu)) <= 1e-5 * abs(ll(out_cpu))
+    # niptrain seeds rand() from the clock, so two runs never agree digit for digit: train on the
+    # GPU backend, then let the REFERENCE tool score the model it wrote
+    log = _run("niptrain_gpu", net, tmp_path / "m1.txt", 0.0001, -5, tmp_path / "trained.net")
+    final = float(log.strip().split("average loglikelihood =")[-1].split()[0])
+    scored = ll(_run("nipinference_cpu", tmp_path / "trained.net", tmp_path / "m1.txt", "P1", tmp_path / "p2.txt"))
+    assert abs(final - scored) <= 2e-2 * abs(final)      # write_model keeps six decimals
+    assert final >= ll(out_cpu) - 0.05                   # EM did at least as well as the generating model
