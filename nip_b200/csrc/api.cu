@@ -216,44 +216,35 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
 
   // ---- engine 2 when the model, the evidence columns and the query allow it ----
   // The chain engines produce the posterior of the JOINT interface state.  A query for the single
-  // interface variable is that vector itself; queries for variables of a composite interface
-  // (coupled chains) are its marginals, formed by a small projection kernel afterwards.
+  // interface variable is that vector itself; every other variable of a chain-structured model
+  // (variables of a composite interface, previous-slice interface variables, the variables of
+  // the leaf cliques) is a linear function of it, evaluated by chain_post_vars afterwards.
   ChainPlan plan;
+  std::vector<ChainQueryVar> qv;
   const bool direct = nq == 0 || (nq == 1 && hm.nif == 1 && query[0] == hm.outg[0]);
-  bool all_interface = nq > 0 && hm.nif > 0;
-  std::vector<int> q_stride(std::max(nq, 1), 1), q_card(std::max(nq, 1), 1), q_off(std::max(nq, 1), 0);
-  for (int i = 0, off = 0; i < nq; i++) {
-    int k = 0, stride = 1;
-    while (k < hm.nif && hm.outg[k] != query[i]) stride *= hm.card[hm.outg[k++]];
-    if (k == hm.nif) { all_interface = false; break; }
-    q_stride[i] = stride; q_card[i] = hm.card[query[i]]; q_off[i] = off;
-    off += hm.card[query[i]];
-  }
-  if (m->engine == NIPGPU_ENGINE_CHAIN && m->chain.ok && (direct || all_interface) &&
-      chain_plan(hm, m->chain, b->n_obs, b->obs_vars.data(), use_evidence, plan)) {
+  const bool plan_ok = m->engine == NIPGPU_ENGINE_CHAIN && m->chain.ok &&
+                       chain_plan(hm, m->chain, b->n_obs, b->obs_vars.data(), use_evidence, plan);
+  if (plan_ok && (direct || !post || chain_query_plan(hm, m->chain, plan, nq, query, forward_only, qv))) {
     if (int e = chain_batch_prepare(m->chain, b->chain, b->n_series, b->len.data(), b->rows, b->t_max, m->stream)) return e;
     const bool project = !direct && post != nullptr;
     const int SPc = m->chain.SP;
     if (project && !b->d_joint)
       NIPGPU_CUDA(cudaMalloc((void**)&b->d_joint, std::max<size_t>((size_t)b->rows * SPc, 1) * sizeof(double)));
+    if (project && !b->d_first) {
+      NIPGPU_CUDA(cudaMalloc((void**)&b->d_first, std::max<long long>(b->rows, 1)));
+      NIPGPU_CUDA(cudaMemsetAsync(b->d_first, 0, std::max<long long>(b->rows, 1), m->stream));
+      if (int e = jt_first_rows(b->d_row_off, b->n_series, b->rows, b->d_first, m->stream)) return e;
+    }
     ChainInferArgs a;
     a.n_series = b->n_series; a.n_obs = b->n_obs; a.t_max = b->t_max; a.rows = b->rows;
     a.d_obs = b->d_obs; a.d_row_off = b->d_row_off; a.want_ll = want_ll; a.forward_only = forward_only;
     a.d_post = project ? b->d_joint : post; a.post_stride = project ? SPc : Q.row; a.post_off = 0;
     a.d_ll = b->d_ll; a.d_status = b->d_status;
     if (int e = chain_infer(hm, m->chain, b->chain, plan, a, m->stream, m->ev0, m->ev1)) return e;
-    if (project) {
-      int* d_q = nullptr;   // [3][nq]: stride, cardinality, offset of every queried variable
-      std::vector<int> packed;
-      packed.insert(packed.end(), q_stride.begin(), q_stride.begin() + nq);
-      packed.insert(packed.end(), q_card.begin(), q_card.begin() + nq);
-      packed.insert(packed.end(), q_off.begin(), q_off.begin() + nq);
-      if (int e = dev_upload(&d_q, packed, m->stream)) return e;
-      const int e2 = project_interface(b->d_joint, b->rows, SPc, hm.S, nq, d_q, Q.row, post, m->stream);
-      NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
-      cudaFree(d_q);
-      if (e2) return e2;
-    }
+    if (project)
+      if (int e = chain_post_vars(hm, m->chain, b->chain, qv, m->d_base0, m->d_base1, m->tab_off, m->d_ipool,
+                                  b->d_joint, b->d_first, b->d_row_off, b->n_series, b->rows, Q.row, post, m->stream))
+        return e;
     NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
     float ms = 0;
     if (b->n_series > 0 && cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) {

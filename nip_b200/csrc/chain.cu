@@ -1355,6 +1355,215 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   return NIPGPU_OK;
 }
 
+// ---- queries beyond the interface variables (see chain.cuh) ----------------------------
+namespace {
+
+// W[cfg][ip][y] = sum over the leaf's free-variable combinations r with digit_slot(r) == y that
+// are compatible with cfg of leaf_table[base[s(ip)] + off[r]], divided by Lambda[cfg][ip]
+__global__ void k_chain_leafpost(const double* leaf_tab, const int* base, const int* off, int R,
+                                 const int* ip_to_s, const int* meta, int slot, int card_y, int n_cfg, int S,
+                                 int SP, const double* lam, double* W) {
+  const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (x >= (long long)n_cfg * S * card_y) return;
+  const int y = (int)(x % card_y), ip = (int)((x / card_y) % S), cfg = (int)(x / ((long long)card_y * S));
+  const int nf = meta[0];
+  const int* card = meta + 1;
+  const int* stride = meta + 1 + nf;
+  const int b = base[ip_to_s[ip]];
+  double s = 0;
+  for (int r = 0; r < R; r++) {
+    int rem = r, ok = 1;
+    for (int k = 0; k < nf; k++) {
+      const int digit = rem % card[k];
+      rem /= card[k];
+      const int code = (cfg / stride[k]) % (card[k] + 1);
+      if (code != card[k] && code != digit) ok = 0;
+      if (k == slot && digit != y) ok = 0;
+    }
+    if (ok) s += leaf_tab[b + off[r]];
+  }
+  const double l = lam[(long long)cfg * SP + ip];
+  W[x] = l != 0 ? s / l : 0.0;
+}
+
+// first slices: gprev[series][i] = sum_j gamma_0(j) base0(i, j) / phi0(j)
+__global__ void k_chain_prev_first(const double* joint, const long long* row_off, int n_series, long long rows,
+                                   const double* base0, const int* ent_of, const double* phi0, int S, int SP,
+                                   double* gprev) {
+  const long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (x >= (long long)n_series * S) return;
+  const int s = (int)(x / S), i = (int)(x - (long long)s * S);
+  const long long r = row_off[s];
+  double acc = 0;
+  if (r < rows) {
+    const double* g = joint + r * SP;
+    for (int j = 0; j < S; j++) {
+      const double p = phi0[j];
+      if (p != 0) acc += g[j] * base0[ent_of[i * S + j]] / p;
+    }
+  }
+  gprev[(long long)s * SP + i] = acc;
+}
+
+struct PostVarsDev {
+  int n;
+  int kind[16], stride[16], card[16], off[16], mult[16], n_cfg[16], fixed_cfg[16];
+  long long w_off[16];
+};
+
+// one thread per (row, output column)
+__global__ void k_chain_post_vars(const double* __restrict__ joint, const int* __restrict__ cfg,
+                                  const unsigned char* __restrict__ first, long long rows, int S, int SP,
+                                  PostVarsDev Q, const double* __restrict__ Wall, int out_row,
+                                  double* __restrict__ out) {
+  const long long total = rows * out_row;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const long long r = x / out_row;
+    const int col = (int)(x - r * out_row);
+    int q = 0;
+    while (q + 1 < Q.n && Q.off[q + 1] <= col) q++;
+    const int d = col - Q.off[q];
+    double s = 0;
+    if (Q.kind[q] == 2) {
+      const int lc = Q.n_cfg[q] > 0 ? (cfg[r] / Q.mult[q]) % Q.n_cfg[q] : Q.fixed_cfg[q];
+      const double* W = Wall + Q.w_off[q] + (long long)lc * S * Q.card[q] + d;
+      const double* g = joint + r * SP;
+      for (int st = 0; st < S; st++) s += g[st] * W[(long long)st * Q.card[q]];
+    } else {
+      if (Q.kind[q] == 1 && first[r]) continue;   // written by k_chain_post_first
+      const double* g = joint + (Q.kind[q] == 1 ? r - 1 : r) * SP;
+      const int stride = Q.stride[q], card = Q.card[q];
+      for (int hi = d * stride; hi < S; hi += stride * card)
+        for (int lo = 0; lo < stride; lo++) s += g[hi + lo];
+    }
+    out[x] = s;
+  }
+}
+
+// previous-slice interface variables on the first slice of every series, from gprev
+__global__ void k_chain_post_first(const double* __restrict__ gprev, const long long* __restrict__ row_off,
+                                   int n_series, long long rows, int S, int SP, PostVarsDev Q, int out_row,
+                                   double* __restrict__ out) {
+  const long long total = (long long)n_series * out_row;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const int sidx = (int)(x / out_row), col = (int)(x - (long long)sidx * out_row);
+    const long long r = row_off[sidx];
+    if (r >= rows) continue;
+    int q = 0;
+    while (q + 1 < Q.n && Q.off[q + 1] <= col) q++;
+    if (Q.kind[q] != 1) continue;
+    const int d = col - Q.off[q], stride = Q.stride[q], card = Q.card[q];
+    const double* g = gprev + (long long)sidx * SP;
+    double s = 0, tot = 0;
+    for (int i = 0; i < S; i++) {
+      tot += g[i];
+      if ((i / stride) % card == d) s += g[i];
+    }
+    out[r * out_row + col] = tot != 0 ? s / tot : 0.0;
+  }
+}
+
+}  // namespace
+
+bool chain_query_plan(const HostModel& hm, const ChainModel& cm, const ChainPlan& plan, int nq,
+                      const int32_t* query, int forward_only, std::vector<ChainQueryVar>& out) {
+  out.clear();
+  if (nq <= 0 || nq > 16 || hm.nif <= 0) return false;
+  int off = 0;
+  long long w_off = 0;
+  for (int i = 0; i < nq; i++) {
+    const int v = query[i];
+    ChainQueryVar q{};
+    q.var = v; q.card = hm.card[v]; q.off = off; q.kind = -1;
+    int stride = 1;
+    for (int k = 0; k < hm.nif; k++) {
+      if (hm.outg[k] == v) { q.kind = 0; q.stride = stride; }
+      if (hm.prev[k] == v) { q.kind = 1; q.stride = stride; }
+      stride *= hm.card[hm.outg[k]];
+    }
+    if (q.kind == 1 && forward_only) return false;   // filtering would need a one-step smoother
+    if (q.kind < 0) {
+      const int l = cm.var_leaf[v];
+      if (l < 0 || l >= cm.n_real) return false;
+      q.kind = 2; q.leaf = l; q.slot = cm.var_slot[v];
+      const int a = (int)(std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) - plan.active_leaf.begin());
+      if (a < (int)plan.active_leaf.size()) { q.mult = plan.mult[a]; q.n_cfg = cm.leaves[l].n_cfg; }
+      else { q.mult = 1; q.n_cfg = 0; q.fixed_cfg = cm.leaves[l].miss_cfg; }
+      q.w_off = w_off;
+      w_off += (long long)cm.leaves[l].n_cfg * cm.S * q.card;
+      if (w_off > (1LL << 27)) return false;
+    }
+    off += q.card;
+    out.push_back(q);
+  }
+  return true;
+}
+
+int chain_post_vars(const HostModel& hm, const ChainModel& cm, const ChainBatch& cb,
+                    const std::vector<ChainQueryVar>& qv, const double* d_base0, const double* d_base1,
+                    const std::vector<int>& tab_off, const int* d_ipool, const double* joint,
+                    const unsigned char* first, const long long* d_row_off, int n_series, long long rows,
+                    int out_row, double* out, cudaStream_t st) {
+  if (rows <= 0 || out_row <= 0) return NIPGPU_OK;
+  const int S = cm.S, SP = cm.SP;
+  PostVarsDev Q{};
+  Q.n = (int)qv.size();
+  long long w_total = 0;
+  bool any_prev = false;
+  for (int i = 0; i < Q.n; i++) {
+    Q.kind[i] = qv[i].kind; Q.stride[i] = qv[i].stride; Q.card[i] = qv[i].card; Q.off[i] = qv[i].off;
+    Q.mult[i] = std::max(qv[i].mult, 1); Q.n_cfg[i] = qv[i].n_cfg; Q.fixed_cfg[i] = qv[i].fixed_cfg; Q.w_off[i] = qv[i].w_off;
+    if (qv[i].kind == 2) w_total = std::max(w_total, qv[i].w_off + (long long)cm.leaves[qv[i].leaf].n_cfg * S * qv[i].card);
+    if (qv[i].kind == 1) any_prev = true;
+  }
+  double* d_W = nullptr;
+  double* d_gprev = nullptr;
+  std::vector<int*> metas;
+  auto cleanup = [&]() { cudaFree(d_W); cudaFree(d_gprev); for (int* p : metas) cudaFree(p); };
+  if (w_total > 0 && cudaMalloc((void**)&d_W, (size_t)w_total * sizeof(double)) != cudaSuccess) return NIPGPU_ENOMEM;
+  for (int i = 0; i < Q.n; i++) {
+    if (qv[i].kind != 2) continue;
+    const ChainLeafHost& L = cm.leaves[qv[i].leaf];
+    const Proj& p = hm.projs[L.proj];
+    std::vector<int> meta{(int)L.free_vars.size()};
+    for (int v : L.free_vars) meta.push_back(hm.card[v]);
+    for (int sstride : L.cfg_stride) meta.push_back(sstride);
+    int* d_meta = nullptr;
+    if (cudaMalloc((void**)&d_meta, meta.size() * sizeof(int)) != cudaSuccess) { cleanup(); return NIPGPU_ENOMEM; }
+    metas.push_back(d_meta);
+    cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);   // `meta` dies at the end of this iteration
+    const long long n = (long long)L.n_cfg * S * qv[i].card;
+    k_chain_leafpost<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(
+        d_base1 + tab_off[L.clique], d_ipool + p.base_pos, d_ipool + p.off_pos, p.R,
+        cm.d_ip_to_s + (size_t)qv[i].leaf * S, d_meta, qv[i].slot, qv[i].card, L.n_cfg, S, SP,
+        cm.d_lam + L.lam_off, d_W + qv[i].w_off);
+    NIPGPU_LAUNCHED();
+  }
+  const long long total = rows * out_row;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+  k_chain_post_vars<<<grid, 256, 0, st>>>(joint, cb.d_cfg, first, rows, S, SP, Q, d_W, out_row, out);
+  NIPGPU_LAUNCHED();
+  if (any_prev && n_series > 0) {
+    if (cudaMalloc((void**)&d_gprev, (size_t)n_series * SP * sizeof(double)) != cudaSuccess) { cleanup(); return NIPGPU_ENOMEM; }
+    const long long n = (long long)n_series * S;
+    k_chain_prev_first<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(joint, d_row_off, n_series, rows,
+                                                                    d_base0 + tab_off[cm.c0], cm.d_ent_of, cm.d_phi0,
+                                                                    S, SP, d_gprev);
+    NIPGPU_LAUNCHED();
+    const long long t2 = (long long)n_series * out_row;
+    k_chain_post_first<<<(unsigned)std::min<long long>((t2 + 255) / 256, 148 * 32), 256, 0, st>>>(
+        d_gprev, d_row_off, n_series, rows, S, SP, Q, out_row, out);
+    NIPGPU_LAUNCHED();
+  }
+  const cudaError_t err = cudaStreamSynchronize(st);
+  cleanup();
+  if (err != cudaSuccess) { set_error(std::string("chain_post_vars: ") + cudaGetErrorString(err)); return NIPGPU_ECUDA; }
+  return NIPGPU_OK;
+}
+
 // E-step of a whole batch on the chain engine: forward, backward (EM flavour), transition
 // counts as a DMMA GEMM, leaf counts, then expected clique tables -> per-variable family
 // counts in the layout of em_learn's `parameters[]` (src/nip.c:2108-2128).

@@ -147,4 +147,28 @@ struct ChainEmArgs {
 int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
                 const ChainEmArgs& x, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 
+// ---- queries beyond the interface variables --------------------------------------------
+// Every variable of a chain-structured model is a function of the posterior of the joint
+// interface state gamma_t the engines produce:
+//   kind 0  interface variable            marginal of gamma_t
+//   kind 1  previous-slice interface var  marginal of gamma_{t-1}; on a series' first slice the
+//           marginal of  sum_j gamma_0(j) base0(i, j) / phi0(j)             (smoothing only)
+//   kind 2  free variable of a leaf       sum_s gamma_t(s) W[cfg_t][s][y],  W = leaf table
+//           restricted to the slice's evidence / Lambda[cfg_t][s]
+struct ChainQueryVar {
+  int kind, var;
+  int stride, card, off;         // joint-state stride and cardinality (kinds 0, 1); output offset
+  int leaf, slot;                // kind 2
+  int mult, n_cfg, fixed_cfg;    // kind 2: digit of the leaf inside the combined evidence index, or fixed
+  long long w_off;               // kind 2: offset of W inside the scratch
+};
+// false when some queried variable is none of the three kinds (caller uses engine 1)
+bool chain_query_plan(const HostModel& hm, const ChainModel& cm, const ChainPlan& plan, int nq,
+                      const int32_t* query, int forward_only, std::vector<ChainQueryVar>& out);
+int chain_post_vars(const HostModel& hm, const ChainModel& cm, const ChainBatch& cb,
+                    const std::vector<ChainQueryVar>& qv, const double* d_base0, const double* d_base1,
+                    const std::vector<int>& tab_off, const int* d_ipool, const double* joint,
+                    const unsigned char* first, const long long* d_row_off, int n_series, long long rows,
+                    int out_row, double* out, cudaStream_t st);
+
 }  // namespace nipgpu

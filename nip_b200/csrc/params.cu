@@ -114,33 +114,6 @@ int init_potential(double* table, int n, const double* cpt, const FamMap& fm, cu
   return NIPGPU_OK;
 }
 
-// one thread per (row, output column); the states with digit x are visited in ascending order
-__global__ void k_project_interface(const double* __restrict__ joint, long long rows, int SP, int S, int nq,
-                                    const int* __restrict__ q_meta, int out_row, double* __restrict__ out) {
-  const long long total = rows * out_row;
-  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total;
-       x += (long long)gridDim.x * blockDim.x) {
-    const long long r = x / out_row;
-    const int col = (int)(x - r * out_row);
-    int q = 0;
-    while (q + 1 < nq && q_meta[2 * nq + q + 1] <= col) q++;
-    const int stride = q_meta[q], card = q_meta[nq + q], digit = col - q_meta[2 * nq + q];
-    const double* row = joint + r * SP;
-    double s = 0;
-    for (int hi = digit * stride; hi < S; hi += stride * card)
-      for (int lo = 0; lo < stride; lo++) s += row[hi + lo];
-    out[x] = s;
-  }
-}
-
-int project_interface(const double* joint, long long rows, int SP, int S, int nq, const int* q_meta,
-                      int out_row, double* out, cudaStream_t st) {
-  if (rows <= 0 || out_row <= 0) return NIPGPU_OK;
-  k_project_interface<<<blocks_for(rows * out_row, 256), 256, 0, st>>>(joint, rows, SP, S, nq, q_meta, out_row, out);
-  NIPGPU_LAUNCHED();
-  return NIPGPU_OK;
-}
-
 int finish_estep(const double* acc, int groups, long long stride, long long n, double pseudo,
                  const double* ll, const int* status, int n_series, double* counts, cudaStream_t st) {
   k_finish_estep<<<blocks_for(n, 256), 256, 0, st>>>(acc, groups, stride, n, pseudo, ll, status,

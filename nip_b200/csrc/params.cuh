@@ -32,9 +32,4 @@ int init_potential(double* table, int n, const double* cpt, const FamMap& fm, cu
 int finish_estep(const double* acc, int groups, long long stride, long long n, double pseudo,
                  const double* ll, const int* status, int n_series, double* counts, cudaStream_t st);
 
-// marginals of the joint interface posterior: out[row][off_q + x] = sum of joint[row][s] over the
-// joint states s whose digit of queried variable q is x (q_meta = [3][nq]: stride, card, offset)
-int project_interface(const double* joint, long long rows, int SP, int S, int nq, const int* q_meta,
-                      int out_row, double* out, cudaStream_t st);
-
 }  // namespace nipgpu
