@@ -386,3 +386,28 @@ def test_composite_interface_queries_on_the_chain_engine(gpu_lib, order):
             want = np.concatenate([posts[i][:, cols[v][0]:cols[v][0] + cols[v][1]] for v in q], axis=1)
             assert_close(got, want, "coupled2x3 %s series %d, interface query %r" % (kind, i, order))
         assert_close(ll, lls, "coupled2x3 %s loglik" % kind)
+
+
+@pytest.mark.parametrize("S,M,B,T", [(7, 3, 60, 11), (64, 32, 40, 25), (130, 4, 21, 6)])
+def test_hmm_all_variables_vs_oracle(gpu_lib, oracle_lib, S, M, B, T):
+    """observation, state and previous-state posteriors of seeded HMMs (missing data, ragged
+    lengths) through the chain engines' query projection, against the oracle"""
+    from nip_b200.synth import HmmSpec
+    h = HmmSpec(S, M, seed=S + M)
+    fm = h.flat()
+    data = h.sample(B, T, seed=3, missing=0.25)
+    rng = np.random.default_rng(5)
+    series = [data[i, :int(rng.integers(1, T + 1))] for i in range(B)]
+    om = oracle_lib.model(fm)
+    m = gpu_lib.Model(fm, engine=0)
+    b = m.batch(h.obs_vars, series)
+    for q in ([0, 1, 2], [2, 0], [0]):          # M1, P1, P0
+        post, ll = b.infer(q)
+        for i, got in enumerate(b.split(post)):
+            want, llw = om.infer(h.obs_vars, series[i], q)
+            assert_close(got, want, "HMM-%d series %d query %r" % (S, i, q), atol=1e-300)
+            assert_close(ll[i], llw, "HMM-%d series %d loglik" % (S, i), atol=1e-12)
+    post, ll = b.infer([0, 1], forward_only=True)
+    for i, got in enumerate(b.split(post)):
+        want, llw = om.infer(h.obs_vars, series[i], [0, 1], forward_only=True)
+        assert_close(got, want, "HMM-%d series %d filtered (M1, P1)" % (S, i), atol=1e-300)
