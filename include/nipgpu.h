@@ -135,7 +135,11 @@ int nipgpu_batch_update(nipgpu_batch* b, const int32_t* data);
  *                row r of series s, variables in query order, or NULL
  *   loglik       host [n_series] total log-likelihood per series as the
  *                reference accumulates it (sum_t log m2 - log m1), or NULL
- * Host buffers; H2D of nothing (batch is resident), D2H of post/loglik. */
+ * Host buffers; H2D of nothing (batch is resident), D2H of post/loglik.
+ * Engine: chain-structured models (one clique over I_{t-1} and I_t, leaf cliques on I_t) run on
+ * the tensor path for any query — interface, previous-slice interface and leaf variables are
+ * computed from the posterior of the joint interface state; only filtering of a previous-slice
+ * variable and evidence on one use the generic join-tree engine, as every other model does. */
 int nipgpu_infer(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence,
                  int32_t n_query, const int32_t* query_vars, int forward_only,
                  double* post, double* loglik);
