@@ -75,7 +75,7 @@ int choose_launch(nipgpu_model* m) {
     l.grid = m->sm_count * std::max(1, std::min({by_smem, 2048 / l.threads, 32}));
   } else if (want == "cta") {
     l.mode = JT_MODE_CTA;
-    l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
+    l.threads = biggest <= 64 ? 32 : biggest <= 256 ? 64 : biggest <= 1024 ? 128 : 256;
     l.smem_bytes = bytes;
     const int by_smem = (int)std::max<size_t>(1, (220 * 1024) / (bytes + 1024));
     l.grid = m->sm_count * std::max(1, std::min({by_smem, 2048 / l.threads, 16}));
@@ -96,7 +96,7 @@ int choose_launch(nipgpu_model* m) {
     l.trace = m->d_trace;
   } else {
     l.mode = JT_MODE_CTA;
-    l.threads = biggest <= 64 ? 32 : biggest <= 512 ? 64 : biggest <= 4096 ? 128 : 256;
+    l.threads = biggest <= 64 ? 32 : biggest <= 256 ? 64 : biggest <= 1024 ? 128 : 256;
     size_t ctas = (size_t)m->sm_count * 2;
     const size_t budget = (size_t)32 << 30;  // keep the workspace under 32 GB
     while (ctas > 1 && ctas * bytes > budget) ctas /= 2;

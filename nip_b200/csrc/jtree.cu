@@ -389,12 +389,16 @@ __device__ void op_marg(Team& tm, const DProgram& P, const double* tab, int pj, 
   const int* __restrict__ base = P.ipool + p.base;
   const int* __restrict__ off = P.ipool + p.off;
   tm.mark(1, pj);
-  const int lanes = p.lanes, sub = tm.tid() % lanes, grp = tm.tid() / lanes;
-  const int groups = tm.size() / lanes;
   if constexpr (Team::kGrid) {
     grid_marg(tm, P, tab, pj, dst);
     return;
   } else {
+    // a destination smaller than the team (the message to a small clique, a variable's
+    // marginal) would leave most threads idle: up to a warp shares each entry then
+    int lanes = p.lanes;
+    while (lanes < 32 && p.m * lanes * 2 <= tm.size() && lanes * 2 <= p.R) lanes *= 2;
+    const int sub = tm.tid() % lanes, grp = tm.tid() / lanes;
+    const int groups = tm.size() / lanes;
     for (int j0 = 0; j0 < p.m; j0 += groups) {
       const int j = j0 + grp;
       double s = 0;
