@@ -78,6 +78,9 @@ int choose_launch(nipgpu_model* m) {
     l.threads = biggest <= 64 ? 32 : biggest <= 256 ? 64 : biggest <= 1024 ? 128 : 256;
     l.smem_bytes = bytes;
     const int by_smem = (int)std::max<size_t>(1, (220 * 1024) / (bytes + 1024));
+    // a single CTA per SM (its tables fill the shared memory): make it a big one, the index-map
+    // gathers of the potential operations need warps to hide behind
+    if (by_smem == 1 && biggest >= 2048) l.threads = 512;
     l.grid = m->sm_count * std::max(1, std::min({by_smem, 2048 / l.threads, 16}));
   } else if (want == "grid") {
     l.mode = JT_MODE_GRID;

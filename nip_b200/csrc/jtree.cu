@@ -78,6 +78,7 @@ constexpr unsigned long long kTraceCap = (JT_TRACE_WORDS - 1) / 2;  // barriers 
 
 struct WarpTeam {
   static constexpr bool kGrid = false;
+  static constexpr int kMaxThreads = 256, kMinBlocks = 2;
   static constexpr int kUnroll = 2;
   __device__ WarpTeam(double*, double*, double*, double*) {}
   __device__ int tid() const { return threadIdx.x & 31; }
@@ -95,6 +96,7 @@ struct WarpTeam {
 
 struct CtaTeam {
   static constexpr bool kGrid = false;
+  static constexpr int kMaxThreads = 512, kMinBlocks = 1;   // one big CTA when the tables fill an SM's shared memory
   static constexpr int kUnroll = 4;
   double* red;
   __device__ CtaTeam(double* r, double*, double*, double*) : red(r) {}
@@ -115,6 +117,7 @@ struct CtaTeam {
 // grid barrier per sum is enough), `scratch` holds size() doubles for two-stage marginals.
 struct GridTeam {
   static constexpr bool kGrid = true;
+  static constexpr int kMaxThreads = 256, kMinBlocks = 2;
   static constexpr int kUnroll = 8;
   double *red, *part, *scratch;
   double2* ring;  // this thread's cp.async slots: ring[u * blockDim.x], u < kRingSlots
@@ -593,7 +596,7 @@ __device__ __forceinline__ void attach_trace(Team&, const TeamMem&) {}
 __device__ __forceinline__ void attach_trace(GridTeam& tm, const TeamMem& M) { tm.trace = M.trace; }
 
 template <class Team>
-__global__ void __launch_bounds__(256, 2) k_jt_forward(DProgram P, DBatch B, DQuery Q, TeamMem M, int want_ll, int emit,
+__global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_forward(DProgram P, DBatch B, DQuery Q, TeamMem M, int want_ll, int emit,
                              double* alpha, double* post, double* ll_out, int* status_out) {
   extern __shared__ double smem[];
   __shared__ double red[40];
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(256, 2) k_jt_forward(DProgram P, DBatch B, DQu
 }
 
 template <class Team>
-__global__ void __launch_bounds__(256, 2) k_jt_backward(DProgram P, DBatch B, DQuery Q, TeamMem M, const double* alpha,
+__global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_backward(DProgram P, DBatch B, DQuery Q, TeamMem M, const double* alpha,
                               double* post, double* acc, long long acc_stride) {
   extern __shared__ double smem[];
   __shared__ double red[40];
@@ -702,7 +705,7 @@ __global__ void __launch_bounds__(256, 2) k_jt_backward(DProgram P, DBatch B, DQ
 }
 
 template <class Team>
-__global__ void __launch_bounds__(256, 2) k_jt_likelihood(DProgram P, DBatch B, const int* proj_off, const int* proj_on,
+__global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_likelihood(DProgram P, DBatch B, const int* proj_off, const int* proj_on,
                                 TeamMem M, double* out) {
   extern __shared__ double smem[];
   __shared__ double red[40];
@@ -731,7 +734,7 @@ __global__ void __launch_bounds__(256, 2) k_jt_likelihood(DProgram P, DBatch B, 
 
 // R1[i] = sum over everything but I_{t-1} of base1, m1_0 = total mass of base0
 template <class Team>
-__global__ void __launch_bounds__(256, 2) k_jt_calibrate(DProgram P, TeamMem M, double* R1, double* m1_0) {
+__global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_calibrate(DProgram P, TeamMem M, double* R1, double* m1_0) {
   extern __shared__ double smem[];
   __shared__ double red[40];
   Team tm(red, M.part, M.scratch, smem);
@@ -755,7 +758,7 @@ __global__ void __launch_bounds__(256, 2) k_jt_calibrate(DProgram P, TeamMem M, 
 }
 
 template <class Team>
-__global__ void __launch_bounds__(256, 2) k_jt_slice(DProgram P, TeamMem M, const double* start, double* out_tables,
+__global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_slice(DProgram P, TeamMem M, const double* start, double* out_tables,
                            double* out_msgs) {
   extern __shared__ double smem[];
   __shared__ double red[40];
