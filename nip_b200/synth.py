@@ -163,14 +163,28 @@ class FactorialSpec:
                 (4, 5, ["X2", "X3", "W0", "W1", "W3"]), (5, 6, ["X1", "X2", "X3", "W0", "W3"])]
     _FAMILY = [0, 1, 3, 2, 6, 5, 4, 4, 4, 4, 4, 4]
     _ADJ = [[0], [1], [2], [3], [3, 4], [1, 5, 4], [0, 2, 5]]   # sepsets of each clique, reference order
+    _IN_OUT = (4, 6)
+    # the uncoupled variant (X^i_t | X^i_{t-1} only): four 5-variable cliques, 4-variable sepsets
+    _U_CLIQUES = [["Y0", "X0"], ["Y1", "X1"], ["Y3", "X3"], ["Y2", "X2"],
+                  ["X2", "W0", "W1", "W2", "W3"], ["X0", "X2", "W0", "W1", "W3"],
+                  ["X0", "X1", "X2", "W1", "W3"], ["X0", "X1", "X2", "X3", "W3"]]
+    _U_SEPSETS = [(0, 5, ["X0"]), (1, 7, ["X1"]), (2, 7, ["X3"]), (3, 7, ["X2"]),
+                  (4, 5, ["X2", "W0", "W1", "W3"]), (5, 6, ["X0", "X2", "W1", "W3"]),
+                  (6, 7, ["X0", "X1", "X2", "W3"])]
+    _U_FAMILY = [0, 1, 3, 2, 5, 6, 4, 7, 4, 4, 4, 4]
+    _U_ADJ = [[0], [1], [2], [3], [4], [0, 5, 4], [6, 5], [1, 3, 2, 6]]
+    _U_IN_OUT = (4, 7)
 
-    def __init__(self, ns: int = 16, ny: int = 4, seed: int = 1):
+    def __init__(self, ns: int = 16, ny: int = 4, seed: int = 1, coupled: bool = True):
         K = self.K
         rng = np.random.default_rng(seed)
-        self.ns, self.ny = ns, ny
+        self.ns, self.ny, self.coupled = ns, ny, coupled
+        if not coupled:
+            self._CLIQUES, self._SEPSETS, self._FAMILY = self._U_CLIQUES, self._U_SEPSETS, self._U_FAMILY
+            self._ADJ, self._IN_OUT = self._U_ADJ, self._U_IN_OUT
         # unnormalised, as written to the .net text: the parser normalises (and so does flat())
         self.E = [rng.random((ns, ny)) + 0.05 for _ in range(K)]            # [x][y]
-        self.A = [rng.random((ns, ns, ns)) + 0.05 for _ in range(K)]        # [w_{i-1}][w_i][x]
+        self.A = [rng.random((ns, ns, ns) if coupled else (ns, ns)) + 0.05 for _ in range(K)]  # [w_{i-1}][w_i][x] / [w_i][x]
         self.pi = [rng.random(ns) + 0.1 for _ in range(K)]
         self.names = ["Y%d" % i for i in range(K)] + ["X%d" % i for i in range(K)] + ["W%d" % i for i in range(K)]
 
@@ -179,7 +193,7 @@ class FactorialSpec:
         nodes = [("Y%d" % i, ny, None) for i in range(K)] + [("X%d" % i, ns, None) for i in range(K)] + \
                 [("W%d" % i, ns, "X%d" % i) for i in range(K)]
         pots = [("Y%d" % i, ["X%d" % i], self.E[i]) for i in range(K)]
-        pots += [("X%d" % i, ["W%d" % ((i - 1) % K), "W%d" % i], self.A[i]) for i in range(K)]
+        pots += [("X%d" % i, (["W%d" % ((i - 1) % K)] if self.coupled else []) + ["W%d" % i], self.A[i]) for i in range(K)]
         pots += [("W%d" % i, [], self.pi[i][None, :]) for i in range(K)]
         return net_text_generic(nodes, pots)
 
@@ -194,13 +208,13 @@ class FactorialSpec:
                 parents += [idx["X%d" % v]]
             elif v < 2 * K:
                 i = v - K
-                parents += [idx["W%d" % i], idx["W%d" % ((i - 1) % K)]]   # last written parent first
+                parents += [idx["W%d" % i]] + ([idx["W%d" % ((i - 1) % K)]] if self.coupled else [])   # last written parent first
             poff.append(len(parents))
         # CPTs as the parser sees them (child fastest, blocks normalised left to right)
         cpt = {}
         for i in range(K):
             cpt[i] = _seq_normalise_blocks(self.E[i].reshape(-1), ny).reshape(ns, ny)
-            cpt[K + i] = _seq_normalise_blocks(self.A[i].reshape(-1), ns).reshape(ns, ns, ns)
+            cpt[K + i] = _seq_normalise_blocks(self.A[i].reshape(-1), ns).reshape(self.A[i].shape)
         cvars = [[idx[n] for n in c] for c in self._CLIQUES]
         tables, toff = [], [0]
         for c, vs in enumerate(cvars):
@@ -236,7 +250,8 @@ class FactorialSpec:
             sepset_var_off=np.cumsum([0] + [len(v) for _, _, v in self._SEPSETS]),
             sepset_vars=np.array([idx[n] for _, _, v in self._SEPSETS for n in v]),
             clique_adj_off=np.cumsum([0] + [len(a) for a in adj]), clique_adj=np.concatenate(adj),
-            outgoing=np.arange(K, 2 * K), prev_outgoing=np.arange(2 * K, 3 * K), in_clique=4, out_clique=6,
+            outgoing=np.arange(K, 2 * K), prev_outgoing=np.arange(2 * K, 3 * K),
+            in_clique=self._IN_OUT[0], out_clique=self._IN_OUT[1],
             var_names=list(self.names),
         ).normalise_dtypes()
 
@@ -253,7 +268,7 @@ class FactorialSpec:
         w = [draw(np.broadcast_to(pi[i], (n_series, self.ns))) for i in range(K)]
         out = np.empty((n_series, T, K), dtype=np.int32)
         for t in range(T):
-            x = [draw(A[i][w[(i - 1) % K], w[i]]) for i in range(K)]
+            x = [draw(A[i][w[(i - 1) % K], w[i]] if self.coupled else A[i][w[i]]) for i in range(K)]
             for i in range(K):
                 out[:, t, i] = draw(E[i][x[i]])
             w = x

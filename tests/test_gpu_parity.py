@@ -295,15 +295,16 @@ def test_launches_are_counted(gpu_lib):
 
 
 # ---- factorial DBN (config C3): cliques too large for shared memory ------------------------
+@pytest.mark.parametrize("coupled", [True, False])
 @pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None), (8, "grid")])
-def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, monkeypatch):
+def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, coupled, monkeypatch):
     """4 ring-coupled chains (C3's topology) with cliques too large for shared memory, in the
     per-CTA HBM workspace and with the whole grid streaming one sequence: smoothing, filtering
     and the E-step against the oracle"""
     from nip_b200.synth import FactorialSpec
     if mode:
         monkeypatch.setenv("NIPGPU_JT_MODE", mode)
-    sp = FactorialSpec(ns, 3, seed=4)
+    sp = FactorialSpec(ns, 3, seed=4, coupled=coupled)
     fm = sp.flat()
     data = sp.sample(3, 4, seed=5, missing=0.2)
     data[:, 0, :] = np.abs(data[:, 0, :])          # observed first slices (DESIGN.md section 7)

@@ -210,3 +210,20 @@ def test_factorial_generator_matches_reference_parse():
               "outgoing", "prev_outgoing"):
         assert np.array_equal(np.asarray(getattr(f, k)), np.asarray(getattr(g, k))), k
     assert (f.in_clique, f.out_clique) == (g.in_clique, g.out_clique)
+
+
+@pytest.mark.parametrize("coupled", [True, False])
+def test_factorial_generators_vs_reference_parser(ref_lib, coupled, tmp_path):
+    """both factorial families (ring-coupled and uncoupled chains): the FlatModel stated by
+    nip_b200.synth equals what the reference's parser + triangulation build for the same text"""
+    from nip_b200.synth import FactorialSpec
+    sp = FactorialSpec(3, 2, seed=15, coupled=coupled)
+    p = tmp_path / "f.net"
+    p.write_text(sp.net_text())
+    g, f = ref_lib.parse(p).export(), sp.flat()
+    for k in ("var_card", "var_flags", "var_parent_off", "var_parents", "var_family", "var_prior_off",
+              "var_prior", "clique_var_off", "clique_vars", "clique_tab_off", "clique_tables",
+              "sepset_cliques", "sepset_var_off", "sepset_vars", "clique_adj_off", "clique_adj",
+              "outgoing", "prev_outgoing"):
+        assert np.array_equal(np.asarray(getattr(f, k)), np.asarray(getattr(g, k))), k
+    assert (f.in_clique, f.out_clique) == (g.in_clique, g.out_clique)

@@ -100,3 +100,15 @@ print("C3 smoothing 8 x 8 (grid team, 403 MB of tables): %.1f ms, %.1f slice-ste
       % (ms, n / ms * 1e3, 6.2e9 * n / ms * 1e3 / 1e12, 6.2e9 * n / ms * 1e3 / HBM))
 ms = best(lambda: (b.estep(), m.last_kernel_ms()[0])[1], 2)
 print("C3 E-step 8 x 8: %.1f ms, %.1f slice-steps/s" % (ms, n / ms * 1e3))
+
+# ---- C3, uncoupled variant: four 16^5-entry cliques ----
+b.close(); m.close()
+sp = FactorialSpec(16, 4, seed=1, coupled=False)
+data = sp.sample(64, 8, seed=2)
+m = api.Model(sp.flat(), engine=1)
+b = m.batch(sp.obs_vars, data)
+ms = best(lambda: (b.infer([4, 5]), m.last_kernel_ms()[0])[1], 2)
+n = 64 * 8
+print("C3 uncoupled variant (four 16^5-entry cliques), smoothing 64 x 8: %.1f ms, %.1f slice-steps/s" % (ms, n / ms * 1e3))
+ms = best(lambda: (b.estep(), m.last_kernel_ms()[0])[1], 2)
+print("C3 uncoupled variant, E-step 64 x 8: %.1f ms, %.1f slice-steps/s" % (ms, n / ms * 1e3))
