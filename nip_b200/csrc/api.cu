@@ -49,8 +49,8 @@ int choose_launch(nipgpu_model* m) {
   if (want.empty()) {
     if (biggest <= 64 && bytes <= 8 * 1024) want = "warp";
     else if (bytes <= 200 * 1024) want = "cta";
-    // measured on 8^6-entry cliques: the grid team (2.9 k slice-steps/s at any batch size) beats one
-    // CTA per sequence on a per-CTA HBM workspace (2.7 k with 600 sequences in flight, 0.8 k with 64)
+    // measured (600 sequences, tools/dev_midsize.py): 7^6-entry cliques 2.5e4 slice-steps/s on per-CTA
+    // HBM workspaces vs 1.9e4 with the grid team's concurrent groups; 8^6: 1.2e4 vs 1.6e4
     else if (biggest >= (1 << 18)) want = "grid";
     else want = "hbm";
   }
@@ -85,12 +85,28 @@ int choose_launch(nipgpu_model* m) {
   } else if (want == "grid") {
     l.mode = JT_MODE_GRID;
     l.threads = 256;
-    l.grid = jt_grid_ctas(l.threads, m->sm_count, &l.smem_bytes);
+    const int all_ctas = jt_grid_ctas(l.threads, m->sm_count, &l.smem_bytes);
+    // tables of a few MB leave a slice barrier-latency bound: several sequences side by side,
+    // each streamed by its own cooperative kernel on a share of the SMs (one when the tables
+    // are hundreds of MB: C3)
+    int groups = 1;
+    while (groups < 8 && 2 * groups * bytes <= ((size_t)256 << 20) && all_ctas / (2 * groups) >= 32) groups *= 2;
+    const char* eg = getenv("NIPGPU_JT_GROUPS");
+    if (eg && atoi(eg) >= 1 && atoi(eg) <= 8) groups = atoi(eg);
+    l.groups = groups;
+    l.grid = all_ctas / groups;
     const size_t part = 2 * (size_t)l.grid + 8, scratch = (size_t)l.grid * l.threads;
-    if (int e = need_gwork(work + part + scratch)) return e;
+    l.group_stride = (work + part + scratch + 1) & ~(size_t)1;   // keeps 16-byte alignment
+    if (int e = need_gwork(l.group_stride * groups)) return e;
     l.gwork = m->d_gwork;
     l.part = m->d_gwork + work;
     l.scratch = l.part + part;
+    for (int g = 0; g < groups; g++) {
+      if (g + 1 < groups && !m->aux_stream[g]) NIPGPU_CUDA(cudaStreamCreateWithFlags(&m->aux_stream[g], cudaStreamNonBlocking));
+      if (!m->aux_event[g]) NIPGPU_CUDA(cudaEventCreateWithFlags(&m->aux_event[g], cudaEventDisableTiming));
+    }
+    for (int g = 0; g < 8; g++) l.aux_stream[g] = m->aux_stream[g];
+    for (int g = 0; g < 9; g++) l.aux_event[g] = m->aux_event[g];
     const char* tr = getenv("NIPGPU_JT_TRACE");
     if (tr && tr[0] == '1' && !m->d_trace) {
       NIPGPU_CUDA(cudaMalloc((void**)&m->d_trace, JT_TRACE_WORDS * sizeof(unsigned long long)));
@@ -107,7 +123,7 @@ int choose_launch(nipgpu_model* m) {
     l.gwork = m->d_gwork;
     l.grid = (int)ctas;
   }
-  l.slots = l.mode == JT_MODE_WARP ? l.grid * (l.threads / 32) : l.mode == JT_MODE_GRID ? 1 : l.grid;
+  l.slots = l.mode == JT_MODE_WARP ? l.grid * (l.threads / 32) : l.mode == JT_MODE_GRID ? l.groups : l.grid;
   return NIPGPU_OK;
 }
 
@@ -400,6 +416,8 @@ void nipgpu_model_destroy(nipgpu_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  for (int g = 0; g < 8; g++) if (m->aux_stream[g]) cudaStreamDestroy(m->aux_stream[g]);
+  for (int g = 0; g < 9; g++) if (m->aux_event[g]) cudaEventDestroy(m->aux_event[g]);
   cudaFree(m->d_trace); cudaFree(m->d_ipool); cudaFree(m->d_projs); cudaFree(m->d_collect); cudaFree(m->d_distribute);
   cudaFree(m->d_path); cudaFree(m->d_proj_var); cudaFree(m->d_proj_fam); cudaFree(m->d_var_flags);
   cudaFree(m->d_coff); cudaFree(m->d_prior_off); cudaFree(m->d_prior_vars); cudaFree(m->d_prior_flags);

@@ -37,6 +37,8 @@ struct nipgpu_model {
   double* d_gwork = nullptr;   // HBM workspace when tables do not fit shared memory
   size_t gwork_doubles = 0;
   unsigned long long* d_trace = nullptr;  // NIPGPU_JT_TRACE=1 (grid team diagnostics)
+  cudaStream_t aux_stream[8] = {};        // grid team: concurrent groups
+  cudaEvent_t aux_event[9] = {};
 
   nipgpu::DProgram prog{};
   nipgpu::JtLaunch launch{};

@@ -158,9 +158,10 @@ struct GridTeam {
     __syncthreads();
     return red[33];
   }
-  __device__ int slot() const { return 0; }
-  __device__ int first() const { return 0; }
-  __device__ int step() const { return 1; }
+  int seq_first = 0, seq_step = 1;   // this kernel's share of the sequences (concurrent groups)
+  __device__ int slot() const { return seq_first; }
+  __device__ int first() const { return seq_first; }
+  __device__ int step() const { return seq_step; }
   __device__ double* work(double* gwork, double*, size_t) const { return gwork; }
 };
 
@@ -589,11 +590,16 @@ struct TeamMem {
   double* part;
   double* scratch;
   unsigned long long* trace;
+  int seq_first, seq_step;
 };
 
 template <class Team>
 __device__ __forceinline__ void attach_trace(Team&, const TeamMem&) {}
-__device__ __forceinline__ void attach_trace(GridTeam& tm, const TeamMem& M) { tm.trace = M.trace; }
+__device__ __forceinline__ void attach_trace(GridTeam& tm, const TeamMem& M) {
+  tm.trace = M.trace;
+  tm.seq_first = M.seq_first;
+  tm.seq_step = M.seq_step;
+}
 
 template <class Team>
 __global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_forward(DProgram P, DBatch B, DQuery Q, TeamMem M, int want_ll, int emit,
@@ -798,7 +804,36 @@ TeamMem team_mem(const DProgram& p, const JtLaunch& l) {
   M.part = l.part;
   M.scratch = l.scratch;
   M.trace = l.trace;
+  M.seq_first = 0;
+  M.seq_step = 1;
   return M;
+}
+
+// memory of group g of a grid-mode launch
+TeamMem group_mem(const DProgram& p, const JtLaunch& l, int g, int groups) {
+  TeamMem M = team_mem(p, l);
+  M.gwork = l.gwork + (size_t)g * l.group_stride;
+  M.part = l.part + (size_t)g * l.group_stride;
+  M.scratch = l.scratch + (size_t)g * l.group_stride;
+  if (g > 0) M.trace = nullptr;
+  M.seq_first = g;
+  M.seq_step = groups;
+  return M;
+}
+
+// grid mode: the groups' cooperative kernels side by side (group 0 on the caller's stream)
+template <class Launch>
+int launch_groups(const JtLaunch& l, int groups, cudaStream_t st, Launch launch) {
+  if (groups <= 1) return launch(0, 1, st);
+  NIPGPU_CUDA(cudaEventRecord(l.aux_event[0], st));
+  for (int g = 1; g < groups; g++) {
+    NIPGPU_CUDA(cudaStreamWaitEvent(l.aux_stream[g - 1], l.aux_event[0], 0));
+    if (int e = launch(g, groups, l.aux_stream[g - 1])) return e;
+    NIPGPU_CUDA(cudaEventRecord(l.aux_event[g], l.aux_stream[g - 1]));
+  }
+  if (int e = launch(0, groups, st)) return e;
+  for (int g = 1; g < groups; g++) NIPGPU_CUDA(cudaStreamWaitEvent(st, l.aux_event[g], 0));
+  return NIPGPU_OK;
 }
 
 // One launcher for the three instantiations of a kernel template.
@@ -850,7 +885,8 @@ JtLaunch jt_fit(const JtLaunch& l, int n_series) {
     r.grid = std::max(1, std::min(l.grid, (n + wpc - 1) / wpc));
     r.slots = r.grid * wpc;
   } else if (l.mode == JT_MODE_GRID) {
-    r.slots = 1;
+    r.groups = std::max(1, std::min(l.groups, n));
+    r.slots = r.groups;
   } else {
     r.grid = std::max(1, std::min(l.grid, n));
     r.slots = r.grid;
@@ -860,18 +896,33 @@ JtLaunch jt_fit(const JtLaunch& l, int n_series) {
 
 int jt_forward(const DProgram& p, const DBatch& b, const DQuery& q, const JtLaunch& l, int want_ll,
                int emit, double* alpha, double* post, double* ll, int* status, cudaStream_t st) {
+  if (l.mode == JT_MODE_GRID)
+    return launch_groups(l, l.groups, st, [&](int g, int groups, cudaStream_t s) {
+      return launch_team(k_jt_forward<WarpTeam>, k_jt_forward<CtaTeam>, k_jt_forward<GridTeam>, l, l.grid, s,
+                         p, b, q, group_mem(p, l, g, groups), want_ll, emit, alpha, post, ll, status);
+    });
   return launch_team(k_jt_forward<WarpTeam>, k_jt_forward<CtaTeam>, k_jt_forward<GridTeam>, l, l.grid, st,
                      p, b, q, team_mem(p, l), want_ll, emit, alpha, post, ll, status);
 }
 
 int jt_backward(const DProgram& p, const DBatch& b, const DQuery& q, const JtLaunch& l,
                 const double* alpha, double* post, double* acc, long long acc_stride, cudaStream_t st) {
+  if (l.mode == JT_MODE_GRID)
+    return launch_groups(l, l.groups, st, [&](int g, int groups, cudaStream_t s) {
+      return launch_team(k_jt_backward<WarpTeam>, k_jt_backward<CtaTeam>, k_jt_backward<GridTeam>, l, l.grid,
+                         s, p, b, q, group_mem(p, l, g, groups), alpha, post, acc, acc_stride);
+    });
   return launch_team(k_jt_backward<WarpTeam>, k_jt_backward<CtaTeam>, k_jt_backward<GridTeam>, l, l.grid,
                      st, p, b, q, team_mem(p, l), alpha, post, acc, acc_stride);
 }
 
 int jt_likelihood(const DProgram& p, const DBatch& b, const int* proj_off, const int* proj_on,
                   const JtLaunch& l, double* out, cudaStream_t st) {
+  if (l.mode == JT_MODE_GRID)
+    return launch_groups(l, l.groups, st, [&](int g, int groups, cudaStream_t s) {
+      return launch_team(k_jt_likelihood<WarpTeam>, k_jt_likelihood<CtaTeam>, k_jt_likelihood<GridTeam>, l,
+                         l.grid, s, p, b, proj_off, proj_on, group_mem(p, l, g, groups), out);
+    });
   return launch_team(k_jt_likelihood<WarpTeam>, k_jt_likelihood<CtaTeam>, k_jt_likelihood<GridTeam>, l,
                      l.grid, st, p, b, proj_off, proj_on, team_mem(p, l), out);
 }

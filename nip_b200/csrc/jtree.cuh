@@ -77,6 +77,12 @@ struct JtLaunch {
   double* part;          // grid mode: 2 x grid doubles for grid-wide sums
   double* scratch;       // grid mode: grid x threads doubles for two-stage marginals
   unsigned long long* trace;  // grid mode, NIPGPU_JT_TRACE=1: per-barrier (tag, ns) records
+  // grid mode with tables of a few MB: `groups` cooperative kernels run side by side, each with
+  // grid CTAs, its own work area (group_stride doubles apart) and every groups-th sequence
+  int groups;
+  size_t group_stride;
+  cudaStream_t aux_stream[8];
+  cudaEvent_t aux_event[9];   // [0] fork, [g] join of group g
 };
 
 constexpr int JT_TRACE_WORDS = 1 + 2 * 8192;
