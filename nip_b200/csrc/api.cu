@@ -38,7 +38,7 @@ int choose_launch(nipgpu_model* m) {
   for (int c = 0; c < hm.nc; c++) biggest = std::max(biggest, hm.csize[c]);
   JtLaunch& l = m->launch;
   l = JtLaunch{};
-  const size_t work = jt_work_doubles(m->prog);
+  size_t work = jt_work_doubles(m->prog);
   const size_t bytes = work * sizeof(double);
   // NIPGPU_JT_MODE = warp | cta | hbm | grid overrides the choice below; the tests use it to run
   // every mode on small models (NIPGPU_FORCE_HBM_WORKSPACE=1 is the older spelling of "hbm")
@@ -85,6 +85,7 @@ int choose_launch(nipgpu_model* m) {
   } else if (want == "grid") {
     l.mode = JT_MODE_GRID;
     l.threads = 256;
+    work = jt_work_doubles(m->prog, true);
     const int all_ctas = jt_grid_ctas(l.threads, m->sm_count, &l.smem_bytes);
     // tables of a few MB leave a slice barrier-latency bound: several sequences side by side,
     // each streamed by its own cooperative kernel on a share of the SMs (one when the tables

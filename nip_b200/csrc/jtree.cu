@@ -800,7 +800,7 @@ __global__ void k_jt_marginal(DProgram P, const double* tables, int pj, double* 
 TeamMem team_mem(const DProgram& p, const JtLaunch& l) {
   TeamMem M;
   M.gwork = l.gwork;
-  M.wstride = jt_work_doubles(p);
+  M.wstride = jt_work_doubles(p, l.mode == JT_MODE_GRID);
   M.part = l.part;
   M.scratch = l.scratch;
   M.trace = l.trace;

@@ -60,8 +60,9 @@ struct DQuery {
 };
 
 // work-area size in doubles for one CTA
-inline size_t jt_work_doubles(const DProgram& p) {
-  const size_t quo = p.msg_max > p.S ? p.msg_max : p.S;  // quotient vector of the grid team
+inline size_t jt_work_doubles(const DProgram& p, bool grid_team = false) {
+  // the grid team also keeps a quotient vector (division-free distribute)
+  const size_t quo = grid_team ? (size_t)(p.msg_max > p.S ? p.msg_max : p.S) : 0;
   return (size_t)p.tab_total + p.msg_total + p.msg_max + 3 * (size_t)p.S + p.scratch + quo + 40;
 }
 
