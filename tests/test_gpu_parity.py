@@ -172,18 +172,30 @@ def test_generic_engine_team_modes(gpu_lib, name, mode, monkeypatch):
         assert_close(m2.slice_mass(), float.fromhex(step["mass"]), "mass (%s)" % mode)
 
 
-def test_empty_and_single_slice(gpu_lib):
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("mode", [None, "grid", "hbm"])
+def test_empty_and_single_slice(gpu_lib, engine, mode, monkeypatch):
+    """T = 0 and T = 1 series, an empty batch, and their E-steps (every engine and team)"""
+    if mode:
+        if engine != 1:
+            pytest.skip("team modes belong to the generic engine")
+        monkeypatch.setenv("NIPGPU_JT_MODE", mode)
     c = Case("hmm5")
-    m = gpu_lib.Model(c.fm)
+    m = gpu_lib.Model(c.fm, engine=engine)
     b = m.batch(c.obs_vars, [np.zeros((0, 1), dtype=np.int32), c.series[6]])   # T = 0 and T = 1
     post, ll = b.infer(c.query)
     assert ll[0] == 0.0
     posts, lls = c.expected("smooth")
     assert_close(post, posts[6], "single-slice series")
     assert_close(ll[1], lls[6], "single-slice loglik")
+    counts, L, st = b.estep(add_pseudocount=False)
+    assert st == 0
+    assert_close(L, lls[6], "single-slice EM loglik")
     b0 = m.batch(c.obs_vars, [])
     post, ll = b0.infer(c.query)
     assert post.shape[0] == 0 and ll.shape[0] == 0
+    counts, L, st = b0.estep(add_pseudocount=True)
+    assert st == 0 and L == 0.0 and np.all(counts == 1.0)      # only the pseudo-count
 
 
 @pytest.mark.parametrize("engine", ENGINES)
