@@ -87,11 +87,12 @@ int choose_launch(nipgpu_model* m) {
     l.threads = 256;
     work = jt_work_doubles(m->prog, true);
     const int all_ctas = jt_grid_ctas(l.threads, m->sm_count, &l.smem_bytes);
-    // tables of a few MB leave a slice barrier-latency bound: several sequences side by side,
-    // each streamed by its own cooperative kernel on a share of the SMs (one when the tables
-    // are hundreds of MB: C3)
+    // Several sequences side by side, each streamed by its own cooperative kernel on a share of
+    // the SMs: with tables of a few MB a slice is barrier-latency bound (four 16^5-entry cliques:
+    // 2.0e3 -> 4.6e3 slice-steps/s), and even the 403 MB of C3 gain (433 -> 589) because one
+    // group's barriers and short operations hide under the others' streaming passes
     int groups = 1;
-    while (groups < 8 && 2 * groups * bytes <= ((size_t)256 << 20) && all_ctas / (2 * groups) >= 32) groups *= 2;
+    while (groups < 8 && 2 * groups * bytes <= ((size_t)16 << 30) && all_ctas / (2 * groups) >= 32) groups *= 2;
     const char* eg = getenv("NIPGPU_JT_GROUPS");
     if (eg && atoi(eg) >= 1 && atoi(eg) <= 8) groups = atoi(eg);
     l.groups = groups;
