@@ -1128,7 +1128,22 @@ int chain_upload_structure(const HostModel& hm, ChainModel& cm, cudaStream_t st)
                                 cudaMemcpyHostToDevice, st));
     NIPGPU_CUDA(cudaStreamSynchronize(st));
   }
-  (void)hm;
+  {  // per-leaf metadata of the refresh kernels, uploaded once
+    std::vector<int> meta;
+    std::vector<long long> miss_rows;
+    cm.leaf_meta_off.clear();
+    for (int l = 0; l < cm.n_real; l++) {
+      const ChainLeafHost& L = cm.leaves[l];
+      cm.leaf_meta_off.push_back((int)meta.size());
+      meta.push_back((int)L.free_vars.size());
+      for (int v : L.free_vars) meta.push_back(hm.card[v]);
+      for (int sstride : L.cfg_stride) meta.push_back(sstride);
+      miss_rows.push_back(L.lam_off + (long long)L.miss_cfg * cm.SP);
+    }
+    if (int e = upload(&cm.d_leaf_meta, meta, st)) return e;
+    if (int e = upload(&cm.d_miss_rows, miss_rows, st)) return e;
+    NIPGPU_CUDA(cudaStreamSynchronize(st));
+  }
   return NIPGPU_OK;
 }
 
@@ -1159,40 +1174,26 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_colsum, 0, cm.SP * sizeof(double), st));
   k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base1 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_colsum);
   NIPGPU_LAUNCHED();
-  std::vector<long long> miss_rows;
   for (int l = 0; l < cm.n_real; l++) {
     const ChainLeafHost& L = cm.leaves[l];
     const Proj& p = hm.projs[L.proj];
-    std::vector<int> meta{(int)L.free_vars.size()};
-    for (int v : L.free_vars) meta.push_back(hm.card[v]);
-    for (int s : L.cfg_stride) meta.push_back(s);
-    meta.insert(meta.end(), L.ip_to_s.begin(), L.ip_to_s.end());
-    int* d_meta = nullptr;
-    NIPGPU_CUDA(cudaMalloc((void**)&d_meta, meta.size() * sizeof(int)));
-    NIPGPU_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     const int n = L.n_cfg * S;
     k_chain_lambda<<<(n + 127) / 128, 128, 0, st>>>(
         d_base1 + tab_off[L.clique], d_ipool + p.base_pos, d_ipool + p.off_pos, p.R,
-        d_meta + 1 + 2 * (int)L.free_vars.size(), d_meta, L.n_cfg, S, cm.SP, cm.d_lam + L.lam_off);
+        cm.d_ip_to_s + (size_t)l * S, cm.d_leaf_meta + cm.leaf_meta_off[l], L.n_cfg, S, cm.SP,
+        cm.d_lam + L.lam_off);
     NIPGPU_LAUNCHED();
-    NIPGPU_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_meta);
-    miss_rows.push_back(L.lam_off + (long long)L.miss_cfg * cm.SP);
   }
-  long long* d_rows = nullptr;
-  if (int e = upload(&d_rows, miss_rows, st)) return e;
-  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, d_rows, (int)miss_rows.size(), S,
-                                                        cm.SP, cm.d_lam0);
+  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, cm.d_miss_rows, cm.n_real, S, cm.SP, cm.d_lam0);
   NIPGPU_LAUNCHED();
-  NIPGPU_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_rows);
+  NIPGPU_CUDA(cudaStreamSynchronize(st));   // m1_0 has landed on the host
   cm.param_version++;
   return NIPGPU_OK;
 }
 
 void chain_free(ChainModel& cm) {
   cudaFree(cm.d_ent_of); cudaFree(cm.d_Bf1); cudaFree(cm.d_Bb1); cudaFree(cm.d_Bb0);
-  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_R1); cudaFree(cm.d_colsum); cudaFree(cm.d_ent_im); cudaFree(cm.d_ent_ip); cudaFree(cm.d_ip_to_s);
+  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_miss_rows); cudaFree(cm.d_R1); cudaFree(cm.d_colsum); cudaFree(cm.d_ent_im); cudaFree(cm.d_ent_ip); cudaFree(cm.d_ip_to_s);
   cm = ChainModel();
 }
 
@@ -1267,18 +1268,23 @@ static int chain_prepare_evidence(const ChainModel& cm, ChainBatch& cb, const Ch
   key.insert(key.end(), plan.active_leaf.begin(), plan.active_leaf.end());
   key.push_back(-1);
   key.insert(key.end(), plan.col_leaf_slot.begin(), plan.col_leaf_slot.end());
-  key.push_back((int)cm.param_version);
-  if (cb.plan_key == key && cb.d_comb) return NIPGPU_OK;
+  const bool same_plan = cb.plan_key == key && cb.d_comb && cb.d_rows;
+  if (same_plan && cb.plan_version == cm.param_version) return NIPGPU_OK;
   const int na = plan.n_active;
-  std::vector<long long> inactive_rows;
-  for (int l = 0; l < cm.n_real; l++)
-    if (std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) == plan.active_leaf.end())
-      inactive_rows.push_back(cm.leaves[l].lam_off + (long long)cm.leaves[l].miss_cfg * cm.SP);
-  cudaFree(cb.d_rows);
-  cb.d_rows = nullptr;
-  if (int e = upload(&cb.d_rows, inactive_rows, st)) return e;
-  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, cb.d_rows, (int)inactive_rows.size(),
-                                                        cm.S, cm.SP, cb.d_lam_static);
+  if (!same_plan) {
+    std::vector<long long> inactive_rows;
+    for (int l = 0; l < cm.n_real; l++)
+      if (std::find(plan.active_leaf.begin(), plan.active_leaf.end(), l) == plan.active_leaf.end())
+        inactive_rows.push_back(cm.leaves[l].lam_off + (long long)cm.leaves[l].miss_cfg * cm.SP);
+    cudaFree(cb.d_rows);
+    cb.d_rows = nullptr;
+    if (int e = upload(&cb.d_rows, inactive_rows, st)) return e;
+    NIPGPU_CUDA(cudaStreamSynchronize(st));   // `inactive_rows` dies here
+    cb.n_inactive = (int)inactive_rows.size();
+  }
+  // the evidence tables follow the parameters (every M-step); the per-row configuration does not
+  k_chain_lam_prod<<<(cm.SP + 127) / 128, 128, 0, st>>>(cm.d_lam, cb.d_rows, cb.n_inactive, cm.S, cm.SP,
+                                                        cb.d_lam_static);
   NIPGPU_LAUNCHED();
   ChainComb K;
   for (int i = 0; i < 8; i++) {
@@ -1296,22 +1302,25 @@ static int chain_prepare_evidence(const ChainModel& cm, ChainBatch& cb, const Ch
   k_chain_combine<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(cm.d_lam, cb.d_lam_static, na, K,
                                                                  plan.n_comb, cm.S, cm.SP, cb.d_comb);
   NIPGPU_LAUNCHED();
-  std::vector<int> cols;  // slot | stride | card | mult
-  cols.insert(cols.end(), plan.col_leaf_slot.begin(), plan.col_leaf_slot.end());
-  cols.insert(cols.end(), plan.col_stride.begin(), plan.col_stride.end());
-  cols.insert(cols.end(), plan.col_card.begin(), plan.col_card.end());
-  cols.insert(cols.end(), plan.col_mult.begin(), plan.col_mult.end());
-  cudaFree(cb.d_cols);
-  cb.d_cols = nullptr;
-  if (int e = upload(&cb.d_cols, cols, st)) return e;
-  if (a.rows > 0) {
-    k_chain_cfg<<<(unsigned)((a.rows + 255) / 256), 256, 0, st>>>(
-        a.d_obs, a.rows, a.n_obs, cb.d_cols, cb.d_cols + a.n_obs, cb.d_cols + 2 * a.n_obs,
-        cb.d_cols + 3 * a.n_obs, plan.c_miss, cb.d_cfg);
-    NIPGPU_LAUNCHED();
+  if (!same_plan) {
+    std::vector<int> cols;  // slot | stride | card | mult
+    cols.insert(cols.end(), plan.col_leaf_slot.begin(), plan.col_leaf_slot.end());
+    cols.insert(cols.end(), plan.col_stride.begin(), plan.col_stride.end());
+    cols.insert(cols.end(), plan.col_card.begin(), plan.col_card.end());
+    cols.insert(cols.end(), plan.col_mult.begin(), plan.col_mult.end());
+    cudaFree(cb.d_cols);
+    cb.d_cols = nullptr;
+    if (int e = upload(&cb.d_cols, cols, st)) return e;
+    if (a.rows > 0) {
+      k_chain_cfg<<<(unsigned)((a.rows + 255) / 256), 256, 0, st>>>(
+          a.d_obs, a.rows, a.n_obs, cb.d_cols, cb.d_cols + a.n_obs, cb.d_cols + 2 * a.n_obs,
+          cb.d_cols + 3 * a.n_obs, plan.c_miss, cb.d_cfg);
+      NIPGPU_LAUNCHED();
+    }
+    NIPGPU_CUDA(cudaStreamSynchronize(st));  // host vectors above die here
+    cb.plan_key = key;
   }
-  NIPGPU_CUDA(cudaStreamSynchronize(st));  // host vectors above die here
-  cb.plan_key = key;
+  cb.plan_version = cm.param_version;
   return NIPGPU_OK;
 }
 

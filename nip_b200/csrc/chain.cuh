@@ -51,7 +51,9 @@ struct ChainModel {
   double m1_0 = 1.0;           // mass of the evidence-free first slice
   double* d_lam = nullptr;     // all Lambda tables
   long long lam_total = 0;
-  int* d_leaf_meta = nullptr;  // flattened per-leaf metadata for the refresh kernel
+  int* d_leaf_meta = nullptr;  // flattened per-leaf metadata for the refresh kernel: [n_free, card[], stride[]]
+  std::vector<int> leaf_meta_off;      // per real leaf: offset inside d_leaf_meta
+  long long* d_miss_rows = nullptr;    // per real leaf: row of its no-evidence Lambda inside d_lam
   long long param_version = 0; // bumped by chain_refresh: invalidates cached evidence tables
 };
 
@@ -68,7 +70,9 @@ struct ChainBatch {
   size_t comb_cap = 0;
   int* d_cols = nullptr;           // column metadata of the cached plan
   long long* d_rows = nullptr;
-  std::vector<int> plan_key;       // identifies the cached plan
+  std::vector<int> plan_key;       // identifies the cached plan (evidence columns -> leaves)
+  long long plan_version = -1;     // parameter version its evidence tables were built from
+  int n_inactive = 0;
   // dense engine (dense.cu): per-sequence state, beta / R rows
   double* d_dense = nullptr;
   int* d_dense_i = nullptr;
