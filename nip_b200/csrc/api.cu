@@ -503,10 +503,23 @@ int nipgpu_batch_create(nipgpu_model* m, int32_t n_series, const int32_t* length
 int nipgpu_batch_update(nipgpu_batch* b, const int32_t* data) {
   if (!b || !data) return fail(NIPGPU_EINVAL, "null argument");
   NIPGPU_CUDA(cudaSetDevice(b->m->device));
-  NIPGPU_CUDA(cudaMemcpyAsync(b->d_obs, data, (size_t)b->rows * b->n_obs * sizeof(int),
-                              cudaMemcpyHostToDevice, b->m->stream));
-  NIPGPU_CUDA(cudaStreamSynchronize(b->m->stream));
+  cudaStream_t st = b->m->stream;
+  NIPGPU_CUDA(cudaMemcpyAsync(b->d_obs, data, (size_t)b->rows * b->n_obs * sizeof(int), cudaMemcpyHostToDevice, st));
   b->chain.plan_key.clear();  // cached per-row evidence configuration is stale
+  // range check on the device (an index >= the cardinality would address past the evidence
+  // tables; the reference would index out of bounds, src/nip.c:994)
+  if (!b->d_check) {
+    std::vector<int> cc(std::max(b->n_obs, 1) + 1, 0);
+    for (int k = 0; k < b->n_obs; k++) cc[k + 1] = b->m->hm.card[b->obs_vars[k]];
+    if (int e = dev_upload(&b->d_check, cc, st)) return e;   // [0] flag, [1..] cardinality per column
+    NIPGPU_CUDA(cudaStreamSynchronize(st));
+  }
+  int flag = 0;
+  NIPGPU_CUDA(cudaMemsetAsync(b->d_check, 0, sizeof(int), st));
+  if (int e = check_obs(b->d_obs, b->rows, b->n_obs, b->d_check + 1, b->d_check, st)) return e;
+  NIPGPU_CUDA(cudaMemcpyAsync(&flag, b->d_check, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  if (flag) return fail(NIPGPU_EINVAL, "observation index >= cardinality");
   return NIPGPU_OK;
 }
 
@@ -515,7 +528,7 @@ void nipgpu_batch_destroy(nipgpu_batch* b) {
   if (b->m) { cudaSetDevice(b->m->device); cudaStreamSynchronize(b->m->stream); }
   cudaFree(b->d_len); cudaFree(b->d_row_off); cudaFree(b->d_obs); cudaFree(b->d_obs_proj);
   cudaFree(b->d_qproj); cudaFree(b->d_qoff); cudaFree(b->d_alpha); cudaFree(b->d_post);
-  cudaFree(b->d_ll); cudaFree(b->d_like); cudaFree(b->d_status); cudaFree(b->d_first); cudaFree(b->d_joint);
+  cudaFree(b->d_ll); cudaFree(b->d_like); cudaFree(b->d_status); cudaFree(b->d_first); cudaFree(b->d_joint); cudaFree(b->d_check);
   chain_batch_free(b->chain);
   delete b;
 }

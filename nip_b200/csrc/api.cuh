@@ -68,6 +68,7 @@ struct nipgpu_batch {
   size_t post_cap = 0;
   int* d_status = nullptr;
   unsigned char* d_first = nullptr;  // [rows] 1 on the first row of every series (memoised likelihood)
+  int* d_check = nullptr;            // [0] range-check flag, [1..n_obs] cardinality per data column
   double* d_joint = nullptr;         // [rows][SP] posterior of the joint interface state (composite interfaces)
   nipgpu::ChainBatch chain;
 };

@@ -114,6 +114,21 @@ int init_potential(double* table, int n, const double* cpt, const FamMap& fm, cu
   return NIPGPU_OK;
 }
 
+// flag[0] = 1 if some observation is >= the cardinality of its column's variable
+__global__ void k_check_obs(const int* __restrict__ obs, long long n, int n_obs, const int* __restrict__ col_card,
+                            int* flag) {
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+       x += (long long)gridDim.x * blockDim.x)
+    if (obs[x] >= col_card[x % n_obs]) *flag = 1;
+}
+
+int check_obs(const int* obs, long long rows, int n_obs, const int* col_card, int* flag, cudaStream_t st) {
+  if (rows <= 0 || n_obs <= 0) return NIPGPU_OK;
+  k_check_obs<<<blocks_for(rows * n_obs, 256), 256, 0, st>>>(obs, rows * n_obs, n_obs, col_card, flag);
+  NIPGPU_LAUNCHED();
+  return NIPGPU_OK;
+}
+
 int finish_estep(const double* acc, int groups, long long stride, long long n, double pseudo,
                  const double* ll, const int* status, int n_series, double* counts, cudaStream_t st) {
   k_finish_estep<<<blocks_for(n, 256), 256, 0, st>>>(acc, groups, stride, n, pseudo, ll, status,

@@ -32,4 +32,7 @@ int init_potential(double* table, int n, const double* cpt, const FamMap& fm, cu
 int finish_estep(const double* acc, int groups, long long stride, long long n, double pseudo,
                  const double* ll, const int* status, int n_series, double* counts, cudaStream_t st);
 
+// device-side range check of a batch's observations (flag[0] set when one is >= its cardinality)
+int check_obs(const int* obs, long long rows, int n_obs, const int* col_card, int* flag, cudaStream_t st);
+
 }  // namespace nipgpu

@@ -424,3 +424,24 @@ def test_hmm_all_variables_vs_oracle(gpu_lib, oracle_lib, S, M, B, T):
     for i, got in enumerate(b.split(post)):
         want, llw = om.infer(h.obs_vars, series[i], [0, 1], forward_only=True)
         assert_close(got, want, "HMM-%d series %d filtered (M1, P1)" % (S, i), atol=1e-300)
+
+
+def test_batch_update_checks_the_observation_range(gpu_lib):
+    """a re-uploaded observation >= the cardinality of its variable is refused (it would index
+    past the evidence tables); valid data is accepted and used"""
+    from nip_b200.api import NipGpuError
+    c = Case("hmm5")
+    m = gpu_lib.Model(c.fm)
+    s = [np.array(x, dtype=np.int32) for x in c.series]
+    b = m.batch(c.obs_vars, s)
+    flat = np.concatenate([x.reshape(-1) for x in s]).astype(np.int32)
+    good = np.where(flat >= 0, (flat + 1) % int(c.fm.var_card[c.obs_vars[0]]), flat).astype(np.int32)
+    b.update(good)
+    post, ll = b.infer(c.query)
+    b2 = m.batch(c.obs_vars, [g.reshape(-1, 1) for g in np.split(good, np.cumsum([len(x) for x in s])[:-1])])
+    post2, ll2 = b2.infer(c.query)
+    assert np.array_equal(post, post2) and np.array_equal(ll, ll2)
+    bad = good.copy()
+    bad[len(bad) // 2] = int(c.fm.var_card[c.obs_vars[0]])
+    with pytest.raises(NipGpuError):
+        b.update(bad)
