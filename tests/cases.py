@@ -7,10 +7,11 @@ from nip_b200.desc import FlatModel, load_json
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALL_CASES = ["model_net", "demo1_net", "empty_net_em", "hmm5", "hmm12_two_leaves", "coupled2x3",
-             "factorial4x3", "no_interface"]
+             "factorial4x3", "no_interface", "two_layer", "shared_obs", "structural_zeros"]
 EM_CASES = ["demo1_net", "empty_net_em", "hmm5", "hmm12_two_leaves", "coupled2x3", "factorial4x3",
-            "no_interface"]
-LIKELIHOOD_CASES = ["model_net", "demo1_net", "hmm5", "hmm12_two_leaves", "coupled2x3", "factorial4x3"]
+            "no_interface", "two_layer", "shared_obs"]
+LIKELIHOOD_CASES = ["model_net", "demo1_net", "hmm5", "hmm12_two_leaves", "coupled2x3", "factorial4x3",
+                    "two_layer", "shared_obs", "structural_zeros"]
 SLICE_CASES = ["model_net", "demo1_net"]
 RTOL = 1e-9   # north star: 1e-9 relative on posteriors, log-likelihood, re-estimated CPTs
 

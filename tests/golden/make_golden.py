@@ -55,8 +55,13 @@ def observed_start(series):
     return out
 
 
+ONLY = None   # set from the command line: only=name1,name2 regenerates just those fixtures
+
+
 def make_case(R, name, net_path, obs_names, series, query_names, em_seed=None, em_iters=3,
               likelihood_marked=None, slice_script=None):
+    if ONLY is not None and name not in ONLY:
+        return
     if em_seed is not None:
         series = observed_start([np.asarray(s).reshape(-1, len(obs_names)) for s in series])
     m = R.parse(net_path)
@@ -215,6 +220,42 @@ def main():
     series = rand_series(r4, [4], 4, 1, 5, 0.2)
     make_case(R, "no_interface", write("noif.net", text), ["W"], series, ["U", "V", "W"], em_seed=9)
 
+    # 8. a hidden middle layer inside the slice: X0 -> X1 -> H1, Y1 | H1 X1, Z1 | H1
+    r6 = np.random.default_rng(16)
+    text = net_text_generic(
+        [("Y1", 4, None), ("Z1", 2, None), ("H1", 2, None), ("X1", 3, None), ("X0", 3, "X1")],
+        [("Y1", ["X1", "H1"], r6.random((3, 2, 4)) + 0.05), ("Z1", ["H1"], r6.random((2, 2)) + 0.05),
+         ("H1", ["X1"], r6.random((3, 2)) + 0.05), ("X1", ["X0"], r6.random((3, 3)) + 0.05),
+         ("X0", [], (r6.random(3) + 0.1)[None, :])])
+    series = rand_series(r6, [4, 2], 6, 1, 9, 0.2)
+    make_case(R, "two_layer", write("two_layer.net", text), ["Y1", "Z1"], series, ["X1", "H1", "Y1", "X0"],
+              em_seed=31, likelihood_marked=["Y1"])
+
+    # 9. two chains with independent dynamics but a SHARED observation Y1 | A1 B1 (explaining away)
+    r7 = np.random.default_rng(17)
+    text = net_text_generic(
+        [("Y1", 3, None), ("U1", 2, None), ("A1", 2, None), ("B1", 3, None), ("A0", 2, "A1"), ("B0", 3, "B1")],
+        [("Y1", ["B1", "A1"], r7.random((3, 2, 3)) + 0.05), ("U1", ["A1"], r7.random((2, 2)) + 0.05),
+         ("A1", ["A0"], r7.random((2, 2)) + 0.05), ("B1", ["B0"], r7.random((3, 3)) + 0.05),
+         ("A0", [], (r7.random(2) + 0.1)[None, :]), ("B0", [], (r7.random(3) + 0.1)[None, :])])
+    series = rand_series(r7, [3, 2], 6, 1, 8, 0.2)
+    make_case(R, "shared_obs", write("shared_obs.net", text), ["Y1", "U1"], series, ["A1", "B1", "B0", "Y1"],
+              em_seed=32, likelihood_marked=["Y1", "U1"])
+
+    # 10. structural zeros: a cyclic, almost deterministic chain and observations that rule states out
+    A = np.array([[0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0.5, 0.5], [1, 0, 0, 0]], dtype=float)
+    E = np.array([[1, 0, 0], [0.5, 0.5, 0], [0, 1, 0], [0, 0, 1]], dtype=float)
+    text = net_text_generic(
+        [("M1", 3, None), ("P1", 4, None), ("P0", 4, "P1")],
+        [("M1", ["P1"], E), ("P1", ["P0"], A), ("P0", [], np.array([[0.5, 0.5, 0, 0]]))])
+    series = [np.array(x).reshape(-1, 1) for x in
+              ([0, 1, 1, 2, 0], [1, 1, 2, 0, 0, 1], [0, 0], [2, 2], [-1, 1, -1, 2], [0, 1, 2, 1], [1], [-1, -1, 0])]
+    make_case(R, "structural_zeros", write("zeros.net", text), ["M1"], series, ["P1", "P0", "M1"],
+              likelihood_marked=["M1"])
+
 
 if __name__ == "__main__":
+    for a in sys.argv[1:]:
+        if a.startswith("only="):
+            ONLY = set(a[5:].split(","))
     main()
