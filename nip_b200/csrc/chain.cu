@@ -1257,6 +1257,11 @@ void chain_batch_free(ChainBatch& cb) {
   cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_rows); cudaFree(cb.d_comb);
   cudaFree(cb.d_rt); cudaFree(cb.d_hvec); cudaFree(cb.d_first); cudaFree(cb.d_r0); cudaFree(cb.d_em_scratch);
   cudaFree(cb.d_dense); cudaFree(cb.d_dense_i);
+  for (int k = 0; k < 3; k++) {
+    if (cb.dense_stream[k]) cudaStreamDestroy(cb.dense_stream[k]);
+    if (cb.dense_join[k]) cudaEventDestroy(cb.dense_join[k]);
+  }
+  if (cb.dense_fork) cudaEventDestroy(cb.dense_fork);
   cb = ChainBatch();
 }
 

@@ -76,6 +76,8 @@ struct ChainBatch {
   // dense engine (dense.cu): per-sequence state, beta / R rows
   double* d_dense = nullptr;
   int* d_dense_i = nullptr;
+  cudaStream_t dense_stream[3] = {};     // the other parts of the batch run here
+  cudaEvent_t dense_fork = nullptr, dense_join[3] = {};
   // EM (chain_estep)
   double *d_rt = nullptr, *d_hvec = nullptr, *d_r0 = nullptr, *d_em_scratch = nullptr;  // beta rows, h_t, r_0 rows
   unsigned char* d_first = nullptr;  // [rows] 1 on the first row of every series

@@ -445,62 +445,95 @@ int dense_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan, con
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_dense_i, (size_t)n * 5 * sizeof(int) + 64));
     (void)doubles;
   }
-  DenseState stt;
-  double* p = cb.d_dense;
-  stt.K = p; p += n; stt.Pp = p; p += n; stt.cp = p; p += n; stt.g = p; p += n;
-  stt.p1 = p; p += n; stt.p2 = p; p += n;
-  double* h = p; p += n; p += n;  // (spare)
-  double* beta = p; p += (size_t)n * SP;
-  double* R0 = p; p += (size_t)n * SP;
-  double* R1b = p;
-  int* ip = cb.d_dense_i;
-  stt.e1 = ip; ip += n; stt.e2 = ip; ip += n; stt.zero = ip; ip += n; stt.bad = ip; ip += n; stt.noev = ip;
-
-  DenseBatch B;
-  B.n_series = n; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted; B.row_off = a.d_row_off; B.cfg = cb.d_cfg;
   const size_t smem = (size_t)(2 * TM * LDA + 2 * TK * LDB) * sizeof(double);
   NIPGPU_CUDA(cudaFuncSetAttribute(k_dense_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NIPGPU_CUDA(cudaFuncSetAttribute(k_dense_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int wgrid = (n + 7) / 8;  // 8 warps (sequences) per 256-thread block
-  auto n_longer = [&](int t) {    // sequences (a prefix of the sorted order) with length > t
-    return (int)(std::lower_bound(cb.len_sorted.begin(), cb.len_sorted.end(), t, std::greater<int>()) - cb.len_sorted.begin());
-  };
   const bool filt = a.forward_only && a.d_post;
   double* fpost = filt ? a.d_post : nullptr;
 
-  k_dense_first<<<wgrid, 256, 0, st>>>(B, S, SP, cm.d_phi0, cb.d_comb, cm.m1_0, plan.c_miss, cb.d_alpha, stt);
-  NIPGPU_LAUNCHED();
-  for (int t = 1; t <= a.t_max; t++) {
-    k_dense_fsettle<<<wgrid, 256, 0, st>>>(B, t, S, SP, cm.d_R1, plan.c_miss, cb.d_alpha, a.want_ll, fpost,
-                                           a.post_stride, a.post_off, stt);
-    NIPGPU_LAUNCHED();
-    const int rows = n_longer(t);
-    if (t < a.t_max && rows > 0) {
-      dim3 grid(SP / TN, (rows + TM - 1) / TM);
-      k_dense_gemm<0><<<grid, 256, smem, st>>>(B, t, rows, SP, cb.d_alpha, 1, cm.d_Bf1, cb.d_comb, stt.g,
-                                               cb.d_alpha, nullptr);
-      NIPGPU_LAUNCHED();
-    }
-  }
-  k_dense_ll<<<(n + 255) / 256, 256, 0, st>>>(B, stt, a.want_ll ? a.d_ll : nullptr, a.d_status);
-  NIPGPU_LAUNCHED();
-  if (a.forward_only || (!a.d_post && !em)) return NIPGPU_OK;
+  // the whole pass for the sorted positions [off, off + cnt) on stream s
+  auto run_part = [&](int off, int cnt, cudaStream_t s) -> int {
+    DenseState stt;
+    double* p = cb.d_dense;
+    stt.K = p + off; p += n; stt.Pp = p + off; p += n; stt.cp = p + off; p += n; stt.g = p + off; p += n;
+    stt.p1 = p + off; p += n; stt.p2 = p + off; p += n;
+    double* h = p + off; p += n; p += n;  // (spare)
+    double* beta = p + (size_t)off * SP; p += (size_t)n * SP;
+    double* R0 = p + (size_t)off * SP; p += (size_t)n * SP;
+    double* R1b = p + (size_t)off * SP;
+    int* ip = cb.d_dense_i;
+    stt.e1 = ip + off; ip += n; stt.e2 = ip + off; ip += n; stt.zero = ip + off; ip += n; stt.bad = ip + off; ip += n;
+    stt.noev = ip + off;
+    DenseBatch B;
+    B.n_series = cnt; B.order = cb.d_order + off; B.len_sorted = cb.d_len_sorted + off; B.row_off = a.d_row_off;
+    B.cfg = cb.d_cfg;
+    const int wgrid = (cnt + 7) / 8;  // 8 warps (sequences) per 256-thread block
+    auto first_len = cb.len_sorted.begin() + off, last_len = first_len + cnt;
+    auto n_longer = [&](int t) {      // sequences (a prefix of the sorted order) with length > t
+      return (int)(std::lower_bound(first_len, last_len, t, std::greater<int>()) - first_len);
+    };
+    const int t_max = cnt > 0 ? *first_len : 0;   // longest sequence of this part
 
-  double* Rcur = R0;
-  double* Rnext = R1b;
-  for (int t = a.t_max - 1; t >= 0; t--) {
-    k_dense_bsettle<<<wgrid, 256, 0, st>>>(B, t, S, SP, cm.d_colsum, cb.d_comb, cb.d_alpha, beta, Rcur, h, a.d_post,
-                                           a.post_stride, a.post_off, em ? em->bt : nullptr,
-                                           em ? em->hvec : nullptr, em ? em->r0 : nullptr, cm.d_phi0);
+    k_dense_first<<<wgrid, 256, 0, s>>>(B, S, SP, cm.d_phi0, cb.d_comb, cm.m1_0, plan.c_miss, cb.d_alpha, stt);
     NIPGPU_LAUNCHED();
-    const int rows = n_longer(t);
-    if (t >= 1 && rows > 0) {
-      dim3 grid(SP / TN, (rows + TM - 1) / TM);
-      k_dense_gemm<1><<<grid, 256, smem, st>>>(B, t, rows, SP, Rcur, 0, cm.d_Bb1, cb.d_comb, h, beta, Rnext);
+    for (int t = 1; t <= t_max; t++) {
+      k_dense_fsettle<<<wgrid, 256, 0, s>>>(B, t, S, SP, cm.d_R1, plan.c_miss, cb.d_alpha, a.want_ll, fpost,
+                                            a.post_stride, a.post_off, stt);
       NIPGPU_LAUNCHED();
-      std::swap(Rcur, Rnext);
+      const int rows = n_longer(t);
+      if (t < t_max && rows > 0) {
+        dim3 grid(SP / TN, (rows + TM - 1) / TM);
+        k_dense_gemm<0><<<grid, 256, smem, s>>>(B, t, rows, SP, cb.d_alpha, 1, cm.d_Bf1, cb.d_comb, stt.g,
+                                                cb.d_alpha, nullptr);
+        NIPGPU_LAUNCHED();
+      }
     }
+    k_dense_ll<<<(cnt + 255) / 256, 256, 0, s>>>(B, stt, a.want_ll ? a.d_ll : nullptr, a.d_status);
+    NIPGPU_LAUNCHED();
+    if (a.forward_only || (!a.d_post && !em)) return NIPGPU_OK;
+
+    double* Rcur = R0;
+    double* Rnext = R1b;
+    for (int t = t_max - 1; t >= 0; t--) {
+      k_dense_bsettle<<<wgrid, 256, 0, s>>>(B, t, S, SP, cm.d_colsum, cb.d_comb, cb.d_alpha, beta, Rcur, h, a.d_post,
+                                            a.post_stride, a.post_off, em ? em->bt : nullptr,
+                                            em ? em->hvec : nullptr, em ? em->r0 : nullptr, cm.d_phi0);
+      NIPGPU_LAUNCHED();
+      const int rows = n_longer(t);
+      if (t >= 1 && rows > 0) {
+        dim3 grid(SP / TN, (rows + TM - 1) / TM);
+        k_dense_gemm<1><<<grid, 256, smem, s>>>(B, t, rows, SP, Rcur, 0, cm.d_Bb1, cb.d_comb, h, beta, Rnext);
+        NIPGPU_LAUNCHED();
+        std::swap(Rcur, Rnext);
+      }
+    }
+    return NIPGPU_OK;
+  };
+
+  // Parts of the batch on their own streams: one part's settle kernels and the ragged last wave
+  // of its GEMMs (256 CTAs on 148 SMs for the whole C4 batch) run under the other parts' GEMMs.
+  // Sorted by length: interleaving would balance ragged sets better, contiguous parts keep the
+  // views plain pointer offsets.
+  int parts = n >= 512 ? 2 : 1;   // C4: 72 ms in one part, 62 ms in two, 67 / 66 ms in three / four
+  if (const char* e = getenv("NIPGPU_DENSE_PARTS")) parts = std::max(1, std::min(4, atoi(e)));
+  if (parts == 1) return run_part(0, n, st);
+  if (!cb.dense_fork) NIPGPU_CUDA(cudaEventCreateWithFlags(&cb.dense_fork, cudaEventDisableTiming));
+  const int per = ((n + parts - 1) / parts + 7) / 8 * 8;
+  NIPGPU_CUDA(cudaEventRecord(cb.dense_fork, st));
+  for (int k = 1; k < parts; k++) {
+    const int off = k * per, cnt = std::min(per, n - off);
+    if (cnt <= 0) break;
+    if (!cb.dense_stream[k - 1]) {
+      NIPGPU_CUDA(cudaStreamCreateWithFlags(&cb.dense_stream[k - 1], cudaStreamNonBlocking));
+      NIPGPU_CUDA(cudaEventCreateWithFlags(&cb.dense_join[k - 1], cudaEventDisableTiming));
+    }
+    NIPGPU_CUDA(cudaStreamWaitEvent(cb.dense_stream[k - 1], cb.dense_fork, 0));
+    if (int e = run_part(off, cnt, cb.dense_stream[k - 1])) return e;
+    NIPGPU_CUDA(cudaEventRecord(cb.dense_join[k - 1], cb.dense_stream[k - 1]));
   }
+  if (int e = run_part(0, std::min(per, n), st)) return e;
+  for (int k = 1; k < parts; k++)
+    if (k * per < n) NIPGPU_CUDA(cudaStreamWaitEvent(st, cb.dense_join[k - 1], 0));
   return NIPGPU_OK;
 }
 
