@@ -66,7 +66,7 @@ def build_host_backend(force=False, verbose=False):
     """nip.h entry points on top of the C ABI; needs the reference headers
     (struct layouts), so it is only (re)built where /root/reference exists."""
     src = [os.path.join(PKG, "host", "nip_gpu_backend.c"), os.path.join(PKG, "host", "nip_model_export.c"),
-           os.path.join(PKG, "host", "nip_data_bin.c")]
+           os.path.join(PKG, "host", "nip_data_bin.c"), os.path.join(PKG, "host", "nip_model_write.c")]
     if not os.path.isdir(REF_SRC) or not all(os.path.exists(s) for s in src):
         return HOST_LIB if os.path.exists(HOST_LIB) else None
     if not force and not _stale(HOST_LIB, src + [LIB]):
