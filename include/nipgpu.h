@@ -205,6 +205,13 @@ int nipgpu_slice_get_clique(nipgpu_model* m, int32_t clique, double* out);
 /* D2H copy of a sepset's current potential (sepset->new), sepsets numbered as in the description */
 int nipgpu_slice_get_sepset(nipgpu_model* m, int32_t sepset, double* out);
 
+/* Ancestral sampling of n_series series of `length` slices from the model's current parameters
+ * (generate_data, src/nip.c:2325-2478, one series at a time with several make_consistent per
+ * variable per slice).  out: host [n_series][length][n_vars] state indices, variables in the
+ * order of the description.  Chain-structured models only (NIPGPU_EUNSUPPORTED otherwise); the
+ * random stream is the library's own (splitmix64 per series), not rand(). */
+int nipgpu_sample(nipgpu_model* m, int32_t n_series, int32_t length, uint64_t seed, int32_t* out);
+
 /* ---- instrumentation -------------------------------------------------- */
 /* number of kernels this library launched since the counter was last reset */
 int64_t nipgpu_launch_count(int reset);

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "nipgpu_em_counts_device", "nipgpu_em_mstep", "nipgpu_likelihood", "nipgpu_slice_reset",
     "nipgpu_slice_use_priors", "nipgpu_slice_enter_prior", "nipgpu_slice_enter_evidence", "nipgpu_slice_get_sepset", "nipgpu_slice_make_consistent",
     "nipgpu_slice_mass", "nipgpu_slice_marginal", "nipgpu_slice_get_clique",
-    "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_jt_trace", "nipgpu_model_stream", "nipgpu_probe_peaks",
+    "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_jt_trace", "nipgpu_sample", "nipgpu_model_stream", "nipgpu_probe_peaks",
 ]
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -86,6 +86,7 @@ def load_library(path=LIB_PATH):
     L.nipgpu_launch_count.argtypes = [_i]
     L.nipgpu_last_kernel_ms.argtypes = [_vp, C.POINTER(_d), C.POINTER(C.c_int32)]
     L.nipgpu_jt_trace.argtypes = [_vp, _vp, _i, _i]
+    L.nipgpu_sample.argtypes = [_vp, _i, _i, C.c_uint64, _vp]
     L.nipgpu_probe_peaks.argtypes = [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]
     L.nipgpu_model_stream.restype = _vp
     L.nipgpu_model_stream.argtypes = [_vp]
@@ -180,6 +181,12 @@ class Model:
         ms, n = _d(), C.c_int32()
         _check(self.L.nipgpu_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def sample(self, n_series, length, seed=1):
+        """[n_series, length, n_vars] int32 states drawn from the model (chain-structured models)"""
+        out = np.zeros((n_series, length, self.fm.n_vars), dtype=np.int32)
+        _check(self.L.nipgpu_sample(self.h, int(n_series), int(length), int(seed), _p(out)))
+        return out
 
     def jt_trace(self, reset=True, cap=8192):
         """(tag, ns) per grid barrier of the generic engine's grid team (NIPGPU_JT_TRACE=1)"""

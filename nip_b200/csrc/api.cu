@@ -863,6 +863,22 @@ int nipgpu_slice_marginal(nipgpu_model* m, int32_t var, double* out) {
   return NIPGPU_OK;
 }
 
+int nipgpu_sample(nipgpu_model* m, int32_t n_series, int32_t length, uint64_t seed, int32_t* out) {
+  if (!m || !out || n_series < 0 || length < 0) return fail(NIPGPU_EINVAL, "bad arguments");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  if (!m->chain.ok) return fail(NIPGPU_EUNSUPPORTED, "sampling needs a chain-structured model");
+  const size_t n = (size_t)n_series * length * m->hm.nv;
+  if (n == 0) return NIPGPU_OK;
+  int* d_out = nullptr;
+  NIPGPU_CUDA(cudaMalloc((void**)&d_out, n * sizeof(int)));
+  int e = chain_sample(m->hm, m->chain, m->d_base0, m->d_base1, m->tab_off, m->d_ipool, n_series, length, seed,
+                       d_out, m->stream);
+  if (e == NIPGPU_OK && cudaMemcpy(out, d_out, n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) e = NIPGPU_ECUDA;
+  cudaFree(d_out);
+  if (e == NIPGPU_EUNSUPPORTED) return fail(e, "sampling: model layout not supported");
+  return e;
+}
+
 int nipgpu_jt_trace(nipgpu_model* m, uint64_t* out, int cap_records, int reset) {
   if (!m || !out || cap_records < 0) return fail(NIPGPU_EINVAL, "bad arguments") , -1;
   if (!m->d_trace) return 0;

@@ -1578,6 +1578,122 @@ int chain_post_vars(const HostModel& hm, const ChainModel& cm, const ChainBatch&
   return NIPGPU_OK;
 }
 
+// ---- ancestral sampling ------------------------------------------------------------------
+namespace {
+
+struct SampleLeaf {
+  int tab, base, off, R, n_free, ip_to_s;   // offsets into base1 / the int pool / d_ip_to_s
+  int card[8], var[8];
+};
+struct SamplePlan {
+  int S, nif, nv, n_leaves, c0_tab;
+  int out_var[16], prev_var[16], card[16];
+};
+
+__device__ __forceinline__ double uniform01(unsigned long long& x) {   // splitmix64
+  x += 0x9e3779b97f4a7c15ull;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// index i with probability w(i) / sum w over n entries given by f(i)
+template <class F>
+__device__ __forceinline__ int draw(int n, F f, unsigned long long& rng) {
+  double tot = 0;
+  for (int i = 0; i < n; i++) tot += f(i);
+  const double u = uniform01(rng) * tot;
+  double acc = 0;
+  int last = 0;
+  for (int i = 0; i < n; i++) {
+    const double w = f(i);
+    if (w > 0) last = i;
+    acc += w;
+    if (u < acc && w > 0) return i;
+  }
+  return last;
+}
+
+__global__ void k_chain_sample(SamplePlan Q, const SampleLeaf* leaves, const double* base0, const double* base1,
+                               const int* ipool, const int* ent_of, const int* ip_to_s, const double* phi0,
+                               const double* lam0, int n_series, int length, unsigned long long seed, int* out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_series) return;
+  unsigned long long rng = seed * 0x2545f4914f6cdd1dull + (unsigned long long)s * 0xd1342543de82ef95ull + 1;
+  const int S = Q.S;
+  const double* c0_0 = base0 + Q.c0_tab;
+  const double* c0_1 = base1 + Q.c0_tab;
+  // lam0[j] = mass of the slice's leaves without evidence: 1 for proper CPTs, and what the
+  // reference's per-slice propagation weighs the state with otherwise (generate_data samples every
+  // variable from its marginal in the consistent, partially instantiated slice)
+  int state = draw(S, [&](int j) { return phi0[j] * lam0[j]; }, rng);
+  int prev = draw(S, [&](int i) { return c0_0[ent_of[i * S + state]]; }, rng);
+  for (int t = 0; t < length; t++) {
+    if (t > 0) {
+      prev = state;
+      state = draw(S, [&](int j) { return c0_1[ent_of[prev * S + j]] * lam0[j]; }, rng);
+    }
+    int* row = out + ((long long)s * length + t) * Q.nv;
+    for (int k = 0, st = state, pv = prev; k < Q.nif; k++) {
+      row[Q.out_var[k]] = st % Q.card[k];
+      row[Q.prev_var[k]] = pv % Q.card[k];
+      st /= Q.card[k];
+      pv /= Q.card[k];
+    }
+    for (int l = 0; l < Q.n_leaves; l++) {
+      const SampleLeaf L = leaves[l];
+      const double* T = base1 + L.tab + ipool[L.base + ip_to_s[L.ip_to_s + state]];
+      int r = draw(L.R, [&](int x) { return T[ipool[L.off + x]]; }, rng);
+      for (int k = 0; k < L.n_free; k++) {
+        row[L.var[k]] = r % L.card[k];
+        r /= L.card[k];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int chain_sample(const HostModel& hm, const ChainModel& cm, const double* d_base0, const double* d_base1,
+                 const std::vector<int>& tab_off, const int* d_ipool, int n_series, int length,
+                 unsigned long long seed, int* d_out, cudaStream_t st) {
+  if (!cm.ok || hm.nif > 16) return NIPGPU_EUNSUPPORTED;
+  SamplePlan Q{};
+  Q.S = cm.S; Q.nif = hm.nif; Q.nv = hm.nv; Q.n_leaves = cm.n_real; Q.c0_tab = tab_off[cm.c0];
+  std::vector<char> covered(hm.nv, 0);
+  for (int k = 0; k < hm.nif; k++) {
+    Q.out_var[k] = hm.outg[k]; Q.prev_var[k] = hm.prev[k]; Q.card[k] = hm.card[hm.outg[k]];
+    covered[hm.outg[k]] = covered[hm.prev[k]] = 1;
+  }
+  std::vector<SampleLeaf> leaves(std::max(cm.n_real, 1));
+  for (int l = 0; l < cm.n_real; l++) {
+    const ChainLeafHost& L = cm.leaves[l];
+    const Proj& p = hm.projs[L.proj];
+    if (L.free_vars.size() > 8) return NIPGPU_EUNSUPPORTED;
+    SampleLeaf& d = leaves[l];
+    d.tab = tab_off[L.clique]; d.base = p.base_pos; d.off = p.off_pos; d.R = p.R;
+    d.n_free = (int)L.free_vars.size(); d.ip_to_s = l * cm.S;
+    // off[r] enumerates the leaf's free variables in clique order, first fastest (HostModel::add_proj)
+    for (int k = 0; k < d.n_free; k++) { d.card[k] = hm.card[L.free_vars[k]]; d.var[k] = L.free_vars[k]; covered[L.free_vars[k]] = 1; }
+  }
+  for (int v = 0; v < hm.nv; v++)
+    if (!covered[v]) return NIPGPU_EUNSUPPORTED;
+  if (n_series <= 0 || length <= 0) return NIPGPU_OK;
+  SampleLeaf* d_leaves = nullptr;
+  NIPGPU_CUDA(cudaMalloc((void**)&d_leaves, leaves.size() * sizeof(SampleLeaf)));
+  NIPGPU_CUDA(cudaMemcpyAsync(d_leaves, leaves.data(), leaves.size() * sizeof(SampleLeaf), cudaMemcpyHostToDevice, st));
+  k_chain_sample<<<(n_series + 127) / 128, 128, 0, st>>>(Q, d_leaves, d_base0, d_base1, d_ipool, cm.d_ent_of,
+                                                         cm.d_ip_to_s, cm.d_phi0, cm.d_lam0, n_series, length, seed,
+                                                         d_out);
+  g_launches++;
+  const cudaError_t err = cudaStreamSynchronize(st);
+  cudaFree(d_leaves);
+  if (err != cudaSuccess) { set_error(std::string("chain_sample: ") + cudaGetErrorString(err)); return NIPGPU_ECUDA; }
+  return NIPGPU_OK;
+}
+
 // E-step of a whole batch on the chain engine: forward, backward (EM flavour), transition
 // counts as a DMMA GEMM, leaf counts, then expected clique tables -> per-variable family
 // counts in the layout of em_learn's `parameters[]` (src/nip.c:2108-2128).

@@ -177,4 +177,13 @@ int chain_post_vars(const HostModel& hm, const ChainModel& cm, const ChainBatch&
                     const unsigned char* first, const long long* d_row_off, int n_series, long long rows,
                     int out_row, double* out, cudaStream_t st);
 
+// Ancestral sampling of whole series from a chain-structured model (generate_data,
+// src/nip.c:2325-2478, needs several make_consistent per variable per slice): one thread per
+// series walks the slices — joint interface state from phi0 / the transition rows of base1, the
+// previous-slice variables of slice 0 from base0, the free variables of every leaf from its table.
+// out: device [n_series][length][n_vars] state indices, variables in model order.
+int chain_sample(const HostModel& hm, const ChainModel& cm, const double* d_base0, const double* d_base1,
+                 const std::vector<int>& tab_off, const int* d_ipool, int n_series, int length,
+                 unsigned long long seed, int* d_out, cudaStream_t st);
+
 }  // namespace nipgpu

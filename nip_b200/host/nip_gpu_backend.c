@@ -388,6 +388,56 @@ void free_timeseries(time_series ts) {
 }
 #endif
 
+/* ---- data generation ---------------------------------------------------------
+ * generate_data() (src/nip.c:2325-2478) samples one series with several make_consistent per
+ * variable per slice.  nip_gpu_generate_set() draws a whole set on the device: n ordinary
+ * `time_series` in which every model variable is observed (columns in model->variables order),
+ * to be freed with free_timeseries().  The random stream is the device library's, not rand(). */
+int nip_gpu_generate_set(nip_model model, int n, int length, unsigned long seed, time_series** results) {
+  backend_entry* e;
+  int32_t* raw;
+  time_series* set;
+  int s, t, k, nv, rc;
+  if (!model || !results || n <= 0 || length <= 0) {
+    nip_report_error(__FILE__, __LINE__, NIP_ERROR_INVALID_ARGUMENT, 1);
+    return 0;
+  }
+  *results = NULL;
+  e = backend_for(model);
+  if (!e) { nip_report_error(__FILE__, __LINE__, NIP_ERROR_GENERAL, 1); return 0; }
+  nv = model->num_of_vars;
+  raw = (int32_t*)calloc((size_t)n * length * nv, sizeof(int32_t));
+  set = (time_series*)calloc((size_t)n, sizeof(time_series));
+  if (!raw || !set) { free(raw); free(set); nip_report_error(__FILE__, __LINE__, NIP_ERROR_OUTOFMEMORY, 1); return 0; }
+  rc = nipgpu_sample(e->gm, n, length, (uint64_t)seed, raw);
+  if (rc != NIPGPU_OK) {
+    fprintf(stderr, "nip gpu backend: %s\n", nipgpu_last_error());
+    nip_report_error(__FILE__, __LINE__, NIP_ERROR_GENERAL, 1);
+    free(raw); free(set);
+    return 0;
+  }
+  for (s = 0; s < n; s++) {
+    time_series ts = (time_series)calloc(1, sizeof(time_series_struct));
+    ts->model = model;
+    ts->length = length;
+    ts->num_of_observed = nv;
+    ts->num_of_hidden = 0;
+    ts->observed = (nip_variable*)calloc((size_t)nv, sizeof(nip_variable));
+    ts->hidden = (nip_variable*)calloc(1, sizeof(nip_variable));
+    ts->data = (int**)calloc((size_t)length, sizeof(int*));
+    for (k = 0; k < nv; k++) ts->observed[k] = model->variables[k];
+    for (t = 0; t < length; t++) {
+      ts->data[t] = (int*)calloc((size_t)nv, sizeof(int));
+      for (k = 0; k < nv; k++) ts->data[t][k] = raw[((size_t)s * length + t) * nv + nipgpu_var_index(model, model->variables[k])];
+    }
+    set[s] = ts;
+  }
+  free(raw);
+  *results = set;
+  nip_gpu_register_set(set, n);
+  return n;
+}
+
 /* ---- EM ---------------------------------------------------------------------
  * Control flow of em_learn (src/nip.c:2076-2250) with E- and M-steps on the
  * device: parameters, expected counts and log-likelihood stay in HBM across

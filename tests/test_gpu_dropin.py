@@ -220,3 +220,26 @@ def test_unchanged_cli_tools_on_the_gpu_backend(gpu_lib, tmp_path):
     scored = ll(_run("nipinference_cpu", tmp_path / "trained.net", tmp_path / "m1.txt", "P1", tmp_path / "p2.txt"))
     assert abs(final - scored) <= 2e-2 * abs(final)      # write_model keeps six decimals
     assert final >= ll(out_cpu) - 0.05                   # EM did at least as well as the generating model
+
+
+def test_generate_set_dropin(libs, tmp_path):
+    """nip_gpu_generate_set(): a whole set of fully observed series drawn on the device, usable by
+    the reference's own code (here: its smoother reproduces the sampled hidden states when every
+    variable is observed)"""
+    ref, gpu = libs
+    gpu.nip_gpu_generate_set.argtypes = [vp, i32, i32, C.c_ulong, C.POINTER(vp)]
+    gpu.nip_gpu_forget_set.argtypes = [vp]
+    h = HmmSpec(6, 4, seed=12)
+    p = tmp_path / "g.net"
+    p.write_text(h.net_text())
+    model = ref.parse(p)
+    out = vp()
+    n = gpu.nip_gpu_generate_set(model.h, 5, 7, 42, C.byref(out))
+    assert n == 5
+    series = C.cast(out, C.POINTER(vp))
+    for i in range(n):
+        model._T[series[i]] = 7
+        post, ll = model.infer(series[i], [1])          # P1 is observed in the generated data
+        assert np.all(np.isclose(post.max(axis=1), 1.0)) and np.isfinite(ll)
+    gpu.nip_gpu_forget_set(out)
+    gpu.nip_gpu_release(model.h)

@@ -446,3 +446,35 @@ def test_batch_update_checks_the_observation_range(gpu_lib):
     bad[len(bad) // 2] = int(c.fm.var_card[c.obs_vars[0]])
     with pytest.raises(NipGpuError):
         b.update(bad)
+
+
+@pytest.mark.parametrize("name", ["hmm5", "coupled2x3", "model_net"])
+def test_device_sampler_matches_the_model(gpu_lib, name):
+    """nipgpu_sample draws whole series on the device; with 200 000 series the empirical marginal of
+    every variable at every slice must sit within 5 sigma of the exact evidence-free marginal, and a
+    previous-slice variable must repeat its successor's value of the slice before.  examples/model.net
+    is declared parent first, so its tables are not proper CPTs (the parser's dimension-0
+    normalisation): there the forward sampler agrees with exact inference on the first slice only,
+    like the reference's generate_data, which never looks at future slices either."""
+    c = Case(name)
+    m = gpu_lib.Model(c.fm, engine=0)
+    N, T = 200000, 5
+    x = m.sample(N, T, seed=11)
+    assert x.shape == (N, T, c.fm.n_vars)
+    for k in range(c.fm.n_interface):
+        assert np.array_equal(x[:, 1:, int(c.fm.prev_outgoing[k])], x[:, :-1, int(c.fm.outgoing[k])])
+    allvars = list(range(c.fm.n_vars))
+    proper = name != "model_net"
+    b = m.batch(c.obs_vars, [np.full((T if proper else 1, len(c.obs_vars)), -1, dtype=np.int32)])
+    post, _ = b.infer(allvars)                      # no evidence: the prior predictive marginals
+    off = 0
+    for v in allvars:
+        card = int(c.fm.var_card[v])
+        for t in range(T if proper else 1):
+            want = post[t, off:off + card]
+            got = np.bincount(x[:, t, v], minlength=card) / N
+            sigma = np.sqrt(np.maximum(want * (1 - want), 1e-12) / N)
+            assert np.all(np.abs(got - want) <= 5 * sigma + 1e-9), (name, v, t, got, want)
+        off += card
+    assert not np.array_equal(x, m.sample(N, T, seed=12))
+    assert np.array_equal(x, m.sample(N, T, seed=11))
