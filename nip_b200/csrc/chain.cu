@@ -1717,7 +1717,17 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   const long long rows = std::max<long long>(a.rows, 1);
   // CTAs of the statistics kernel (one per SM, split-K); dense: split-K of the count GEMM, the
   // leaf pass uses row ranges so that its grid fills the machine
-  const int parts = dense ? 8 : std::max(1, x.sm_count);
+  int parts = std::max(1, x.sm_count);
+  if (dense) {  // split-K of the count GEMM: fill whole waves of SMs (1024 states: 64 tiles x 37 = 16 x 148)
+    const int tiles = (SP / 128) * (SP / 128), sms = std::max(1, x.sm_count);
+    double best = 0;
+    parts = 8;
+    for (int k = 4; k <= 48; k++) {
+      const int ctas = tiles * k, waves = (ctas + sms - 1) / sms;
+      const double eff = (double)ctas / ((double)waves * sms);
+      if (eff > best + 1e-9) { best = eff; parts = k; }
+    }
+  }
   const int partsC = dense ? std::max(1, 2 * x.sm_count / (SP / 128)) : parts;
   if (!cb.d_rt) {
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_rt, rows * SP * sizeof(double)));
