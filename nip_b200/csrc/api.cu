@@ -97,6 +97,11 @@ int choose_launch(nipgpu_model* m) {
     if (eg && atoi(eg) >= 1 && atoi(eg) <= 8) groups = atoi(eg);
     l.groups = groups;
     l.grid = all_ctas / groups;
+    // Concurrent cooperative kernels are only validated one by one by the runtime: together they
+    // must never ask for more CTAs than can be resident, or each would spin in its grid barrier
+    // waiting for CTAs the others keep out.  All groups run the same kernel (same occupancy) and
+    // join before the next kind is launched; a spare slot per group leaves room for a stray CTA.
+    if (groups > 1 && l.grid > 8) l.grid -= 1;
     const size_t part = 2 * (size_t)l.grid + 8, scratch = (size_t)l.grid * l.threads;
     l.group_stride = (work + part + scratch + 1) & ~(size_t)1;   // keeps 16-byte alignment
     if (int e = need_gwork(l.group_stride * groups)) return e;
