@@ -785,12 +785,26 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
     const double* sp = sb + TR * LD;
     const int* sc = s_c + slot * (TR + 1);
     // ---- G += Aop^T Bop (rows k0 .. k0+KC-1: A from tile row i-1, B from tile row i) ----
+    if constexpr (NT == 8) {
+      // 2 x 2 tiles per warp: two A and two B fragments feed four tensor instructions
+      const int m2 = 2 * (w & 3), n2 = 2 * (w >> 2);
 #pragma unroll
-    for (int kk = 0; kk < KC / 4; kk++) {
-      const double a = so[(4 * kk + q) * LD + 8 * mt + g];
+      for (int kk = 0; kk < KC / 4; kk++) {
+        const double a0 = so[(4 * kk + q) * LD + 8 * m2 + g], a1 = so[(4 * kk + q) * LD + 8 * (m2 + 1) + g];
+        const double b0 = sb[(4 * kk + q + 1) * LD + 8 * n2 + g], b1 = sb[(4 * kk + q + 1) * LD + 8 * (n2 + 1) + g];
+        dmma(acc[0][0], acc[0][1], a0, b0);
+        dmma(acc[1][0], acc[1][1], a0, b1);
+        dmma(acc[2][0], acc[2][1], a1, b0);
+        dmma(acc[3][0], acc[3][1], a1, b1);
+      }
+    } else {
 #pragma unroll
-      for (int n = 0; n < NH; n++)
-        dmma(acc[n][0], acc[n][1], a, sb[(4 * kk + q + 1) * LD + 8 * (nh * NH + n) + g]);
+      for (int kk = 0; kk < KC / 4; kk++) {
+        const double a = so[(4 * kk + q) * LD + 8 * mt + g];
+#pragma unroll
+        for (int n = 0; n < NH; n++)
+          dmma(acc[n][0], acc[n][1], a, sb[(4 * kk + q + 1) * LD + 8 * (nh * NH + n) + g]);
+      }
     }
     // ---- posterior rows into the evidence-indexed tables ----
     {
@@ -811,8 +825,10 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
   double* outG = partG + (long long)blockIdx.x * SP * SP;
 #pragma unroll
   for (int n = 0; n < NH; n++) {
-    outG[(8 * mt + g) * SP + 8 * (nh * NH + n) + 2 * q] = acc[n][0];
-    outG[(8 * mt + g) * SP + 8 * (nh * NH + n) + 2 * q + 1] = acc[n][1];
+    int mi = mt, ni = nh * NH + n;
+    if (NT == 8) { mi = 2 * (w & 3) + (n >> 1); ni = 2 * (w >> 2) + (n & 1); }
+    outG[(8 * mi + g) * SP + 8 * ni + 2 * q] = acc[n][0];
+    outG[(8 * mi + g) * SP + 8 * ni + 2 * q + 1] = acc[n][1];
   }
   double* outC = partC + (long long)blockIdx.x * tab;
   for (int x = threadIdx.x; x < tab; x += NTH) {
