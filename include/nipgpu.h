@@ -172,6 +172,27 @@ int nipgpu_model_counts_offsets(const nipgpu_model* m, int64_t* off);
  * iteration) before the M-step. */
 int nipgpu_em_counts_device(nipgpu_model* m, double** counts_dev, int64_t* n_doubles);
 
+/* ---- several GPUs of one box ----------------------------------
+ * A group is the same model compiled once per device (nipgpu_model_create with different
+ * `device`).  The caller shards the series of a set over the members (one batch per member,
+ * any rule: sequences are independent given the parameters, src/nip.c:2182-2207).  Inference
+ * and the likelihood loop need no exchange: call nipgpu_infer on every member.  EM needs one:
+ *   nipgpu_group_em_estep  every member runs e_step over its batch, then ONE
+ *                          ncclAllReduce(sum, double) over [family counts | loglik | status]
+ *                          leaves the set-wide totals in every member's HBM accumulator; the 1.0
+ *                          pseudo-count (src/nip.c:2171-2172) enters once; counts / loglik /
+ *                          status as in nipgpu_em_estep, reported from member 0
+ *   nipgpu_group_em_mstep  m_step (src/nip.c:2010-2071) redundantly on every member, so the
+ *                          parameters never leave HBM
+ * A group of one member does no collective and does not need NCCL (bound at run time). */
+typedef struct nipgpu_group nipgpu_group;
+int nipgpu_group_create(nipgpu_model** models, int n, nipgpu_group** out);
+void nipgpu_group_destroy(nipgpu_group* g);
+int nipgpu_group_size(const nipgpu_group* g);
+int nipgpu_group_em_estep(nipgpu_group* g, nipgpu_batch** batches, const uint8_t* use_evidence,
+                          int add_pseudocount, double* counts, double* loglik, int* status);
+int nipgpu_group_em_mstep(nipgpu_group* g, const double* counts);
+
 /* M-step on the device from the accumulator (m_step, src/nip.c:2010-2071):
  * normalise_cpd, reset cliques to 1, multiply CPTs into family cliques,
  * priors <- normalised counts of parentless variables.  When `counts` is not
@@ -205,6 +226,22 @@ int nipgpu_slice_get_clique(nipgpu_model* m, int32_t clique, double* out);
 /* D2H copy of a sepset's current potential (sepset->new), sepsets numbered as in the description */
 int nipgpu_slice_get_sepset(nipgpu_model* m, int32_t sepset, double* out);
 
+/* make_consistent (src/nip.c:1600-1617) on the state the CALLER holds, whatever put it there
+ * (reset_model/use_priors/nip_enter_evidence, but also finish_timeslice_message_pass,
+ * src/nip.c:1069-1098, as generate_data does, :2433-2461): collect towards cliques[0], then
+ * distribute, every message pass as nip_message_pass (src/nipjointree.c:676-709: swap old/new,
+ * new = marginal of the sender, receiver *= new/old with x/0 -> 0).
+ *   clique_tables   every clique->p, concatenated as in the description (clique_tab_off)
+ *   sepset_tables   every sepset->new, concatenated in description order (may be NULL when the
+ *                   model has no sepsets)
+ *   clique_out      consistent clique->p, same layout (may alias clique_tables)
+ *   sepset_new_out  sepset->new after the call (the distribute messages), or NULL
+ *   sepset_old_out  sepset->old after the call (the collect messages), or NULL
+ * One host-to-device copy, one kernel, one device-to-host copy per call (a captured CUDA graph
+ * on persistent pinned/device buffers: no allocation after the first call). */
+int nipgpu_slice_propagate(nipgpu_model* m, const double* clique_tables, const double* sepset_tables,
+                           double* clique_out, double* sepset_new_out, double* sepset_old_out);
+
 /* Ancestral sampling of n_series series of `length` slices from the model's current parameters
  * (generate_data, src/nip.c:2325-2478, one series at a time with several make_consistent per
  * variable per slice).  out: host [n_series][length][n_vars] state indices, variables in the
@@ -230,6 +267,10 @@ int nipgpu_jt_trace(nipgpu_model* m, uint64_t* out, int cap_records, int reset);
  * stream of DMMA m8n8k4 instructions, the same with scalar DFMA, and a plain
  * device-to-device copy.  Used by bench.py as roofline denominators. */
 int nipgpu_probe_peaks(int device, double* dmma_tflops, double* dfma_tflops, double* copy_gbs);
+/* micro-probe behind the chain kernels' schedule: `chains` (1, 2, 4 or 8) independent
+ * accumulator chains of DMMA m8n8k4 per warp, warps_per_block x blocks warps; reports the clocks
+ * one warp spends per DMMA (issue interval when chains hide the latency, else the latency). */
+int nipgpu_probe_dmma_chain(int chains, int warps_per_block, int blocks, double* clocks_per_dmma);
 /* the CUDA stream (cudaStream_t) all work of this model is enqueued on */
 void* nipgpu_model_stream(nipgpu_model* m);
 

@@ -30,6 +30,8 @@ ABI_SYMBOLS = [
     "nipgpu_slice_use_priors", "nipgpu_slice_enter_prior", "nipgpu_slice_enter_evidence", "nipgpu_slice_get_sepset", "nipgpu_slice_make_consistent",
     "nipgpu_slice_mass", "nipgpu_slice_marginal", "nipgpu_slice_get_clique",
     "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_jt_trace", "nipgpu_sample", "nipgpu_model_stream", "nipgpu_probe_peaks",
+    "nipgpu_probe_dmma_chain", "nipgpu_slice_propagate", "nipgpu_group_create", "nipgpu_group_destroy",
+    "nipgpu_group_size", "nipgpu_group_em_estep", "nipgpu_group_em_mstep",
 ]
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -88,6 +90,14 @@ def load_library(path=LIB_PATH):
     L.nipgpu_jt_trace.argtypes = [_vp, _vp, _i, _i]
     L.nipgpu_sample.argtypes = [_vp, _i, _i, C.c_uint64, _vp]
     L.nipgpu_probe_peaks.argtypes = [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]
+    L.nipgpu_probe_dmma_chain.argtypes = [_i, _i, _i, C.POINTER(_d)]
+    L.nipgpu_slice_propagate.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
+    L.nipgpu_group_create.argtypes = [_vp, _i, C.POINTER(_vp)]
+    L.nipgpu_group_destroy.argtypes = [_vp]
+    L.nipgpu_group_destroy.restype = None
+    L.nipgpu_group_size.argtypes = [_vp]
+    L.nipgpu_group_em_estep.argtypes = [_vp, _vp, _vp, _i, _vp, C.POINTER(_d), C.POINTER(_i)]
+    L.nipgpu_group_em_mstep.argtypes = [_vp, _vp]
     L.nipgpu_model_stream.restype = _vp
     L.nipgpu_model_stream.argtypes = [_vp]
     _lib = L
@@ -215,10 +225,53 @@ class Model:
         _check(self.L.nipgpu_slice_marginal(self.h, int(var), _p(out)))
         return out
 
+    def slice_propagate(self, tables, sepsets):
+        """make_consistent on the caller's tree state: (tables, sepset new) -> (tables, new, old)"""
+        t = np.ascontiguousarray(tables, dtype=np.float64)
+        sp = np.ascontiguousarray(sepsets, dtype=np.float64)
+        out, new, old = np.zeros_like(t), np.zeros_like(sp), np.zeros_like(sp)
+        _check(self.L.nipgpu_slice_propagate(self.h, _p(t), _p(sp) if sp.size else None, _p(out),
+                                             _p(new) if sp.size else None, _p(old) if sp.size else None))
+        return out, new, old
+
     def slice_clique(self, c):
         out = np.zeros(int(self.fm.clique_tab_off[c + 1] - self.fm.clique_tab_off[c]))
         _check(self.L.nipgpu_slice_get_clique(self.h, int(c), _p(out)))
         return out
+
+
+class Group:
+    """nipgpu_group handle: the same model on several devices of one box, one batch (shard) per
+    member; EM sums the expected counts with one ncclAllReduce per iteration."""
+
+    def __init__(self, models):
+        self.L = load_library()
+        self.models = list(models)
+        arr = (_vp * len(self.models))(*[m.h for m in self.models])
+        h = _vp()
+        _check(self.L.nipgpu_group_create(arr, len(self.models), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nipgpu_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def estep(self, batches, use_evidence=None, add_pseudocount=True, want_counts=True):
+        n = self.models[0].counts_size()
+        counts = np.zeros(n) if want_counts else None
+        ll, st = _d(), _i()
+        arr = (_vp * len(batches))(*[b.h for b in batches])
+        m = _mask(use_evidence, self.models[0].fm.n_vars)
+        _check(self.L.nipgpu_group_em_estep(self.h, arr, _p(m), int(add_pseudocount), _p(counts),
+                                            C.byref(ll), C.byref(st)))
+        return counts, ll.value, st.value
+
+    def mstep(self, counts=None):
+        c = None if counts is None else np.ascontiguousarray(counts, dtype=np.float64)
+        _check(self.L.nipgpu_group_em_mstep(self.h, _p(c)))
 
 
 class Batch:

@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
     "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
 ]
-SOURCES = ["api.cu", "jtree.cu", "chain.cu", "dense.cu", "params.cu", "probe.cu", "model.cpp"]
+SOURCES = ["api.cu", "jtree.cu", "chain.cu", "dense.cu", "params.cu", "probe.cu", "group.cu", "model.cpp"]
 
 
 def _nvcc():
@@ -54,7 +54,7 @@ def build_device_library(force=False, verbose=False, extra_flags=()):
             if verbose and (r.stdout or r.stderr):
                 print(r.stdout, r.stderr)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -72,7 +72,7 @@ def build_host_backend(force=False, verbose=False):
     if not force and not _stale(HOST_LIB, src + [LIB]):
         return HOST_LIB
     cmd = ["gcc", "-std=gnu99", "-O2", "-fPIC", "-shared", "-Wall", "-Wno-unused",
-           "-include", os.path.join(ROOT, "oracle", "refbuild", "nip_errcodes_shim.h"),
+           "-include", os.path.join(PKG, "host", "nip_errcodes_shim.h"),
            "-I" + REF_SRC, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(PKG, "host"),
            "-o", HOST_LIB, *src, "-L" + PKG, "-lnipgpu", "-Wl,-rpath,$ORIGIN", "-Wl,-Bsymbolic-functions", "-lm"]
     if verbose:

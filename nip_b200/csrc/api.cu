@@ -9,7 +9,7 @@
 namespace nipgpu {
 
 static thread_local std::string g_error;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
 
 namespace {
@@ -431,6 +431,9 @@ void nipgpu_model_destroy(nipgpu_model* m) {
   cudaFree(m->d_orig); cudaFree(m->d_prior); cudaFree(m->d_base0); cudaFree(m->d_base1);
   cudaFree(m->d_R1); cudaFree(m->d_m10); cudaFree(m->d_counts); cudaFree(m->d_acc); cudaFree(m->d_gwork);
   cudaFree(m->d_slice_start); cudaFree(m->d_slice_tab); cudaFree(m->d_slice_msg);
+  if (m->prop_graph) cudaGraphExecDestroy(m->prop_graph);
+  cudaFree(m->d_prop); cudaFree(m->d_vec);
+  if (m->h_prop) cudaFreeHost(m->h_prop);
   chain_free(m->chain);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -580,8 +583,12 @@ int nipgpu_em_counts_device(nipgpu_model* m, double** counts_dev, int64_t* n_dou
   return NIPGPU_OK;
 }
 
-int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int add_pseudocount,
-                    double* counts, double* loglik, int* status) {
+}  // extern "C"
+
+namespace nipgpu {
+// E-step of one model on its own stream, nothing awaited: when this returns the kernels are
+// enqueued and m->d_counts (+ loglik, status) will hold this device's share.
+int estep_enqueue(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int add_pseudocount) {
   if (!m || !b || b->m != m) return fail(NIPGPU_EINVAL, "model/batch mismatch");
   NIPGPU_CUDA(cudaSetDevice(m->device));
   const HostModel& hm = m->hm;
@@ -599,18 +606,7 @@ int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidenc
     x.d_base0 = m->d_base0; x.d_base1 = m->d_base1; x.tab_off = &m->tab_off; x.d_ipool = m->d_ipool;
     x.pseudo = add_pseudocount ? 1.0 : 0.0; x.d_counts = m->d_counts; x.sm_count = m->sm_count;
     const int rc = chain_estep(hm, m->chain, b->chain, plan, x, m->stream, m->ev0, m->ev1);
-    if (rc == NIPGPU_OK) {
-      double tail[2] = {0, 0};
-      NIPGPU_CUDA(cudaMemcpyAsync(tail, m->d_counts + n, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-      if (counts)
-        NIPGPU_CUDA(cudaMemcpyAsync(counts, m->d_counts, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-      NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
-      float ms = 0;
-      if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 7; }
-      if (loglik) *loglik = tail[0];
-      if (status) *status = tail[1] != 0 ? NIPGPU_EBADLUCK : 0;
-      return NIPGPU_OK;
-    }
+    if (rc == NIPGPU_OK) { m->last_kernel_n = 7; return NIPGPU_OK; }
     if (rc != NIPGPU_EUNSUPPORTED) return rc;
   }
   const int* obs_proj = nullptr;
@@ -631,16 +627,33 @@ int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidenc
   NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
   if (int e = finish_estep(m->d_acc, l.slots, n, n, add_pseudocount ? 1.0 : 0.0, b->d_ll, b->d_status,
                            b->n_series, m->d_counts, m->stream)) return e;
+  m->last_kernel_n = 2;
+  return NIPGPU_OK;
+}
+
+// waits for the stream and brings the scalars (and, on request, the counts) home
+int estep_finish(nipgpu_model* m, double* counts, double* loglik, int* status) {
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  const long long n = m->hm.coff[m->hm.nv];
   double tail[2] = {0, 0};
   NIPGPU_CUDA(cudaMemcpyAsync(tail, m->d_counts + n, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   if (counts)
     NIPGPU_CUDA(cudaMemcpyAsync(counts, m->d_counts, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 2; }
+  if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) m->last_kernel_ms = ms;
   if (loglik) *loglik = tail[0];
   if (status) *status = tail[1] != 0 ? NIPGPU_EBADLUCK : 0;
   return NIPGPU_OK;
+}
+}  // namespace nipgpu
+
+extern "C" {
+
+int nipgpu_em_estep(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int add_pseudocount,
+                    double* counts, double* loglik, int* status) {
+  if (int e = estep_enqueue(m, b, use_evidence, add_pseudocount)) return e;
+  return estep_finish(m, counts, loglik, status);
 }
 
 int nipgpu_em_mstep(nipgpu_model* m, const double* counts) {
@@ -820,21 +833,80 @@ int nipgpu_slice_make_consistent(nipgpu_model* m) {
     if (int e = apply_vector(m->d_slice_start + m->tab_off[c], hm.csize[c], stride_of(c, v), hm.card[v],
                              m->d_prior + hm.prior_off[v], m->d_prior_flags + k, st)) return e;
   }
-  double* d_vec = nullptr;
-  NIPGPU_CUDA(cudaMalloc((void**)&d_vec, (size_t)hm.card_max * sizeof(double)));
+  // all evidence vectors in one upload (persistent buffer, one slot of card_max per variable)
+  if (!m->d_vec) NIPGPU_CUDA(cudaMalloc((void**)&m->d_vec, (size_t)hm.nv * hm.card_max * sizeof(double)));
+  m->lik_stage.assign((size_t)hm.nv * hm.card_max, 1.0);
+  bool any = false;
   for (int v = 0; v < hm.nv; v++) {
     bool all_one = true;
     for (double x : m->lik[v]) all_one = all_one && x == 1.0;
     if (all_one) continue;
-    const int c = hm.family[v];
-    NIPGPU_CUDA(cudaMemcpyAsync(d_vec, m->lik[v].data(), (size_t)hm.card[v] * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (int e = apply_vector(m->d_slice_start + m->tab_off[c], hm.csize[c], stride_of(c, v), hm.card[v], d_vec, nullptr, st)) { cudaFree(d_vec); return e; }
-    NIPGPU_CUDA(cudaStreamSynchronize(st));
+    any = true;
+    std::copy(m->lik[v].begin(), m->lik[v].end(), m->lik_stage.begin() + (size_t)v * hm.card_max);
   }
-  cudaFree(d_vec);
+  if (any) {
+    NIPGPU_CUDA(cudaMemcpyAsync(m->d_vec, m->lik_stage.data(), m->lik_stage.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int v = 0; v < hm.nv; v++) {
+      bool all_one = true;
+      for (double x : m->lik[v]) all_one = all_one && x == 1.0;
+      if (all_one) continue;
+      const int c = hm.family[v];
+      if (int e = apply_vector(m->d_slice_start + m->tab_off[c], hm.csize[c], stride_of(c, v), hm.card[v],
+                               m->d_vec + (size_t)v * hm.card_max, nullptr, st)) return e;
+    }
+  }
   if (int e = jt_slice(m->prog, m->launch, m->d_slice_start, m->d_slice_tab, m->d_slice_msg, st)) return e;
   NIPGPU_CUDA(cudaStreamSynchronize(st));
   m->slice_consistent = true;
+  return NIPGPU_OK;
+}
+
+// make_consistent (src/nip.c:1600-1617) as one device transaction on the caller's own tree
+// state.  First call: buffers + a captured graph; every call: memcpy into the pinned block, one
+// graph launch (H2D, k_jt_propagate, D2H), one sync, memcpy out.
+int nipgpu_slice_propagate(nipgpu_model* m, const double* clique_tables, const double* sepset_tables,
+                           double* clique_out, double* sepset_new_out, double* sepset_old_out) {
+  if (!m || !clique_tables || !clique_out) return fail(NIPGPU_EINVAL, "bad arguments");
+  const size_t T = (size_t)m->prog.tab_total, S = (size_t)m->hm.msg_total;
+  if (S > 0 && !sepset_tables) return fail(NIPGPU_EINVAL, "bad arguments");
+  NIPGPU_CUDA(cudaSetDevice(m->device));
+  const size_t n_in = T + S, n_out = T + 2 * S;
+  cudaStream_t st = m->stream;
+  if (!m->h_prop) {
+    NIPGPU_CUDA(cudaMallocHost((void**)&m->h_prop, (n_in + n_out) * sizeof(double)));
+    NIPGPU_CUDA(cudaMalloc((void**)&m->d_prop, (n_in + n_out) * sizeof(double)));
+  }
+  memcpy(m->h_prop, clique_tables, T * sizeof(double));
+  if (S) memcpy(m->h_prop + T, sepset_tables, S * sizeof(double));
+  auto enqueue = [&]() -> int {
+    NIPGPU_CUDA(cudaMemcpyAsync(m->d_prop, m->h_prop, n_in * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int e = jt_propagate(m->prog, m->launch, m->d_prop, m->d_prop + n_in, st)) return e;
+    NIPGPU_CUDA(cudaMemcpyAsync(m->h_prop + n_in, m->d_prop + n_in, n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return NIPGPU_OK;
+  };
+  if (m->launch.mode == JT_MODE_GRID) {   // cooperative launches are not captured
+    if (int e = enqueue()) return e;
+  } else {
+    if (!m->prop_graph) {
+      cudaGraph_t g = nullptr;
+      NIPGPU_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int e = enqueue();
+      const cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (e) { if (g) cudaGraphDestroy(g); return e; }
+      NIPGPU_CUDA(ce);
+      const cudaError_t ie = cudaGraphInstantiate(&m->prop_graph, g, 0);
+      cudaGraphDestroy(g);
+      NIPGPU_CUDA(ie);
+    } else {
+      g_launches++;   // the kernel inside the graph
+    }
+    NIPGPU_CUDA(cudaGraphLaunch(m->prop_graph, st));
+  }
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  const double* o = m->h_prop + n_in;
+  memcpy(clique_out, o, T * sizeof(double));
+  if (S && sepset_new_out) memcpy(sepset_new_out, o + T, S * sizeof(double));
+  if (S && sepset_old_out) memcpy(sepset_old_out, o + T + S, S * sizeof(double));
   return NIPGPU_OK;
 }
 
@@ -898,8 +970,8 @@ int nipgpu_jt_trace(nipgpu_model* m, uint64_t* out, int cap_records, int reset) 
 }
 
 int64_t nipgpu_launch_count(int reset) {
-  const int64_t n = g_launches;
-  if (reset) g_launches = 0;
+  const int64_t n = g_launches.load();
+  if (reset) g_launches.store(0);
   return n;
 }
 

@@ -48,8 +48,14 @@ struct nipgpu_model {
   // ---- single-slice state (stateful API) ----
   std::vector<std::vector<double>> lik;  // host mirror of variable->likelihood
   std::vector<char> prior_entered;
+  std::vector<double> lik_stage;         // [nv][card_max] staging of all evidence vectors
   double *d_slice_start = nullptr, *d_slice_tab = nullptr, *d_slice_msg = nullptr;
   bool slice_consistent = false;
+  // nipgpu_slice_propagate: one pinned block [in | out], its device twin, and the captured
+  // H2D -> kernel -> D2H graph (no allocation, one launch, one sync per call)
+  double *h_prop = nullptr, *d_prop = nullptr;
+  cudaGraphExec_t prop_graph = nullptr;
+  double *d_vec = nullptr;   // card_max doubles: evidence vector of the stateful API
 };
 
 struct nipgpu_batch {
@@ -72,3 +78,10 @@ struct nipgpu_batch {
   double* d_joint = nullptr;         // [rows][SP] posterior of the joint interface state (composite interfaces)
   nipgpu::ChainBatch chain;
 };
+
+namespace nipgpu {
+// the two halves of nipgpu_em_estep (api.cu); the multi-device group (group.cu) puts one
+// all-reduce between them
+int estep_enqueue(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int add_pseudocount);
+int estep_finish(nipgpu_model* m, double* counts, double* loglik, int* status);
+}  // namespace nipgpu

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -12,7 +13,7 @@
 namespace nipgpu {
 
 void set_error(const std::string& msg);
-extern int64_t g_launches;  // kernels launched by this library (nipgpu_launch_count)
+extern std::atomic<int64_t> g_launches;  // kernels launched by this library (nipgpu_launch_count)
 
 #define NIPGPU_CUDA(call)                                                              \
   do {                                                                                 \

@@ -778,6 +778,39 @@ __global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_slic
   for (int i = tm.tid(); i < P.msg_total; i += tm.size()) out_msgs[i] = w.msg[i];
 }
 
+// make_consistent (src/nip.c:1600-1617) on WHATEVER state the caller holds: `in` = every
+// clique's current table followed by every sepset's current potential (`new`), exactly what
+// nip_collect_evidence / nip_distribute_evidence start from.  Each message pass is
+// nip_message_pass (src/nipjointree.c:676-709): swap old/new, new = marginal of the sender,
+// receiver *= new/old (x/0 -> 0).  `out` = consistent tables, then every sepset's `new` (the
+// distribute message) and `old` (the collect message) — one contiguous block, so the host needs
+// one copy in and one copy out per call.
+template <class Team>
+__global__ void __launch_bounds__(Team::kMaxThreads, Team::kMinBlocks) k_jt_propagate(DProgram P, TeamMem M, const double* in, double* out) {
+  extern __shared__ double smem[];
+  __shared__ double red[40];
+  Team tm(red, M.part, M.scratch, smem);
+  attach_trace(tm, M);
+  Work w = carve(P, M.gwork ? M.gwork : smem);
+  load_tables(tm, P, w, in, false);
+  for (int i = tm.tid(); i < P.msg_total; i += tm.size()) w.msg[i] = in[P.tab_total + i];
+  tm.sync();
+  for (int i = 0; i < P.n_collect; i++) {   // collect: old = what the sepset held, new = marginal
+    const DMsg m = P.collect[i];
+    op_marg(tm, P, w.tab, m.proj_src, w.tmp);
+    op_absorb_ratio(tm, P, w, m.proj_dst, w.tmp, w.msg + m.slot);
+    for (int k = tm.tid(); k < m.size; k += tm.size()) w.msg[m.slot + k] = w.tmp[k];
+    tm.sync();
+  }
+  double* out_new = out + P.tab_total;
+  double* out_old = out_new + P.msg_total;
+  for (int i = tm.tid(); i < P.msg_total; i += tm.size()) out_old[i] = w.msg[i];
+  tm.sync();
+  do_distribute(tm, P, w, P.distribute, P.n_distribute);
+  for (int i = tm.tid(); i < P.tab_total; i += tm.size()) out[i] = w.tab[i];
+  for (int i = tm.tid(); i < P.msg_total; i += tm.size()) out_new[i] = w.msg[i];
+}
+
 // single-slice API: mass = sum of cliques - sum of sepsets (nip_probability_mass,
 // src/nipjointree.c:1156-1188) of the consistent tables left by k_jt_slice
 __global__ void k_jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out) {
@@ -874,6 +907,7 @@ int jt_grid_ctas(int threads, int sm_count, size_t* smem_bytes) {
   probe(k_jt_likelihood<GridTeam>);
   probe(k_jt_calibrate<GridTeam>);
   probe(k_jt_slice<GridTeam>);
+  probe(k_jt_propagate<GridTeam>);
   return sm_count * per_sm;
 }
 
@@ -1006,6 +1040,12 @@ int jt_slice(const DProgram& p, const JtLaunch& l, const double* start, double* 
   return launch_team(k_jt_slice<CtaTeam>, k_jt_slice<CtaTeam>, k_jt_slice<GridTeam>, one,
                      one.mode == JT_MODE_GRID ? one.grid : 1, st, p, team_mem(p, one), start, out_tables,
                      out_msgs);
+}
+
+int jt_propagate(const DProgram& p, const JtLaunch& l, const double* in, double* out, cudaStream_t st) {
+  const JtLaunch one = single_team(l, p);
+  return launch_team(k_jt_propagate<CtaTeam>, k_jt_propagate<CtaTeam>, k_jt_propagate<GridTeam>, one,
+                     one.mode == JT_MODE_GRID ? one.grid : 1, st, p, team_mem(p, one), in, out);
 }
 
 }  // namespace nipgpu

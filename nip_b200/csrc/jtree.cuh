@@ -111,6 +111,9 @@ int jt_calibrate(const DProgram& p, const JtLaunch& l, double* R1, double* m1_0,
 int jt_slice(const DProgram& p, const JtLaunch& l, const double* start_tables, double* out_tables,
              double* out_msgs, cudaStream_t st);
 
+// make_consistent on the caller's own state: in = [tables | sepsets], out = [tables | sepset new | sepset old]
+int jt_propagate(const DProgram& p, const JtLaunch& l, const double* in, double* out, cudaStream_t st);
+
 // reductions of the single-slice API on the consistent tables (device side)
 int jt_mass(const double* tables, int n_tab, const double* msgs, int n_msg, double* out, cudaStream_t st);
 int jt_marginal(const DProgram& p, const double* tables, int proj, double* out, cudaStream_t st);

@@ -124,6 +124,8 @@ int nip_gpu_read_timeseries_bin(nip_model model, const char* filename, time_seri
     return 0;
   }
   *results = set;
+#ifdef NIP_GPU_WRAP_SETS   /* only where free_timeseries() is the wrapper that unregisters the set */
   nip_gpu_register_set(set, n);
+#endif
   return n;
 }

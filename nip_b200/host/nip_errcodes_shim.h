@@ -1,5 +1,5 @@
-/* TEST INFRASTRUCTURE — force-included (gcc -include) when compiling the
- * reference sources where they lie under /root/reference/src.
+/* Force-included (gcc -include) wherever the reference's headers are compiled: the host glue
+ * of this package and the reference sources themselves (oracle/Makefile).
  *
  * HEAD's niperrorhandler.h only defines NIP_NO_ERROR (src/niperrorhandler.h:32)
  * although nip.c / nipparsers.c / util/ still use the NIP_ERROR_* names

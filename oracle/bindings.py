@@ -210,6 +210,9 @@ class RefLib:
         L.refh_get_prior.argtypes = [_vp, _i, _vp]
         L.refh_enter_evidence.argtypes = [_vp, _i, _vp]
         L.refh_marginal.argtypes = [_vp, _i, _vp]
+        L.refh_next_slice.argtypes = [_vp]
+        L.refh_sepset_size.argtypes = [_vp, _i]
+        L.refh_get_sepset.argtypes = [_vp, _i, _i, _vp]
         L.refh_time_infer.restype = _d
         L.refh_time_infer.argtypes = [_vp, _i, _i, _vp, _i, _i]
         L.refh_time_em_iteration.restype = _d
@@ -328,6 +331,24 @@ class RefModel:
         out = np.zeros(int(self._cards()[var]))
         self.lib.L.refh_marginal(self.h, int(var), _p(out))
         return out
+
+    def next_slice(self):
+        """generate_data's slice hand-over: alpha out, reset, priors with history, alpha in"""
+        if self.lib.L.refh_next_slice(self.h):
+            raise RuntimeError("reference timeslice message pass failed")
+
+    def sepset(self, s, new=True):
+        out = np.zeros(self.lib.L.refh_sepset_size(self.h, int(s)))
+        self.lib.L.refh_get_sepset(self.h, int(s), int(new), _p(out))
+        return out
+
+    def tree_state(self):
+        """every clique->p, then every sepset's new and old potential, concatenated"""
+        fm = self.export()
+        parts = [self.clique(c, original=False) for c in range(fm.n_cliques)]
+        parts += [self.sepset(s, True) for s in range(fm.n_sepsets)]
+        parts += [self.sepset(s, False) for s in range(fm.n_sepsets)]
+        return np.concatenate(parts) if parts else np.zeros(0)
 
     def time_infer(self, ts_list, query, want_ll=True, nproc=1):
         arr = (C.c_void_p * len(ts_list))(*ts_list)

@@ -254,6 +254,44 @@ int refh_marginal(void* m, int var, double* out) {
   return NIP_NO_ERROR;
 }
 
+/* generate_data's hand-over between two slices (src/nip.c:2433-2441, 2464-2474): alpha out of
+ * the consistent tree, forget the evidence, priors with history, alpha into in_clique->p.  The
+ * next make_consistent() has to start from THAT clique state. */
+int refh_next_slice(void* m) {
+  nip_model model = (nip_model)m;
+  int n = model->outgoing_interface_size, i, e;
+  int* card = (int*)calloc((size_t)(n > 0 ? n : 1), sizeof(int));
+  nip_potential alpha;
+  for (i = 0; i < n; i++) card[i] = NIP_CARDINALITY(model->outgoing_interface[i]);
+  alpha = nip_new_potential(card, n, NULL);
+  free(card);
+  e = start_timeslice_message_pass(model, FORWARD, alpha);
+  reset_model(model);
+  use_priors(model, NIP_HAD_A_PREVIOUS_TIMESLICE);
+  if (e == NIP_NO_ERROR) e = finish_timeslice_message_pass(model, FORWARD, alpha, NULL);
+  nip_free_potential(alpha);
+  return e;
+}
+
+/* sepset potentials in the description's order; which: 0 = old, 1 = new */
+int refh_sepset_size(void* m, int s) {
+  int ns = 0, n = -1;
+  nip_sepset* seps = nipgpu_model_sepsets((nip_model)m, &ns);
+  if (seps && s < ns) n = seps[s]->new->size_of_data;
+  free(seps);
+  return n;
+}
+
+void refh_get_sepset(void* m, int s, int which, double* out) {
+  int ns = 0;
+  nip_sepset* seps = nipgpu_model_sepsets((nip_model)m, &ns);
+  if (seps && s < ns) {
+    nip_potential p = which ? seps[s]->new : seps[s]->old;
+    memcpy(out, p->data, sizeof(double) * (size_t)p->size_of_data);
+  }
+  free(seps);
+}
+
 /* ---- CPU baseline timing ------------------------------------------------
  * Smoothing over a set of series, optionally sharded over `nproc` forked
  * workers (the reference is single-threaded with global state, so processes

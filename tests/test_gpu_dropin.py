@@ -116,22 +116,108 @@ def test_em_learn_dropin(libs, tmp_path):
     gpu.nip_gpu_release(m_gpu.h)
 
 
-def test_make_consistent_dropin(libs, tmp_path):
+def _demo1_like_net():
+    """general tree: three cliques, in_clique != out_clique, a parentless non-interface variable"""
+    rng = np.random.default_rng(5)
+    t = lambda *shape: rng.random(shape) + 0.05
+    return net_text_generic(
+        [("D1", 2, None), ("C1", 3, None), ("B1", 3, None), ("A1", 4, None), ("A0", 4, "A1")],
+        [("D1", [], t(1, 2)), ("C1", ["A1", "D1"], t(8, 3)), ("B1", ["C1"], t(3, 3)),
+         ("A1", ["A0"], t(4, 4)), ("A0", [], t(1, 4))])
+
+
+@pytest.mark.parametrize("memo", ["1", "0"])
+def test_make_consistent_dropin(libs, tmp_path, memo, monkeypatch):
+    """make_consistent() must work on WHATEVER tree state the host holds (src/nip.c:1600-1617),
+    not on a reconstruction: evidence entered on an already consistent tree, and the
+    inter-slice message multiplied into in_clique->p by finish_timeslice_message_pass
+    (generate_data, src/nip.c:2433-2461).  Compared: every clique->p, both potentials of every
+    sepset, the mass and every marginal, after every step, with and without the memo."""
     ref, gpu = libs
-    h = HmmSpec(6, 4, seed=2)
-    p = tmp_path / "m.net"
+    monkeypatch.setenv("NIP_GPU_SLICE_MEMO", memo)
+    nets = {"hmm": HmmSpec(6, 4, seed=2).net_text(), "tree": _demo1_like_net()}
+    for name, text in nets.items():
+        p = tmp_path / (name + ".net")
+        p.write_text(text)
+        m_ref, m_gpu = ref.parse(p), ref.parse(p)
+        cards = m_ref._cards()
+        rng = np.random.default_rng(11)
+
+        def both(f):
+            f(m_ref)
+            f(m_gpu)
+
+        def check(what):
+            m_ref.make_consistent()
+            gpu.make_consistent(m_gpu.h)
+            assert_close(m_gpu.tree_state(), m_ref.tree_state(), "%s: %s: cliques and sepsets" % (name, what))
+            assert_close(m_gpu.mass(), m_ref.mass(), "%s: %s: model_prob_mass" % (name, what))
+            for v in range(len(cards)):
+                assert_close(m_gpu.marginal(v), m_ref.marginal(v), "%s: %s: get_probability(%d)" % (name, what, v))
+
+        for rep in range(2):                      # the second round is served from the memo when it is on
+            both(lambda m: (m.reset(), m.use_priors(0)))
+            check("priors only")
+            lik0 = np.array([0.1, 0.7, 0.0, 0.2, 0.5, 0.3])[:cards[0]]
+            both(lambda m: m.enter_evidence(0, lik0))
+            check("soft evidence")
+            hard = np.zeros(cards[1]); hard[1] = 1.0
+            both(lambda m: m.enter_evidence(1, hard))   # on the consistent tree: needs new/old division
+            check("second evidence on a consistent tree")
+            for t in range(3):                       # three slices of generate_data's loop
+                both(lambda m: m.next_slice())
+                check("slice %d after the inter-slice message" % (t + 1))
+                e = rng.random(cards[0]) + 0.01
+                both(lambda m: m.enter_evidence(0, e))
+                check("slice %d with evidence" % (t + 1))
+        gpu.nip_gpu_release(m_gpu.h)
+
+
+def test_inference_after_training_is_not_served_stale(libs, tmp_path):
+    """infer -> em_learn -> infer on a registered set: the second answer must come from the
+    trained parameters (the parked pass of the first call is stale)"""
+    ref, gpu = libs
+    gpu.nip_gpu_register_set.argtypes = [vp, i32]
+    gpu.nip_gpu_forget_set.argtypes = [vp]
+    h = HmmSpec(5, 3, seed=6)
+    p = tmp_path / "s.net"
     p.write_text(h.net_text())
-    m_ref, m_gpu = ref.parse(p), ref.parse(p)
-    for m in (m_ref, m_gpu):
-        m.reset()
-        m.use_priors(0)
-        m.enter_evidence(0, [0.1, 0.7, 0.0, 0.2])
-    m_ref.make_consistent()
-    gpu.make_consistent(m_gpu.h)
-    assert_close(m_gpu.mass(), m_ref.mass(), "model_prob_mass on the mirrored tree")
-    for v in range(3):
-        assert_close(m_gpu.marginal(v), m_ref.marginal(v), "get_probability on the mirrored tree")
-    gpu.nip_gpu_release(m_gpu.h)
+    model = ref.parse(p)
+    data = h.sample(6, 14, seed=2)
+    ts = [model.timeseries(h.obs_vars, s) for s in data]
+    arr = (vp * len(ts))(*ts)
+    q = _vars(ref, model, [1])
+    gpu.nip_gpu_register_set(arr, len(ts))
+    before = _flat(ref, gpu.forward_backward_inference(ts[0], q, 1, None), 5)
+    ref.L.refh_seed(5)
+    lc = ref.L.refh_new_double_list()
+    assert gpu.em_learn(arr, len(ts), 1.0, lc) == 0
+    ref.L.refh_free_double_list(lc)
+    after = _flat(ref, gpu.forward_backward_inference(ts[1], q, 1, None), 5)
+    want, _ = model.infer(ts[1], [1])               # the reference on the trained host model
+    assert_close(after, want, "series 1 after em_learn")
+    again = _flat(ref, gpu.forward_backward_inference(ts[0], q, 1, None), 5)
+    assert_close(again, model.infer(ts[0], [1])[0], "series 0 after em_learn")
+    assert np.abs(again - before).max() > 1e-3      # training did change the answer
+    gpu.nip_gpu_forget_set(arr)
+    gpu.nip_gpu_release(model.h)
+
+
+def test_set_with_reordered_columns_is_rejected(libs, tmp_path):
+    """series of one set must list their observed variables in the same order; anything else
+    would enter evidence on the wrong variable"""
+    ref, gpu = libs
+    gpu.nip_gpu_smooth_set.argtypes = [vp, i32, vp, i32, i32, vp, vp]
+    h = HmmSpec(4, 4, seed=1)
+    p = tmp_path / "r.net"
+    p.write_text(h.net_text())
+    model = ref.parse(p)
+    a = model.timeseries([0, 1], np.zeros((3, 2), dtype=np.int32))
+    b = model.timeseries([1, 0], np.zeros((3, 2), dtype=np.int32))
+    arr = (vp * 2)(a, b)
+    res = (vp * 2)()
+    assert gpu.nip_gpu_smooth_set(arr, 2, _vars(ref, model, [1]), 1, 0, res, None) == 3   # NIP_ERROR_INVALID_ARGUMENT
+    gpu.nip_gpu_release(model.h)
 
 
 def test_transparent_batching_of_per_series_calls(libs, tmp_path):
@@ -203,7 +289,7 @@ def test_unchanged_cli_tools_on_the_gpu_backend(gpu_lib, tmp_path):
     h = HmmSpec(12, 5, seed=3)
     net = tmp_path / "h.net"
     net.write_text(h.net_text())
-    _run("nipsample_cpu", net, 40, 15, tmp_path / "all.txt")
+    _run("sample_driver_cpu", net, 40, 15, 11, tmp_path / "all.txt")
     _observed_only(tmp_path / "all.txt", tmp_path / "m1.txt", "M1")
     out_cpu = _run("nipinference_cpu", net, tmp_path / "m1.txt", "P1", tmp_path / "post_cpu.txt")
     out_gpu = _run("nipinference_gpu", net, tmp_path / "m1.txt", "P1", tmp_path / "post_gpu.txt")
@@ -222,6 +308,91 @@ def test_unchanged_cli_tools_on_the_gpu_backend(gpu_lib, tmp_path):
     # write_model keeps six decimals (a probability below 5e-7 reloads as 0), so only a loose check
     if np.isfinite(scored):
         assert abs(final - scored) <= 0.2
+
+
+def _table(text):
+    """all numbers of a tool's stdout, line by line"""
+    rows = []
+    for line in text.split("\n"):
+        vals = []
+        for tok in line.replace("=", " ").replace(",", " ").replace("(", " ").replace(")", " ").split():
+            try:
+                vals.append(float(tok))
+            except ValueError:
+                pass
+        if vals:
+            rows.append(vals)
+    return rows
+
+
+def _same_numbers(a, b, what, rtol=2e-5):
+    ta, tb = _table(a), _table(b)
+    assert len(ta) == len(tb) and len(ta) > 0, what
+    for ra, rb in zip(ta, tb):
+        assert len(ra) == len(rb), what
+        assert np.allclose(ra, rb, rtol=rtol, atol=1.5e-6), (what, ra, rb)    # %g / %f: six digits
+
+
+def _sample_files(tmp_path, h, n=30, T=12, seed=7):
+    net = tmp_path / "h.net"
+    net.write_text(h.net_text())
+    _run("sample_driver_cpu", net, n, T, seed, tmp_path / "all.txt")
+    _observed_only(tmp_path / "all.txt", tmp_path / "m1.txt", "M1")
+    return net
+
+
+def test_generate_data_on_the_gpu_backend(gpu_lib, tmp_path):
+    """generate_data (src/nip.c:2325-2478) unchanged, its make_consistent calls on the device:
+    with the same rand() seed the GPU-linked build draws the same series as the reference
+    (the slices of a series depend on each other through in_clique->p, which the replacement
+    must honour), and the unchanged nipsample tool produces series whose previous-slice column
+    repeats the interface state of the slice before"""
+    h = HmmSpec(7, 4, seed=5)
+    net = tmp_path / "g.net"
+    net.write_text(h.net_text())
+    _run("sample_driver_cpu", net, 12, 9, 123, tmp_path / "cpu.txt")
+    _run("sample_driver_gpu", net, 12, 9, 123, tmp_path / "gpu.txt")
+    assert open(tmp_path / "cpu.txt").read() == open(tmp_path / "gpu.txt").read()
+    _run("nipsample_gpu", net, 20, 10, tmp_path / "s.txt")
+    lines = open(tmp_path / "s.txt").read().split("\n")
+    cols = lines[0].split(",")
+    p0, p1 = cols.index("P0"), cols.index("P1")
+    n_pairs, prev = 0, None
+    for l in lines[1:]:
+        if not l.strip():
+            prev = None
+            continue
+        row = l.split(",")
+        if prev is not None:
+            assert row[p0] == prev[p1], "P0 of a slice must be the P1 drawn in the slice before"
+            n_pairs += 1
+        prev = row
+    assert n_pairs == 20 * 9
+
+
+def test_niplikelihood_nipjoint_nipmap_on_the_gpu_backend(gpu_lib, tmp_path):
+    """the remaining callers of the fine-grained API (util/niplikelihood.c:111-135,
+    util/nipjoint.c:77-96) and of the smoother (util/nipmap.c:139-145), unchanged and relinked:
+    same files in, same numbers out as the reference build"""
+    h = HmmSpec(9, 5, seed=13)
+    net = _sample_files(tmp_path, h)
+    for memo in ("1", "0"):
+        os.environ["NIP_GPU_SLICE_MEMO"] = memo
+        try:
+            _same_numbers(_run("niplikelihood_gpu", net, tmp_path / "m1.txt", "M1"),
+                          _run("niplikelihood_cpu", net, tmp_path / "m1.txt", "M1"), "niplikelihood memo=" + memo)
+        finally:
+            del os.environ["NIP_GPU_SLICE_MEMO"]
+    _same_numbers(_run("nipjoint_gpu", net, tmp_path / "m1.txt"),
+                  _run("nipjoint_cpu", net, tmp_path / "m1.txt"), "nipjoint (hidden variables)")
+    _same_numbers(_run("nipjoint_gpu", net, tmp_path / "m1.txt", "P1"),
+                  _run("nipjoint_cpu", net, tmp_path / "m1.txt", "P1"), "nipjoint P1")
+    _run("nipmap_gpu", net, tmp_path / "m1.txt", tmp_path / "map_gpu.txt")
+    _run("nipmap_cpu", net, tmp_path / "m1.txt", tmp_path / "map_cpu.txt")
+    a, b = open(tmp_path / "map_cpu.txt").read().split("\n"), open(tmp_path / "map_gpu.txt").read().split("\n")
+    assert len(a) == len(b) and len(a) > 30 * 12
+    differ = sum(x.split() != y.split() for x, y in zip(a, b))
+    assert differ <= 2, "MAP states differ in %d rows (only exact posterior ties may)" % differ
 
 
 def test_generate_set_dropin(libs, tmp_path):
