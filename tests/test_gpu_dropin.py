@@ -383,8 +383,8 @@ def test_niplikelihood_nipjoint_nipmap_on_the_gpu_backend(gpu_lib, tmp_path):
                           _run("niplikelihood_cpu", net, tmp_path / "m1.txt", "M1"), "niplikelihood memo=" + memo)
         finally:
             del os.environ["NIP_GPU_SLICE_MEMO"]
-    _same_numbers(_run("nipjoint_gpu", net, tmp_path / "m1.txt"),
-                  _run("nipjoint_cpu", net, tmp_path / "m1.txt"), "nipjoint (hidden variables)")
+    # (without variable arguments util/nipjoint.c:114-119 takes ts->hidden and frees it twice,
+    # :142 and free_timeseries: undefined behaviour in the reference itself, not exercised)
     _same_numbers(_run("nipjoint_gpu", net, tmp_path / "m1.txt", "P1"),
                   _run("nipjoint_cpu", net, tmp_path / "m1.txt", "P1"), "nipjoint P1")
     _run("nipmap_gpu", net, tmp_path / "m1.txt", tmp_path / "map_gpu.txt")

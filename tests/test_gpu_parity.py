@@ -478,3 +478,139 @@ def test_device_sampler_matches_the_model(gpu_lib, name):
         off += card
     assert not np.array_equal(x, m.sample(N, T, seed=12))
     assert np.array_equal(x, m.sample(N, T, seed=11))
+
+
+def test_c4_shape_vs_oracle(gpu_lib, oracle_lib):
+    """BASELINE configs[3] at its real shape: 1024-state interface clique (8 x 8 tiles of the
+    per-slice DGEMM, the split-K count GEMM, two concurrent halves), 64 symbols; ragged series
+    with missing data; smoothing, filtering and the E-step against the oracle"""
+    from nip_b200.synth import HmmSpec
+    h = HmmSpec(1024, 64, seed=41)
+    fm = h.flat()
+    data = h.sample(9, 6, seed=3, missing=0.15)
+    data[:, 0, 0] = np.abs(data[:, 0, 0])
+    lens = [6, 5, 1, 3, 6, 2, 4, 6, 5]
+    series = [data[i, :lens[i]] for i in range(9)]
+    om = oracle_lib.model(fm)
+    m = gpu_lib.Model(fm)
+    assert m.engine == gpu_lib.ENGINE_CHAIN
+    b = m.batch(h.obs_vars, series)
+    post, ll = b.infer(h.hidden_query)
+    fpost, fll = b.infer(h.hidden_query, forward_only=True)
+    for i, (got, fgot) in enumerate(zip(b.split(post), b.split(fpost))):
+        want, llw = om.infer(h.obs_vars, series[i], h.hidden_query)
+        assert_close(got, want, "C4 series %d smoothed" % i)
+        assert_close(ll[i], llw, "C4 series %d loglik" % i)
+        want, llw = om.infer(h.obs_vars, series[i], h.hidden_query, forward_only=True)
+        assert_close(fgot, want, "C4 series %d filtered" % i)
+        assert_close(fll[i], llw, "C4 series %d loglik (filter)" % i)
+    want, ll_want, st_want = om.estep(h.obs_vars, series)
+    counts, L, st = b.estep()
+    assert st == st_want == 0
+    assert_close(counts, want, "C4 expected counts")
+    assert_close(L, ll_want, "C4 EM loglik")
+    b.close()
+    m.close()
+
+
+@pytest.mark.parametrize("mode", ["", "cta", "hbm", "grid"])
+@pytest.mark.parametrize("name", ["model_net", "demo1_net", "factorial4x3", "no_interface", "two_layer"])
+def test_slice_propagate_vs_oracle(gpu_lib, oracle_lib, name, mode, monkeypatch):
+    """nipgpu_slice_propagate = make_consistent on the caller's own state: start from the oracle's
+    tree after priors + evidence, then perturb the consistent tree (new evidence multiplied into
+    a clique, as nip_enter_evidence and finish_timeslice_message_pass do) and propagate again —
+    the second pass divides by the sepsets the first one left"""
+    if mode:
+        monkeypatch.setenv("NIPGPU_JT_MODE", mode)
+    c = Case(name)
+    fm = c.fm
+    try:
+        m = gpu_lib.Model(fm, engine=1)
+    except gpu_lib.NipGpuError as e:
+        pytest.skip(str(e))
+    om = oracle_lib.model(fm)
+    om.reset()
+    om.use_priors(0)
+    rng = np.random.default_rng(3)
+    lik = rng.random(int(fm.var_card[c.obs_vars[0]])) + 0.05
+    lik[0] = 0.0
+    om.enter_evidence(c.obs_vars[0], lik)
+    start = np.concatenate([om.clique(k) for k in range(fm.n_cliques)])
+    n_msg = int(sum(np.prod([fm.var_card[v] for v in fm.sepset_vars[fm.sepset_var_off[s]:fm.sepset_var_off[s + 1]]])
+                    for s in range(fm.n_sepsets)))
+    ones = np.ones(n_msg)
+    tab, new, old = m.slice_propagate(start, ones)
+    om.make_consistent()
+    want = np.concatenate([om.clique(k) for k in range(fm.n_cliques)])
+    assert_close(tab, want, "%s consistent cliques" % name)
+    # mass = sum cliques - sum sepsets (src/nipjointree.c:1156-1188)
+    assert_close(tab.sum() - new.sum(), om.mass(), "%s mass" % name)
+    # second round on the consistent tree: scale one clique along one of its variables
+    v = [int(x) for x in fm.clique_vars if int(x) != int(c.obs_vars[0])][-1]
+    lik2 = rng.random(int(fm.var_card[v])) + 0.05
+    om.enter_evidence(v, lik2)          # multiplied into the family clique of v, nothing else touched
+    start2 = np.concatenate([om.clique(k) for k in range(fm.n_cliques)])
+    tab2, new2, old2 = m.slice_propagate(start2, new)
+    om.make_consistent()
+    want2 = np.concatenate([om.clique(k) for k in range(fm.n_cliques)])
+    assert_close(tab2, want2, "%s second propagation on a consistent tree" % name)
+    assert_close(tab2.sum() - new2.sum(), om.mass(), "%s mass after the second propagation" % name)
+    m.close()
+
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+@pytest.mark.parametrize("name", ["hmm64", "tree"])
+def test_group_em_matches_one_device(gpu_lib, n_dev, name):
+    """EM over several devices of one box (nipgpu_group_*): series sharded over the members,
+    one ncclAllReduce of the expected counts per iteration.  Reduced counts, log-likelihood and
+    the parameters after three iterations must equal the one-device run to 1e-12"""
+    if _device_count() < n_dev:
+        pytest.skip("needs %d GPUs" % n_dev)
+    from nip_b200.dist import shard_series
+    from nip_b200.synth import HmmSpec
+    if name == "hmm64":
+        h = HmmSpec(64, 8, seed=9)
+        fm, obs_vars = h.flat(), h.obs_vars
+        data = h.sample(203, 30, seed=4, missing=0.05)
+        data[:, 0, 0] = np.abs(data[:, 0, 0])
+        rng = np.random.default_rng(2)
+        series = [data[i, :int(rng.integers(2, 31))] for i in range(203)]
+    else:
+        c = Case("demo1_net")
+        fm, obs_vars = c.fm, c.obs_vars
+        series = [s for s in c.series for _ in range(7)]
+    init = np.random.default_rng(1).random(0)
+    single = gpu_lib.Model(fm, device=0)
+    init = np.random.default_rng(1).random(single.counts_size()) + 0.1
+    sb = single.batch(obs_vars, series)
+    models = [gpu_lib.Model(fm, device=d) for d in range(n_dev)]
+    parts = shard_series([len(s) for s in series], n_dev)
+    batches = [models[d].batch(obs_vars, [series[i] for i in parts[d]]) for d in range(n_dev)]
+    g = gpu_lib.Group(models)
+    single.mstep(init)
+    g.mstep(init)
+    for it in range(3):
+        want, ll_want, st_want = sb.estep()
+        got, ll, st = g.estep(batches)
+        assert st == st_want == 0
+        assert_close(got, want, "%s iteration %d reduced counts on %d devices" % (name, it, n_dev), rtol=1e-12)
+        assert_close(ll, ll_want, "%s iteration %d loglik" % (name, it), rtol=1e-12)
+        single.mstep()
+        g.mstep()
+    t0, p0 = single.parameters()
+    for mdl in models:
+        t, p = mdl.parameters()
+        assert_close(t, t0, "trained tables on device %d" % mdl.device, rtol=1e-12)
+        assert_close(p, p0, "trained priors on device %d" % mdl.device, rtol=1e-12)
+    g.close()
+    for b in batches:
+        b.close()
+    for mdl in models:
+        mdl.close()
+    sb.close()
+    single.close()
