@@ -173,6 +173,55 @@ def test_make_consistent_dropin(libs, tmp_path, memo, monkeypatch):
         gpu.nip_gpu_release(m_gpu.h)
 
 
+@pytest.mark.parametrize("n_dev", [2, 4, 8])
+def test_em_learn_dropin_on_several_devices(libs, tmp_path, n_dev, monkeypatch):
+    """NIP_GPU_DEVICES=0,1,...: em_learn (src/nip.c:2076-2250, called by util/niptrain.c:151)
+    shards the series over the devices inside the C boundary, one ncclAllReduce of the expected
+    counts per iteration.  Learning curve and trained CPTs: 1e-12 against the one-device run,
+    1e-9 against the reference"""
+    import torch
+    if torch.cuda.device_count() < n_dev:
+        pytest.skip("needs %d GPUs" % n_dev)
+    ref, gpu = libs
+    h = HmmSpec(9, 4, seed=17)
+    p = tmp_path / "e.net"
+    p.write_text(h.net_text())
+    data = h.sample(37, 21, seed=5, missing=0.05)
+    data[:, 0, 0] = np.abs(data[:, 0, 0])
+    rng = np.random.default_rng(3)
+    series = [data[i, :int(rng.integers(3, 22))] for i in range(37)]
+
+    def train(lib_em, model, seed):
+        ts = [model.timeseries(h.obs_vars, s) for s in series]
+        arr = (vp * len(ts))(*ts)
+        ref.L.refh_seed(seed)
+        lc = ref.L.refh_new_double_list()
+        st = lib_em(arr, len(ts), 1e-4, lc)
+        curve = np.zeros(4096)
+        n = ref.L.refh_double_list_to_array(lc, curve.ctypes.data_as(vp), 4096)
+        ref.L.refh_free_double_list(lc)
+        return st, curve[:n].copy(), model.parameters()
+
+    m_ref = ref.parse(p)
+    st_ref, curve_ref = m_ref.em_learn([m_ref.timeseries(h.obs_vars, s) for s in series], 1e-4, 31)
+    t_ref, p_ref = m_ref.parameters()
+    monkeypatch.delenv("NIP_GPU_DEVICES", raising=False)
+    m_one = ref.parse(p)
+    st_one, curve_one, (t_one, p_one) = train(gpu.em_learn, m_one, 31)
+    gpu.nip_gpu_release(m_one.h)
+    monkeypatch.setenv("NIP_GPU_DEVICES", ",".join(str(d) for d in range(n_dev)))
+    m_many = ref.parse(p)
+    st_many, curve_many, (t_many, p_many) = train(gpu.em_learn, m_many, 31)
+    gpu.nip_gpu_release(m_many.h)
+    assert st_ref == st_one == st_many == 0
+    assert len(curve_ref) == len(curve_one) == len(curve_many) and len(curve_ref) >= 3
+    assert_close(curve_many, curve_one, "learning curve, %d devices vs one" % n_dev, rtol=1e-12)
+    assert_close(t_many, t_one, "trained tables, %d devices vs one" % n_dev, rtol=1e-10)
+    assert_close(curve_many, curve_ref, "learning curve vs the reference")
+    assert_close(t_many, t_ref, "trained original_p vs the reference", rtol=1e-8)
+    assert_close(p_many, p_ref, "trained priors vs the reference", rtol=1e-8)
+
+
 def test_inference_after_training_is_not_served_stale(libs, tmp_path):
     """infer -> em_learn -> infer on a registered set: the second answer must come from the
     trained parameters (the parked pass of the first call is stale)"""
