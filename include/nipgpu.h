@@ -256,6 +256,8 @@ int64_t nipgpu_launch_count(int reset);
  * nipgpu_infer / nipgpu_em_estep call, measured with CUDA events on the library's
  * stream; n receives the number of launches summed. */
 int nipgpu_last_kernel_ms(nipgpu_model* m, double* ms, int32_t* n);
+/* the forward kernel's share of the last nipgpu_infer on the tensor path (0 elsewhere) */
+int nipgpu_last_forward_ms(nipgpu_model* m, double* ms);
 /* Diagnostics of the generic engine's grid team (models whose cliques are streamed through
  * HBM; recording is on when the model was created with NIPGPU_JT_TRACE=1 in the environment):
  * copies up to cap_records (tag, device-timer ns) pairs, one per grid-wide barrier, into
@@ -271,6 +273,13 @@ int nipgpu_probe_peaks(int device, double* dmma_tflops, double* dfma_tflops, dou
  * accumulator chains of DMMA m8n8k4 per warp, warps_per_block x blocks warps; reports the clocks
  * one warp spends per DMMA (issue interval when chains hide the latency, else the latency). */
 int nipgpu_probe_dmma_chain(int chains, int warps_per_block, int blocks, double* clocks_per_dmma);
+/* the chain kernels' sweep alone (128 DMMAs of one 8 x 64 . 64 x 64 contraction, B fragments from
+ * shared memory), back to back on one warp per scheduler: clocks per sweep of B-fragment delivery
+ * variant `variant` (nip_b200/csrc/sweep.cuh); 2048 is the tensor pipe's floor. */
+int nipgpu_probe_sweep(int variant, int blocks, double* clocks_per_sweep);
+/* scalar FP64 arithmetic and DMMA on one pipe?  clocks per DMMA of a warp that issues
+ * `dfma_per_dmma` (0, 1, 2, 4) independent DFMAs after every DMMA */
+int nipgpu_probe_dmma_dfma(int dfma_per_dmma, int warps_per_block, int blocks, double* clocks_per_dmma);
 /* the CUDA stream (cudaStream_t) all work of this model is enqueued on */
 void* nipgpu_model_stream(nipgpu_model* m);
 

@@ -15,7 +15,8 @@ import numpy as np
 from .desc import FlatModel, ModelDesc
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libnipgpu.so")
+# NIPGPU_LIB_PATH: development only (A/B timing of kernel variants built side by side)
+LIB_PATH = os.environ.get("NIPGPU_LIB_PATH") or os.path.join(PKG, "libnipgpu.so")
 
 ENGINE_AUTO, ENGINE_JTREE, ENGINE_CHAIN = 0, 1, 2
 EBADLUCK = 8
@@ -29,8 +30,8 @@ ABI_SYMBOLS = [
     "nipgpu_em_counts_device", "nipgpu_em_mstep", "nipgpu_likelihood", "nipgpu_slice_reset",
     "nipgpu_slice_use_priors", "nipgpu_slice_enter_prior", "nipgpu_slice_enter_evidence", "nipgpu_slice_get_sepset", "nipgpu_slice_make_consistent",
     "nipgpu_slice_mass", "nipgpu_slice_marginal", "nipgpu_slice_get_clique",
-    "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_jt_trace", "nipgpu_sample", "nipgpu_model_stream", "nipgpu_probe_peaks",
-    "nipgpu_probe_dmma_chain", "nipgpu_slice_propagate", "nipgpu_group_create", "nipgpu_group_destroy",
+    "nipgpu_launch_count", "nipgpu_last_kernel_ms", "nipgpu_last_forward_ms", "nipgpu_jt_trace", "nipgpu_sample", "nipgpu_model_stream", "nipgpu_probe_peaks",
+    "nipgpu_probe_dmma_chain", "nipgpu_probe_sweep", "nipgpu_probe_dmma_dfma", "nipgpu_slice_propagate", "nipgpu_group_create", "nipgpu_group_destroy",
     "nipgpu_group_size", "nipgpu_group_em_estep", "nipgpu_group_em_mstep",
 ]
 
@@ -87,10 +88,13 @@ def load_library(path=LIB_PATH):
     L.nipgpu_launch_count.restype = C.c_int64
     L.nipgpu_launch_count.argtypes = [_i]
     L.nipgpu_last_kernel_ms.argtypes = [_vp, C.POINTER(_d), C.POINTER(C.c_int32)]
+    L.nipgpu_last_forward_ms.argtypes = [_vp, C.POINTER(_d)]
     L.nipgpu_jt_trace.argtypes = [_vp, _vp, _i, _i]
     L.nipgpu_sample.argtypes = [_vp, _i, _i, C.c_uint64, _vp]
     L.nipgpu_probe_peaks.argtypes = [_i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]
     L.nipgpu_probe_dmma_chain.argtypes = [_i, _i, _i, C.POINTER(_d)]
+    L.nipgpu_probe_sweep.argtypes = [_i, _i, C.POINTER(_d)]
+    L.nipgpu_probe_dmma_dfma.argtypes = [_i, _i, _i, C.POINTER(_d)]
     L.nipgpu_slice_propagate.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
     L.nipgpu_group_create.argtypes = [_vp, _i, C.POINTER(_vp)]
     L.nipgpu_group_destroy.argtypes = [_vp]
@@ -191,6 +195,11 @@ class Model:
         ms, n = _d(), C.c_int32()
         _check(self.L.nipgpu_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def last_forward_ms(self):
+        ms = _d()
+        _check(self.L.nipgpu_last_forward_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def sample(self, n_series, length, seed=1):
         """[n_series, length, n_vars] int32 states drawn from the model (chain-structured models)"""

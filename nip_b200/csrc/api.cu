@@ -266,7 +266,11 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
     a.d_obs = b->d_obs; a.d_row_off = b->d_row_off; a.want_ll = want_ll; a.forward_only = forward_only;
     a.d_post = project ? b->d_joint : post; a.post_stride = project ? SPc : Q.row; a.post_off = 0;
     a.d_ll = b->d_ll; a.d_status = b->d_status;
-    if (int e = chain_infer(hm, m->chain, b->chain, plan, a, m->stream, m->ev0, m->ev1)) return e;
+    NIPGPU_CUDA(cudaEventRecord(m->ev_mid, m->stream));   // re-recorded between the two kernels of the warp-resident path
+    g_chain_mid_event = m->ev_mid;
+    const int ce = chain_infer(hm, m->chain, b->chain, plan, a, m->stream, m->ev0, m->ev1);
+    g_chain_mid_event = nullptr;
+    if (ce) return ce;
     if (project)
       if (int e = chain_post_vars(hm, m->chain, b->chain, qv, m->d_base0, m->d_base1, m->tab_off, m->d_ipool,
                                   b->d_joint, b->d_first, b->d_row_off, b->n_series, b->rows, Q.row, post, m->stream))
@@ -276,6 +280,8 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
     if (b->n_series > 0 && cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) {
       m->last_kernel_ms = ms;
       m->last_kernel_n = forward_only ? 1 : 2;
+      float f = 0;
+      m->last_forward_ms = cudaEventElapsedTime(&f, m->ev0, m->ev_mid) == cudaSuccess ? f : 0;
     }
     return NIPGPU_OK;
   }
@@ -343,6 +349,7 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
   NIPGPU_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   NIPGPU_CUDA(cudaEventCreate(&m->ev0));
   NIPGPU_CUDA(cudaEventCreate(&m->ev1));
+  NIPGPU_CUDA(cudaEventCreate(&m->ev_mid));
   cudaStream_t st = m->stream;
 
   // ---- table offsets (int: the reference indexes tables with int too) ----
@@ -437,6 +444,7 @@ void nipgpu_model_destroy(nipgpu_model* m) {
   chain_free(m->chain);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->ev_mid) cudaEventDestroy(m->ev_mid);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -973,6 +981,12 @@ int64_t nipgpu_launch_count(int reset) {
   const int64_t n = g_launches.load();
   if (reset) g_launches.store(0);
   return n;
+}
+
+int nipgpu_last_forward_ms(nipgpu_model* m, double* ms) {
+  if (!m || !ms) return fail(NIPGPU_EINVAL, "bad arguments");
+  *ms = m->last_forward_ms;
+  return NIPGPU_OK;
 }
 
 int nipgpu_last_kernel_ms(nipgpu_model* m, double* ms, int32_t* n) {

@@ -15,8 +15,8 @@ struct nipgpu_model {
   int engine = NIPGPU_ENGINE_JTREE;  // preferred engine
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double last_kernel_ms = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+  double last_kernel_ms = 0, last_forward_ms = 0;
   int last_kernel_n = 0;
 
   // ---- structure (immutable) ----

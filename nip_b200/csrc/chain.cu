@@ -13,6 +13,7 @@
 // The transition table is pre-arranged once per parameter change in "fragment
 // order" so that every B operand is one conflict-free 8-byte load per lane.
 #include "chain.cuh"
+#include "sweep.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -21,13 +22,6 @@
 namespace nipgpu {
 
 namespace {
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-      : "+d"(c0), "+d"(c1)
-      : "d"(a), "d"(b));
-}
-
 
 // position of A(k-state, n-state) inside a fragment-ordered SPxSP table
 // For NT >= 2 the fragments of n-tiles (2m, 2m+1) of one lane are adjacent (one LDS.128).
@@ -141,71 +135,6 @@ __global__ void k_chain_cfg(const int* obs, long long rows, int n_obs, const int
     if (col_slot[k] >= 0 && o >= 0) c += (o - col_card[k]) * col_stride[k] * col_mult[k];
   }
   cfg[r] = c;
-}
-
-__device__ __forceinline__ void dmma_init(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
-               : "=d"(c0), "=d"(c1)
-               : "d"(a), "d"(b), "d"(0.0));
-}
-
-// acc[n] = sum over the 2*NT k-steps of A(k-step) x B(k-step, n): the whole
-// [8 x SP] . [SP x SP] contraction of one slice (2*NT*NT tensor instructions).
-// One 16-byte shared load brings the B fragments of two neighbouring n-tiles;
-// they are fetched a k-step ahead.
-//
-// A warp can issue one DMMA per ~16 cycles and is alone on its scheduler, so the
-// issue slots between two DMMAs are free.  `side(slot)` is called after every
-// tensor instruction with a compile-time slot number 0 .. 2*NT*NT-1; callers hang
-// small pieces of work there that do not depend on this sweep's result.
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < N) {
-    f(std::integral_constant<int, I>{});
-    static_for<I + 1, N>(f);
-  }
-}
-
-template <int NT, class Side>
-__device__ __forceinline__ void mma_sweep(double (&acc)[NT][2], const double (&a)[NT][2],
-                                          const double* __restrict__ frag, Side side) {
-  double b[2][NT];
-  auto fetch = [&](auto ksc, auto bufc) {
-    constexpr int ks = decltype(ksc)::value, buf = decltype(bufc)::value;
-    if constexpr (NT >= 2) {
-      const double2* p = reinterpret_cast<const double2*>(frag) + ((ks * (NT / 2)) << 5);
-      static_for<0, NT / 2>([&](auto n2c) {
-        constexpr int n2 = decltype(n2c)::value;
-        const double2 v = p[n2 << 5];
-        b[buf][2 * n2] = v.x;
-        b[buf][2 * n2 + 1] = v.y;
-      });
-    } else {
-      b[buf][0] = frag[ks << 5];
-    }
-  };
-  fetch(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
-  static_for<0, 2 * NT>([&](auto ksc) {
-    constexpr int ks = decltype(ksc)::value;
-    if constexpr (ks + 1 < 2 * NT)
-      fetch(std::integral_constant<int, ks + 1>{}, std::integral_constant<int, (ks + 1) & 1>{});
-    const double av = a[ks >> 1][ks & 1];
-    static_for<0, NT>([&](auto nc) {
-      constexpr int n = decltype(nc)::value;
-      if constexpr (ks == 0) dmma_init(acc[n][0], acc[n][1], av, b[0][n]);
-      else dmma(acc[n][0], acc[n][1], av, b[ks & 1][n]);
-      side(std::integral_constant<int, ks * NT + n>{});
-    });
-  });
-}
-
-// Spreads W work items evenly over the NS side slots of a sweep: slot s runs the items
-// w with  w*NS/W == s  (several per slot when W > NS).  Everything folds at compile time.
-template <int NS, int W, int SLOT, class Item>
-__device__ __forceinline__ void run_items(Item& item) {
-  static_for<0, W>([&](auto wc) {
-    if constexpr ((decltype(wc)::value * NS) / W == SLOT) item(wc);
-  });
 }
 
 // running log-likelihood sum_t log(m2_t) - log(m1_t) kept as a product with a
@@ -628,6 +557,8 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   }
 }
 
+#include "chain_pair.cuh"
+
 // ----------------------------------------------------------------- EM ----
 // Sufficient statistics of the whole batch in one pass over the two row stores
 // (own[k] from the forward kernel, bt[k] = beta_k and hv[k] = h_k from the backward kernel):
@@ -938,9 +869,26 @@ int set_smem(K kernel, size_t bytes) {
   return NIPGPU_OK;
 }
 
+// NT = 4 / 8: every 8-sequence group on a pair of warps of one scheduler (chain_pair.cuh);
+// NIPGPU_CHAIN_PAIR=0 keeps the one-warp kernels (A/B timing)
+static bool use_pair(int NT) {
+  static const bool on = [] { const char* e = getenv("NIPGPU_CHAIN_PAIR"); return !(e && e[0] == '0'); }();
+  return on && (NT == 4 || NT == 8);
+}
+
 template <int NT, bool FILT, bool WLL>
 int launch_forward_v(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
                      cudaStream_t st) {
+  if constexpr (NT == 4 || NT == 8) {
+    if (use_pair(NT)) {
+      const size_t smem = PairGeom<NT>::smem_bytes();
+      if (int e = set_smem(k_chain_forward_pair<NT, FILT, WLL>, smem)) return e;
+      k_chain_forward_pair<NT, FILT, WLL><<<(B.n_series + 31) / 32, 256, smem, st>>>(
+          C, B, alpha, a.d_post, a.post_stride, a.post_off, a.d_ll, a.d_status);
+      NIPGPU_LAUNCHED();
+      return NIPGPU_OK;
+    }
+  }
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
   if (int e = set_smem(k_chain_forward<NT, FILT, WLL>, smem)) return e;
   const int grid = (B.n_series + 31) / 32;
@@ -966,6 +914,22 @@ int launch_backward(const ChainDev& C, const ChainBatchDev& B, const ChainInferA
   const int grid = (B.n_series + 31) / 32;
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
   const bool vec = ((a.post_stride | a.post_off) & 1) == 0 && C.S == C.SP;
+  if constexpr (NT == 4 || NT == 8) {
+    if (use_pair(NT)) {
+      const size_t psm = PairGeom<NT>::smem_bytes();
+      if (vec) {
+        if (int e = set_smem(k_chain_backward_pair<NT, true, false>, psm)) return e;
+        k_chain_backward_pair<NT, true, false><<<grid, 256, psm, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                                       a.post_off, nullptr, nullptr, nullptr);
+      } else {
+        if (int e = set_smem(k_chain_backward_pair<NT, false, false>, psm)) return e;
+        k_chain_backward_pair<NT, false, false><<<grid, 256, psm, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                                        a.post_off, nullptr, nullptr, nullptr);
+      }
+      NIPGPU_LAUNCHED();
+      return NIPGPU_OK;
+    }
+  }
   if (vec) {
     if (int e = set_smem(k_chain_backward<NT, true, false>, smem)) return e;
     k_chain_backward<NT, true, false><<<grid, 128, smem, st>>>(C, B, alpha, a.d_post, a.post_stride,
@@ -994,8 +958,19 @@ int launch_em(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a
   if (int e = launch_forward_v<NT, false, true>(C, B, a, alpha, st)) return e;
   const int grid = (B.n_series + 31) / 32;
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
-  if (int e = set_smem(k_chain_backward<NT, true, true>, smem)) return e;
-  k_chain_backward<NT, true, true><<<grid, 128, smem, st>>>(C, B, alpha, nullptr, C.SP, 0, s.bt, s.r0, s.hv);
+  bool paired = false;
+  if constexpr (NT == 4 || NT == 8) {
+    if (use_pair(NT)) {
+      const size_t psm = PairGeom<NT>::smem_bytes();
+      if (int e = set_smem(k_chain_backward_pair<NT, true, true>, psm)) return e;
+      k_chain_backward_pair<NT, true, true><<<grid, 256, psm, st>>>(C, B, alpha, nullptr, C.SP, 0, s.bt, s.r0, s.hv);
+      paired = true;
+    }
+  }
+  if (!paired) {
+    if (int e = set_smem(k_chain_backward<NT, true, true>, smem)) return e;
+    k_chain_backward<NT, true, true><<<grid, 128, smem, st>>>(C, B, alpha, nullptr, C.SP, 0, s.bt, s.r0, s.hv);
+  }
   NIPGPU_LAUNCHED();
   if (int e = set_smem(k_chain_stats<NT>, s.smem)) return e;
   k_chain_stats<NT><<<s.parts, 32 * NT * (NT >= 2 ? 2 : 1), s.smem, st>>>(alpha, s.bt, s.hv, B.cfg, s.first, C.lam_comb, s.rows,
@@ -1345,6 +1320,9 @@ static int chain_prepare_evidence(const ChainModel& cm, ChainBatch& cb, const Ch
   return NIPGPU_OK;
 }
 
+// instrumentation: when set, recorded between the forward and the backward kernel of chain_infer
+cudaEvent_t g_chain_mid_event = nullptr;
+
 int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
                 const ChainInferArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
   (void)hm;
@@ -1372,6 +1350,7 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
     default: set_error("chain: unsupported interface size"); return NIPGPU_EUNSUPPORTED;
   }
   if (e) return e;
+  if (g_chain_mid_event) NIPGPU_CUDA(cudaEventRecord(g_chain_mid_event, st));
   if (!a.forward_only && a.d_post) {
     switch (cm.NT) {
       case 1: e = launch_backward<1>(C, B, a, cb.d_alpha, st); break;

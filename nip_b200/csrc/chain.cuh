@@ -124,6 +124,7 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
 int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan,
                 const ChainInferArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 void chain_batch_free(ChainBatch& cb);
+extern cudaEvent_t g_chain_mid_event;   // instrumentation: recorded between the forward and backward kernels
 // dense.cu
 int dense_refresh_mats(const ChainModel& cm, const double* d_base1_c0, cudaStream_t st);
 // E-step outputs of the dense backward pass (see k_chain_stats in chain.cu for what they mean)

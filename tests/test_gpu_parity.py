@@ -63,6 +63,7 @@ def test_unmarked_columns_are_ignored(gpu_lib, oracle_lib, engine):
 
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("S,M,B,T", [(64, 32, 48, 40), (7, 3, 100, 17), (33, 5, 19, 9),
+                                     (30, 4, 77, 23), (32, 6, 9, 12), (57, 3, 130, 11),   # 4 / 8 state tiles: warp pairs
                                      (72, 5, 150, 9), (130, 4, 21, 6), (200, 3, 300, 5),
                                      (72, 4, 700, 6)])  # > 64: GEMM E-step; 700: two concurrent halves
 def test_hmm_em_vs_oracle(gpu_lib, oracle_lib, engine, S, M, B, T):
@@ -84,6 +85,7 @@ def test_hmm_em_vs_oracle(gpu_lib, oracle_lib, engine, S, M, B, T):
 
 @pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("S,M,B,T", [(64, 32, 48, 40), (7, 3, 100, 17), (33, 5, 19, 9),
+                                     (30, 4, 77, 23), (32, 6, 9, 12), (57, 3, 130, 11),   # 4 / 8 state tiles: warp pairs
                                      (72, 5, 150, 9), (130, 4, 21, 6), (72, 4, 700, 6)])   # > 64 states: tiled-GEMM engine
 def test_hmm_vs_oracle(gpu_lib, oracle_lib, engine, S, M, B, T):
     """seeded synthetic HMMs of the benchmark family, ragged lengths, missing data"""
