@@ -40,6 +40,10 @@ struct ChainDev {
 };
 
 struct ChainBatchDev {
+  int* fexp;               // [rows] exponent carried by the stored forward row (pair kernels)
+  double* zc;              // [n_series] sum of the last forward row
+  int* zf;                 // [n_series] its exponent
+  double* rn_out;          // [rows] E-step: 1 / (forward row . beta row), or nullptr
   int n_series;
   const int* order;        // sorted position -> series
   const int* len_sorted;
@@ -581,7 +585,10 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
     k_chain_stats(const double* __restrict__ own, const double* __restrict__ bt, const double* __restrict__ hv,
                   const int* __restrict__ cfg, const unsigned char* __restrict__ first,
                   const double* __restrict__ lam_comb, long long rows, int n_comb, int phases,
-                  double* __restrict__ partG, double* __restrict__ partC) {
+                  double* __restrict__ partG, double* __restrict__ partC,
+                  const double* __restrict__ rnv) {
+  // rnv[k] = 1 / (own_k . beta_k) when the producing kernels know it from their scale bookkeeping
+  // (warp-pair kernels); nullptr: the dot products are formed here
   // NT m-tiles x GR halves of the n-tiles: 2 NT warps keep four warps on every scheduler
   constexpr int SP = 8 * NT, KC = 32, LD = SP + 4, GR = NT >= 2 ? 2 : 1, NW = NT * GR, NTH = 32 * NW;
   constexpr int TR = KC + 1, NH = NT / GR, STG = 3 * TR * LD;
@@ -590,7 +597,8 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
   // stage s (2): Aop rows at sm + s * STG, Bop rows TR * LD further, posterior rows 2 TR LD further;
   // tile row i of the tile starting at k0 holds data row k0 - 1 + i
   double* s_h = sm + 2 * STG;               // [3][TR + 1] h of the tile's rows (tile t in slot t % 3)
-  double* s_lam = s_h + 3 * (TR + 1) + 1;   // [n_comb][SP] evidence rows
+  double* s_rn = s_h + 3 * (TR + 1) + 1;    // [3][TR + 1] 1 / N of the tile's rows
+  double* s_lam = s_rn + 3 * (TR + 1) + 1;  // [n_comb][SP] evidence rows
   const int tab = n_comb * SP;
   double* s_tab = s_lam + tab;              // [phases][n_comb][SP]
   int* s_c = reinterpret_cast<int*>(s_tab + (long long)phases * tab);  // [3][TR + 1] evidence index, -1 - c: opens a series
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
   constexpr int MS = (TR + NTH - 1) / NTH;
   int m_c[MS];
   unsigned char m_f[MS];
-  double m_h[MS];
+  double m_h[MS], m_rn[MS];
   auto meta_load = [&](long long k0) {  // only requests: nothing here waits for the values
 #pragma unroll
     for (int u = 0; u < MS; u++) {
@@ -636,6 +644,7 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
       m_f[u] = ok ? __ldg(first + k) : 0;
       m_c[u] = ok ? __ldg(cfg + k) : 0;
       m_h[u] = ok ? __ldg(hv + k) : 0.0;
+      m_rn[u] = (ok && rnv) ? __ldg(rnv + k) : 0.0;
     }
   };
   auto meta_store = [&](int slot) {
@@ -645,6 +654,7 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
       if (i < TR) {
         s_c[slot * (TR + 1) + i] = m_f[u] ? -1 - m_c[u] : m_c[u];
         s_h[slot * (TR + 1) + i] = m_h[u];
+        s_rn[slot * (TR + 1) + i] = m_rn[u];
       }
     }
   };
@@ -655,23 +665,26 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
     double* sp = sb + TR * LD;
     const int* sc = s_c + slot * (TR + 1);
     const double* sh = s_h + slot * (TR + 1);
+    const double* srn = s_rn + slot * (TR + 1);
     double N[RW];
+    if (!rnv) {
 #pragma unroll
-    for (int u = 0; u < RW; u++) {
-      double part = 0;
+      for (int u = 0; u < RW; u++) {
+        double part = 0;
 #pragma unroll
-      for (int c = 0; c < CW; c++) part += ro[u][c] * rb[u][c];
-      N[u] = part;
+        for (int c = 0; c < CW; c++) part += ro[u][c] * rb[u][c];
+        N[u] = part;
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+        for (int u = 0; u < RW; u++) N[u] += __shfl_xor_sync(0xffffffffu, N[u], sft);
     }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1)
-#pragma unroll
-      for (int u = 0; u < RW; u++) N[u] += __shfl_xor_sync(0xffffffffu, N[u], sft);
 #pragma unroll
     for (int u = 0; u < RW; u++) {
       const int i = w + u * NW;
       if (i < TR) {
-        const double rn = N[u] != 0 ? 1.0 / N[u] : 0.0;
+        const double rn = rnv ? srn[i] : (N[u] != 0 ? 1.0 / N[u] : 0.0);
         // the pair (this row, next row) counts unless the next row opens a series or lies outside
         const bool pair = i < KC && k0 + i < k_end && sc[i + 1] >= 0;
         const double wk = pair ? sh[i + 1] * rn : 0.0;
@@ -869,6 +882,26 @@ int set_smem(K kernel, size_t bytes) {
   return NIPGPU_OK;
 }
 
+// zc[series] = sum of the series' last forward row, zf[series] = the exponent that row carries:
+// Z = zc 2^-zf is the series' evidence mass in the units of the bookkeeping (one warp per series)
+__global__ void k_chain_final(const double* __restrict__ alpha, const int* __restrict__ fexp,
+                              const long long* __restrict__ row_off, const int* __restrict__ order,
+                              const int* __restrict__ len_sorted, int n_series, int SP, double* zc, int* zf) {
+  const int bp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (bp >= n_series) return;
+  const int T = len_sorted[bp], orig = order[bp];
+  double s = 0;
+  if (T > 0) {
+    const double* row = alpha + (row_off[orig] + T - 1) * SP;
+    for (int j = lane; j < SP; j += 32) s += row[j];
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    zc[orig] = s;
+    zf[orig] = T > 0 ? fexp[row_off[orig] + T - 1] : 0;
+  }
+}
+
 // NT = 4 / 8: every 8-sequence group on a pair of warps of one scheduler (chain_pair.cuh);
 // NIPGPU_CHAIN_PAIR=0 keeps the one-warp kernels (A/B timing)
 static bool use_pair(int NT) {
@@ -886,6 +919,11 @@ int launch_forward_v(const ChainDev& C, const ChainBatchDev& B, const ChainInfer
       k_chain_forward_pair<NT, FILT, WLL><<<(B.n_series + 31) / 32, 256, smem, st>>>(
           C, B, alpha, a.d_post, a.post_stride, a.post_off, a.d_ll, a.d_status);
       NIPGPU_LAUNCHED();
+      if (!FILT && B.n_series > 0) {   // a backward pass follows: its normalisers
+        k_chain_final<<<(B.n_series + 7) / 8, 256, 0, st>>>(alpha, B.fexp, B.row_off, B.order, B.len_sorted,
+                                                          B.n_series, C.SP, B.zc, B.zf);
+        NIPGPU_LAUNCHED();
+      }
       return NIPGPU_OK;
     }
   }
@@ -974,7 +1012,8 @@ int launch_em(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a
   NIPGPU_LAUNCHED();
   if (int e = set_smem(k_chain_stats<NT>, s.smem)) return e;
   k_chain_stats<NT><<<s.parts, 32 * NT * (NT >= 2 ? 2 : 1), s.smem, st>>>(alpha, s.bt, s.hv, B.cfg, s.first, C.lam_comb, s.rows,
-                                                      s.n_comb, s.phases, s.partG, s.partC);
+                                                      s.n_comb, s.phases, s.partG, s.partC,
+                                                      paired ? B.rn_out : nullptr);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
@@ -1236,6 +1275,9 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
   if (int e = upload(&cb.d_order, cb.order, st)) return e;
   if (int e = upload(&cb.d_len_sorted, cb.len_sorted, st)) return e;
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_alpha, std::max<long long>(rows, 1) * cm.SP * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cb.d_fexp, std::max<long long>(rows, 1) * sizeof(int)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cb.d_zc, (size_t)std::max(n_series, 1) * sizeof(double)));
+  NIPGPU_CUDA(cudaMalloc((void**)&cb.d_zf, (size_t)std::max(n_series, 1) * sizeof(int)));
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_cfg, std::max<long long>(rows, 1) * sizeof(int)));
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_lam_static, cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaStreamSynchronize(st));
@@ -1245,6 +1287,7 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
 
 void chain_batch_free(ChainBatch& cb) {
   cudaFree(cb.d_order); cudaFree(cb.d_len_sorted); cudaFree(cb.d_cfg); cudaFree(cb.d_alpha);
+  cudaFree(cb.d_fexp); cudaFree(cb.d_zc); cudaFree(cb.d_zf); cudaFree(cb.d_rn);
   cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_rows); cudaFree(cb.d_comb);
   cudaFree(cb.d_rt); cudaFree(cb.d_hvec); cudaFree(cb.d_first); cudaFree(cb.d_r0); cudaFree(cb.d_em_scratch);
   cudaFree(cb.d_dense); cudaFree(cb.d_dense_i);
@@ -1330,6 +1373,7 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   ChainBatchDev B;
   B.n_series = a.n_series; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
   B.cfg = cb.d_cfg; B.row_off = a.d_row_off;
+  B.fexp = cb.d_fexp; B.zc = cb.d_zc; B.zf = cb.d_zf; B.rn_out = cb.d_rn;
   ChainDev C;
   C.S = cm.S; C.SP = cm.SP; C.c_miss = plan.c_miss;
   C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
@@ -1700,7 +1744,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   const bool dense = cm.dense;   // |I| > 64: per-slice GEMMs (dense.cu) + dense_stats
   const size_t tab = (size_t)plan.n_comb * SP;
   // k_chain_stats: two (own, beta) tile stages + posterior tile + `phases` evidence-indexed tables
-  const size_t stats_fixed = sizeof(double) * (6 * 33 * (SP + 4) + 3 * 34 + 1 + tab) + 3 * 34 * sizeof(int) + 16;
+  const size_t stats_fixed = sizeof(double) * (6 * 33 * (SP + 4) + 2 * (3 * 34 + 1) + tab) + 3 * 34 * sizeof(int) + 16;
   int phases = 4;
   while (phases > 1 && stats_fixed + phases * tab * sizeof(double) > 220 * 1024) phases /= 2;
   if (!dense && stats_fixed + phases * tab * sizeof(double) > 220 * 1024) return NIPGPU_EUNSUPPORTED;
@@ -1727,6 +1771,8 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   if (!cb.d_rt) {
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_rt, rows * SP * sizeof(double)));
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_hvec, rows * sizeof(double)));
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_rn, rows * sizeof(double)));
+    NIPGPU_CUDA(cudaMemsetAsync(cb.d_rn, 0, rows * sizeof(double), st));
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_first, rows));
     NIPGPU_CUDA(cudaMalloc((void**)&cb.d_r0, (size_t)std::max(a.n_series, 1) * SP * sizeof(double)));
     NIPGPU_CUDA(cudaMemsetAsync(cb.d_first, 0, rows, st));
@@ -1759,6 +1805,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   ChainBatchDev B;
   B.n_series = a.n_series; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
   B.cfg = cb.d_cfg; B.row_off = a.d_row_off;
+  B.fexp = cb.d_fexp; B.zc = cb.d_zc; B.zf = cb.d_zf; B.rn_out = cb.d_rn;
   ChainDev C;
   C.S = S; C.SP = SP; C.c_miss = plan.c_miss;
   C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;

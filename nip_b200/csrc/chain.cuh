@@ -65,6 +65,12 @@ struct ChainBatch {
   int* d_len_sorted = nullptr;
   int* d_cfg = nullptr;            // [rows] combined evidence index per data row
   double* d_alpha = nullptr;       // [rows][SP], same row order as the API
+  // scale bookkeeping of the warp-pair kernels: binary exponent carried by every stored forward
+  // row, and per series the sum of its last forward row with that row's exponent
+  int* d_fexp = nullptr;           // [rows]
+  double* d_zc = nullptr;          // [n_series]
+  int* d_zf = nullptr;             // [n_series]
+  double* d_rn = nullptr;          // [rows] E-step: 1 / (forward row . beta row), from the bookkeeping
   double* d_lam_static = nullptr;  // [SP] product of the inactive real leaves' no-evidence rows
   double* d_comb = nullptr;        // [n_comb][SP] combined evidence table of the cached plan
   size_t comb_cap = 0;

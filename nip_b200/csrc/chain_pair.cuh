@@ -135,6 +135,24 @@ __device__ __forceinline__ double pow2_rescale(int maxhi, bool& need) {
   return need ? __hiloint2double((2046 - e) << 20, 0) : 1.0;
 }
 
+// 4-byte read-only load that stays where it is written (see ldg_pinned in chain.cu)
+__device__ __forceinline__ int ldg_pinned_int(const int* p, bool on) {
+  int v = 0;
+  if (on) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// exponent the rescale adds to the vector's (0 when none is needed)
+__device__ __forceinline__ int pow2_rescale_exp(int maxhi) {
+  const int e = (maxhi >> 20) & 0x7ff;
+  return (e != 0 && (e < 1023 - 60 || e > 1023 + 60)) ? 1023 - e : 0;
+}
+// 2^k as a double, k clamped to the normal range
+__device__ __forceinline__ double pow2_double(int k) {
+  k = k < -1000 ? -1000 : (k > 1000 ? 1000 : k);
+  return __hiloint2double((1023 + k) << 20, 0);
+}
+
 // m <= 0 / m == 0 for a finite double, on the integer pipe
 __device__ __forceinline__ bool le_zero(double m) {
   const int hi = __double2hiint(m), lo = __double2loint(m);
@@ -211,6 +229,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
     mine[n][1] = C.phi0[8 * (t0 + n) + 2 * q + 1] * lam[n][1];
   }
   double m1n = C.m1_0;     // m1 of the slice being settled, times the common factor of its m2
+  int ea = 0;              // binary exponent the vector being settled carries (sum of the rescales)
   bool noev_p = c_cur == C.c_miss, on_p = T > 0;
 
   // Side work of one sweep.  Part A (first quarter of the slots) touches only the own half of the
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
   constexpr int B_F = B_FILT + NH;            // 1 item   : rescale (rare)
   constexpr int WB = B_F + 1;
   double pa[2], da[2], part_c = 0, part_d = 0, their_c = 0, their_d = 0, cs = 0, ds = 0, cinv = 1.0, fscale = 1.0;
-  int s_slice = 0, par = 0, mx = 0;
+  int s_slice = 0, par = 0, mx = 0, fk = 0;
   bool need = false, scaled = false;
   auto item_a = [&](auto wc) {
     constexpr int w = decltype(wc)::value;
@@ -258,6 +277,9 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
     } else if constexpr (w >= A_ST && w < A_EXP) {
       constexpr int n = w - A_ST;
       if (on_p) reinterpret_cast<double2*>(alpha + (row0 + s_slice) * SP)[4 * (t0 + n) + q] = make_double2(mine[n][0], mine[n][1]);
+      if constexpr (n == 0) {
+        if (on_p && q == 0 && h == 0) B.fexp[row0 + s_slice] = ea;
+      }
     } else if constexpr (w == A_EXP) {
       mx = 0;
 #pragma unroll
@@ -288,6 +310,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
     } else if constexpr (w == B_EXP + 2) {
       mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       fscale = pow2_rescale(mx, need);
+      fk = pow2_rescale_exp(mx);
     } else if constexpr (w == B_RED) {
       if constexpr (SUMS) cs = part_c + their_c;    // the same two numbers in both warps: a + b == b + a
     } else if constexpr (w == B_RED + 1) {
@@ -342,6 +365,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
 #pragma unroll
       for (int n = 0; n < NH; n++) { mine[n][0] *= fscale; mine[n][1] *= fscale; }
     }
+    ea += fk;       // exponent of the vector of slice t
     c_cur = c_next;
     load_lam(c_cur, t + 1 < T);     // evidence row of slice t+1
     if (t + 2 < T) c_next = __ldg(cfg + t + 2);
@@ -361,8 +385,9 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
 
 // --------------------------------------------------------------- backward ---
 // beta_{t-1} = f_t A (lambda_t * beta_t) with f_t an exact power of two (1 almost always);
-// posterior of slice t = normalise(alpha_t * beta_t).  Exchange record: the own half of
-// r_t = lambda_t * beta_t (the sweep's A operand) and the own half of sum(alpha_t * beta_t).
+// posterior of slice t = alpha_t * beta_t / (alpha_t . beta_t), the normaliser from the scale
+// bookkeeping (no sum, no reciprocal per slice).  Exchange record: the own half of
+// r_t = lambda_t * beta_t (the sweep's A operand).
 // EM variant: stores the carried beta_t (rt[t]) and f_t (hvec[t]) instead of posteriors, and
 // r_0 / (phi0 . r_0) per series; see k_chain_backward and k_chain_stats.
 template <int NT, bool VEC, bool EM>
@@ -414,19 +439,26 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
   for (int n = 0; n < NH; n++) beta[n][0] = beta[n][1] = 1.0;
   int c_pre = (Tw >= 2 && Tw - 2 < T) ? cfg[Tw - 2] : 0;
 
-  constexpr int A_MUL = 0;                    // NH items : a = alpha_t * beta_t (own half), partial sum
-  constexpr int A_X = A_MUL + NH;             // NH + 1   : exchange record (r half, the partial)
-  constexpr int A_EXP = A_X + NH + 1;         // 1 item   : largest exponent of the own half of r
-  constexpr int WA = A_EXP + 1;
+  // The normaliser of the posterior needs no sum: forward row . beta row = Z 2^(Fa_t + Fb_t) for
+  // every t, with Z = sum of the last forward row / 2^(its exponent) (k_chain_final) and Fa / Fb
+  // the exponents the two recursions have put on their vectors.
+  const double rbase = safe_rcp(valid ? B.zc[orig] : 0.0);
+  const int zf = valid ? B.zf[orig] : 0;
+  int eb = 0;                                 // exponent carried by beta_t
+  int fa_cur = has_last ? B.fexp[row0 + Tw - 1] : 0, fa_nxt = 0, fa_pre = 0;   // exponents of the forward rows t, t-1, t-2
+
+  constexpr int A_MUL = 0;                    // NH items : a = alpha_t * beta_t (own half)
+  constexpr int A_X = A_MUL + NH;             // NH items : exchange record (r half)
+  constexpr int A_EXP = A_X + NH;             // 1 item   : largest exponent of the own half of r
+  constexpr int A_RN = A_EXP + 1;             // 1 item   : 1 / (alpha_t . beta_t)
+  constexpr int WA = A_RN + 1;
   constexpr int B_EXP = 0;                    // 3 items  : largest exponent of r, the power of two
-  constexpr int B_RED = B_EXP + 3;            // 3 items  : posterior normaliser
-  constexpr int B_INV = B_RED + 3;            // 1 item
-  constexpr int B_ST = B_INV + 1;             // NH items : posterior of slice t / the carried beta (EM)
+  constexpr int B_ST = B_EXP + 3;             // NH items : posterior of slice t / the carried beta (EM)
   constexpr int B_LD = B_ST + NH;             // NH items : alpha_{t-1} (prefetched) -> a
-  constexpr int B_F = B_LD + NH;              // 1 item   : rescale (rare), h of the E-step
+  constexpr int B_F = B_LD + NH;              // 1 item   : rescale vote, scalars of the E-step
   constexpr int WB = B_F + 1;
-  double ps[2], part_p = 0, their_p = 0, psum = 0, pinv = 1.0, fscale = 1.0;
-  int t_cur = 0, par = 0, mx = 0;
+  double pinv = 1.0, fscale = 1.0;
+  int t_cur = 0, par = 0, mx = 0, fk = 0;
   bool on = false, first_next = false, need = false, scaled = false;
   auto item_a = [&](auto wc) {
     constexpr int w = decltype(wc)::value;
@@ -435,21 +467,16 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
         constexpr int n = w - A_MUL;
         a[n][0] *= beta[n][0];
         a[n][1] *= beta[n][1];
-        if constexpr (n == 0) { ps[0] = a[n][0]; ps[1] = a[n][1]; }
-        else { ps[0] += a[n][0]; ps[1] += a[n][1]; }
       }
-    } else if constexpr (w >= A_X && w < A_X + NH) {
+    } else if constexpr (w >= A_X && w < A_EXP) {
       constexpr int n = w - A_X;
       xw(par)[n << 5] = make_double2(r[n][0], r[n][1]);
-    } else if constexpr (w == A_X + NH) {
-      if constexpr (!EM) {
-        part_p = ps[0] + ps[1];
-        xw(par)[NH << 5] = make_double2(part_p, 0.0);
-      }
     } else if constexpr (w == A_EXP) {
       mx = 0;
 #pragma unroll
       for (int n = 0; n < NH; n++) mx = max(mx, max(hi_word(r[n][0]), hi_word(r[n][1])));
+    } else if constexpr (w == A_RN) {
+      pinv = rbase * pow2_double(zf - fa_cur - eb);
     }
   };
   auto mid = [&]() {
@@ -460,7 +487,6 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
       rth[n][0] = v.x;
       rth[n][1] = v.y;
     }
-    if constexpr (!EM) their_p = xr(par)[NH << 5].x;
   };
   auto item_b = [&](auto wc) {
     constexpr int w = decltype(wc)::value;
@@ -472,15 +498,8 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
     } else if constexpr (w == B_EXP + 2) {
       mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       fscale = pow2_rescale(mx, need);
-      if (first_next) { fscale = 1.0; need = false; }   // slice t-1 restarts this row with beta = 1
-    } else if constexpr (w == B_RED) {
-      if constexpr (!EM) psum = part_p + their_p;
-    } else if constexpr (w == B_RED + 1) {
-      if constexpr (!EM) psum += __shfl_xor_sync(0xffffffffu, psum, 1);
-    } else if constexpr (w == B_RED + 2) {
-      if constexpr (!EM) psum += __shfl_xor_sync(0xffffffffu, psum, 2);
-    } else if constexpr (w == B_INV) {
-      if constexpr (!EM) pinv = safe_rcp(psum);
+      fk = pow2_rescale_exp(mx);
+      if (first_next) { fscale = 1.0; need = false; fk = 0; }   // slice t-1 restarts this row with beta = 1
     } else if constexpr (w >= B_ST && w < B_LD) {
       constexpr int n = w - B_ST;
       if constexpr (EM) {  // E-step: the carried beta_t itself
@@ -501,10 +520,14 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
         a[n][0] = an[n][0];
         a[n][1] = an[n][1];
       }
+      if constexpr (w == B_LD) fa_cur = fa_nxt;   // requested a sweep ago, like alpha_{t-1}
     } else if constexpr (w == B_F) {
       scaled = __any_sync(0xffffffffu, need);   // a vote, no branch inside the sweep
       if constexpr (EM) {
-        if (on && q == 0 && h == 0) hvec[row0 + t_cur] = fscale;
+        if (on && q == 0 && h == 0) {
+          hvec[row0 + t_cur] = fscale;
+          B.rn_out[row0 + t_cur] = pinv;
+        }
       }
     }
   };
@@ -519,6 +542,8 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
     const bool p0 = Tw >= 2 && Tw - 2 < T;
     load_half(C.lam_comb + (long long)c_pre * SP, p0, lam);
     if (!EM) load_half(alpha + (row0 + Tw - 2) * SP, p0, an);
+    fa_nxt = p0 ? B.fexp[row0 + Tw - 2] : 0;
+    fa_pre = ldg_pinned_int(B.fexp + row0 + Tw - 3, Tw >= 3 && Tw - 3 < T);
     if (Tw >= 3 && Tw - 3 < T) c_pre = __ldg(cfg + Tw - 3);
   }
   for (int t = Tw - 1; t >= 1; t--) {
@@ -542,10 +567,13 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
         r[n][0] *= fscale; r[n][1] *= fscale;
       }
     }
+    eb = first_next ? 0 : eb + fk;   // exponent of beta_{t-1}
     {  // requests for iteration t-1: lambda_{t-2}, alpha_{t-2}, evidence index of slice t-3
       const bool p2 = t >= 2 && t - 2 < T;
       load_half(C.lam_comb + (long long)c_pre * SP, p2, lam);
       if (!EM) load_half(alpha + (row0 + t - 2) * SP, p2, an);
+      fa_nxt = fa_pre;   // requested a whole iteration ago (a 4-byte load behind the alpha rows' HBM reads takes that long)
+      fa_pre = ldg_pinned_int(B.fexp + row0 + t - 3, t >= 3 && t - 3 < T);
       if (t >= 3 && t - 3 < T) c_pre = __ldg(cfg + t - 3);
     }
   }
@@ -555,7 +583,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
     par = 0;
     static_for<0, WA>(item_a);
     double zpart = 0;
-    if constexpr (EM) {   // the record's partial carries phi0 . r_0 (own half)
+    if constexpr (EM) {   // one more record slot: phi0 . r_0 (own half)
       double z0 = 0, z1 = 0;
 #pragma unroll
       for (int n = 0; n < NH; n++) {
@@ -566,8 +594,9 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
       xw(par)[NH << 5] = make_double2(zpart, 0.0);
     }
     mid();
-    static_for<B_RED, B_LD>(item_b);
+    static_for<B_ST, B_LD>(item_b);
     if constexpr (EM) {
+      if (on && q == 0 && h == 0) B.rn_out[row0] = pinv;
       const double ztheirs = xr(par)[NH << 5].x;
       const double zinv = safe_rcp(quad_sum_full(zpart + ztheirs));
       if (0 < T) {
