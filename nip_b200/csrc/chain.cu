@@ -35,6 +35,8 @@ __host__ __device__ inline int frag_index(int kstate, int nstate, int NT) {
 
 struct ChainDev {
   int S, SP, c_miss;   // c_miss: combined evidence index meaning "no evidence in this slice"
+  int AS;              // doubles per stored forward row: SP, or S rounded up to even when one 8-state
+                       // tile holds the interface (a 4-state model moves 32 B per row, not 64)
   double m1_0;         // mass of the evidence-free first slice
   const double *Bf1, *Bb1, *Bb0, *phi0, *lam0, *R1, *colsum, *lam_comb;
 };
@@ -308,7 +310,9 @@ __global__ void __launch_bounds__(128, 1) k_chain_forward(ChainDev C, ChainBatch
       if (FILT) cinv = safe_rcp(cs);
     } else if constexpr (w >= I_ST && w < I_DOT) {
       constexpr int n = w - I_ST;
-      if (on_p) reinterpret_cast<double2*>(alpha + (row0 + s_slice) * SP)[4 * n + q] = make_double2(own[n][0], own[n][1]);
+      const int AS = NT == 1 ? C.AS : SP;
+      if (on_p && (NT > 1 || 2 * q < AS))
+        reinterpret_cast<double2*>(alpha + (row0 + s_slice) * AS)[4 * n + q] = make_double2(own[n][0], own[n][1]);
       if (FILT) {  // filtering: the forward marginal of I_s is alpha_s = own / c
         double* prow = post + (row0 + s_slice) * post_stride + post_off;
         const int col = 8 * n + 2 * q;
@@ -413,6 +417,8 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   const double* frag = sB + (NT >= 2 ? 2 * lane : lane);
   const double2* csv = reinterpret_cast<const double2*>(s_cs);
   double beta[NT][2], r[NT][2], lam[NT][2], a[NT][2], an[NT][2], u[NT][2];
+  const int AS = NT == 1 ? C.AS : SP;                 // stride of the stored forward rows
+  const bool arow = NT > 1 || 2 * q < AS;             // this lane's pair of states exists in them
   auto load_row = [&](const double* base, bool on, double (&dst)[NT][2]) {
     const double2* p = reinterpret_cast<const double2*>(base);
 #pragma unroll
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   // prologue: the longest rows start at slice Tw-1 with beta = 1, r = lambda
   const bool has_last = Tw >= 1 && Tw - 1 < T;
   load_row(C.lam_comb + (long long)(has_last ? cfg[Tw - 1] : 0) * SP, has_last, r);
-  if (!EM) load_row(alpha + (row0 + Tw - 1) * SP, has_last, a);
+  if (!EM) load_row(alpha + (row0 + Tw - 1) * AS, has_last && arow, a);
 #pragma unroll
   for (int n = 0; n < NT; n++) beta[n][0] = beta[n][1] = 1.0;
   int c_pre = (Tw >= 2 && Tw - 2 < T) ? cfg[Tw - 2] : 0;
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
   {
     const bool p0 = Tw >= 2 && Tw - 2 < T;
     load_row(C.lam_comb + (long long)c_pre * SP, p0, lam);
-    if (!EM) load_row(alpha + (row0 + Tw - 2) * SP, p0, an);
+    if (!EM) load_row(alpha + (row0 + Tw - 2) * AS, p0 && arow, an);
     if (Tw >= 3 && Tw - 3 < T) c_pre = __ldg(cfg + Tw - 3);
   }
   for (int t = Tw - 1; t >= 1; t--) {
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
     {  // requests for iteration t-1: lambda_{t-2}, alpha_{t-2}, evidence index of slice t-3
       const bool p2 = t >= 2 && t - 2 < T;
       load_row(C.lam_comb + (long long)c_pre * SP, p2, lam);
-      if (!EM) load_row(alpha + (row0 + t - 2) * SP, p2, an);
+      if (!EM) load_row(alpha + (row0 + t - 2) * AS, p2 && arow, an);
       if (t >= 3 && t - 3 < T) c_pre = __ldg(cfg + t - 3);
     }
   }
@@ -586,7 +592,7 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
                   const int* __restrict__ cfg, const unsigned char* __restrict__ first,
                   const double* __restrict__ lam_comb, long long rows, int n_comb, int phases,
                   double* __restrict__ partG, double* __restrict__ partC,
-                  const double* __restrict__ rnv) {
+                  const double* __restrict__ rnv, int own_stride) {
   // rnv[k] = 1 / (own_k . beta_k) when the producing kernels know it from their scale bookkeeping
   // (warp-pair kernels); nullptr: the dot products are formed here
   // NT m-tiles x GR halves of the n-tiles: 2 NT warps keep four warps on every scheduler
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(32 * NT * (NT >= 2 ? 2 : 1), 1)
       for (int c = 0; c < CW; c++) {
         const int col = lane + 32 * c;
         const bool ok = okr && col < SP;
-        ro[u][c] = ok ? __ldg(own + k * SP + col) : 0.0;
+        ro[u][c] = (ok && col < own_stride) ? __ldg(own + k * own_stride + col) : 0.0;
         rb[u][c] = ok ? __ldg(bt + k * SP + col) : 0.0;
       }
     }
@@ -1013,7 +1019,7 @@ int launch_em(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a
   if (int e = set_smem(k_chain_stats<NT>, s.smem)) return e;
   k_chain_stats<NT><<<s.parts, 32 * NT * (NT >= 2 ? 2 : 1), s.smem, st>>>(alpha, s.bt, s.hv, B.cfg, s.first, C.lam_comb, s.rows,
                                                       s.n_comb, s.phases, s.partG, s.partC,
-                                                      paired ? B.rn_out : nullptr);
+                                                      paired ? B.rn_out : nullptr, NT == 1 ? C.AS : C.SP);
   NIPGPU_LAUNCHED();
   return NIPGPU_OK;
 }
@@ -1376,6 +1382,7 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   B.fexp = cb.d_fexp; B.zc = cb.d_zc; B.zf = cb.d_zf; B.rn_out = cb.d_rn;
   ChainDev C;
   C.S = cm.S; C.SP = cm.SP; C.c_miss = plan.c_miss;
+  C.AS = cm.NT == 1 ? std::max(2, 2 * ((cm.S + 1) / 2)) : cm.SP;
   C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
   C.R1 = cm.d_R1; C.colsum = cm.d_colsum; C.m1_0 = cm.m1_0; C.lam_comb = cb.d_comb;
   if (a.n_series == 0) return NIPGPU_OK;
@@ -1808,6 +1815,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   B.fexp = cb.d_fexp; B.zc = cb.d_zc; B.zf = cb.d_zf; B.rn_out = cb.d_rn;
   ChainDev C;
   C.S = S; C.SP = SP; C.c_miss = plan.c_miss;
+  C.AS = cm.NT == 1 ? std::max(2, 2 * ((S + 1) / 2)) : SP;
   C.Bf1 = cm.d_Bf1; C.Bb1 = cm.d_Bb1; C.Bb0 = cm.d_Bb0; C.phi0 = cm.d_phi0; C.lam0 = cm.d_lam0;
   C.R1 = cm.d_R1; C.colsum = cm.d_colsum; C.m1_0 = cm.m1_0; C.lam_comb = cb.d_comb;
   NIPGPU_CUDA(cudaMemsetAsync(cb.d_r0, 0, (size_t)std::max(a.n_series, 1) * SP * sizeof(double), st));

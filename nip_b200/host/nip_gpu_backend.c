@@ -378,6 +378,83 @@ int nip_gpu_smooth_set(time_series* set, int n, nip_variable vars[], int nvars, 
   return rc == NIPGPU_OK ? NIP_NO_ERROR : NIP_ERROR_GENERAL;
 }
 
+/* ---- packed data file -> device batch ---------------------
+ * A set written by nip_gpu_write_timeseries_bin() (nip_data_bin.c) goes from the file to HBM in
+ * one bulk read and one upload: no time_series structs, no per-row allocation, none of
+ * read_timeseries()'s two tokenising passes (src/nip.c:512-667).  Results come back flat:
+ *   *post     malloc'ed, sum(lengths) rows x (sum of card(vars)) doubles, series after series
+ *   *loglik   malloc'ed, one value per series (NULL argument: not wanted)
+ *   *lengths  malloc'ed, slices per series;  return value = number of series, 0 on error
+ * Every column of the file must name a variable of the model. */
+int nip_gpu_smooth_bin(nip_model model, const char* filename, nip_variable vars[], int nvars, int forward_only,
+                       double** post, double** loglik, int** lengths) {
+  backend_entry* e;
+  FILE* f;
+  char magic[4];
+  int32_t version = 0, n = 0, n_cols = 0, *len = NULL, *col = NULL, *data = NULL, *q = NULL;
+  unsigned char* mask = NULL;
+  nipgpu_batch* b = NULL;
+  double *P = NULL, *L = NULL;
+  long rows = 0;
+  int k, s, row = 0, ok, rc = NIPGPU_EINVAL;
+  if (!model || !filename || !post || !lengths || (nvars > 0 && !vars)) { report(__FILE__, __LINE__, NIP_ERROR_INVALID_ARGUMENT); return 0; }
+  *post = NULL; *lengths = NULL;
+  if (loglik) *loglik = NULL;
+  e = backend_for(model, 1);
+  if (!e) { report(__FILE__, __LINE__, NIP_ERROR_GENERAL); return 0; }
+  f = fopen(filename, "rb");
+  if (!f) { report(__FILE__, __LINE__, NIP_ERROR_GENERAL); return 0; }
+  ok = fread(magic, 1, 4, f) == 4 && memcmp(magic, "NIPB", 4) == 0 && fread(&version, 4, 1, f) == 1 && version == 1 &&
+       fread(&n, 4, 1, f) == 1 && fread(&n_cols, 4, 1, f) == 1 && n > 0 && n_cols >= 0;
+  if (ok) {
+    col = (int32_t*)calloc((size_t)(n_cols > 0 ? n_cols : 1), sizeof(int32_t));
+    len = (int32_t*)calloc((size_t)n, sizeof(int32_t));
+    ok = col && len;
+  }
+  for (k = 0; ok && k < n_cols; k++) {   /* column symbols -> model variables */
+    int32_t l = 0;
+    char sym[4096];
+    nip_variable v;
+    ok = fread(&l, 4, 1, f) == 1 && l >= 0 && l < (int32_t)sizeof(sym) && fread(sym, 1, (size_t)l, f) == (size_t)l;
+    if (!ok) break;
+    sym[l] = 0;
+    v = model_variable(model, sym);
+    ok = v != NULL;
+    if (ok) col[k] = nipgpu_var_index(model, v);
+  }
+  ok = ok && fread(len, 4, (size_t)n, f) == (size_t)n;
+  for (s = 0; ok && s < n; s++) { ok = len[s] >= 0; rows += len[s]; }
+  if (ok) {
+    const size_t cells = (size_t)rows * (size_t)n_cols;
+    data = (int32_t*)malloc(sizeof(int32_t) * (cells > 0 ? cells : 1));
+    ok = data && fread(data, 4, cells, f) == cells;   /* the whole set in one read */
+  }
+  fclose(f);
+  if (ok) {
+    q = (int32_t*)calloc((size_t)(nvars > 0 ? nvars : 1), sizeof(int32_t));
+    for (k = 0; q && k < nvars; k++) { q[k] = nipgpu_var_index(model, vars[k]); row += NIP_CARDINALITY(vars[k]); }
+    mask = marked_mask(model);
+    P = (double*)malloc(sizeof(double) * (size_t)((long)rows * row > 0 ? (long)rows * row : 1));
+    L = loglik ? (double*)malloc(sizeof(double) * (size_t)n) : NULL;
+    ok = q && mask && P && (!loglik || L);
+  }
+  if (ok) {
+    rc = nipgpu_batch_create(e->gm[0], n, len, n_cols, col, data, &b);
+    if (rc == NIPGPU_OK) rc = nipgpu_infer(e->gm[0], b, mask, nvars, q, forward_only, nvars > 0 ? P : NULL, L);
+    if (rc != NIPGPU_OK) report_device_error();
+    nipgpu_batch_destroy(b);
+  }
+  free(col); free(data); free(q); free(mask);
+  if (!ok || rc != NIPGPU_OK) {
+    free(len); free(P); free(L);
+    report(__FILE__, __LINE__, NIP_ERROR_GENERAL);
+    return 0;
+  }
+  *post = P; *lengths = len;
+  if (loglik) *loglik = L;
+  return n;
+}
+
 /* ---- transparent batching -----------------------------
  * util/nipinference.c:125-129 and util/nipmap.c:139-145 call the smoother once per
  * series of a set they read with read_timeseries().  A registered set is smoothed

@@ -444,6 +444,43 @@ def test_niplikelihood_nipjoint_nipmap_on_the_gpu_backend(gpu_lib, tmp_path):
     assert differ <= 2, "MAP states differ in %d rows (only exact posterior ties may)" % differ
 
 
+def test_packed_file_straight_into_a_batch(libs, tmp_path):
+    """a set written by nip_gpu_write_timeseries_bin() is smoothed straight
+    from the file (one bulk read, one upload, no time_series structs) — same posteriors and
+    log-likelihoods as the reference computes on the series it was written from"""
+    ref, gpu = libs
+    gpu.nip_gpu_write_timeseries_bin.argtypes = [vp, i32, C.c_char_p]
+    gpu.nip_gpu_smooth_bin.argtypes = [vp, C.c_char_p, vp, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    h = HmmSpec(11, 6, seed=19)
+    p = tmp_path / "f.net"
+    p.write_text(h.net_text())
+    model = ref.parse(p)
+    data = h.sample(9, 14, seed=6, missing=0.1)
+    series = [data[i, :4 + i] for i in range(9)]
+    ts = [model.timeseries(h.obs_vars, s) for s in series]
+    arr = (vp * len(ts))(*ts)
+    path = str(tmp_path / "set.bin").encode()
+    assert gpu.nip_gpu_write_timeseries_bin(arr, len(ts), path) == 0
+    post, ll, lens = vp(), vp(), vp()
+    n = gpu.nip_gpu_smooth_bin(model.h, path, _vars(ref, model, [1, 0]), 2, 0, C.byref(post), C.byref(ll), C.byref(lens))
+    assert n == 9
+    L = np.ctypeslib.as_array(C.cast(lens, C.POINTER(C.c_int32)), (n,))
+    assert list(L) == [len(s) for s in series]
+    P = np.ctypeslib.as_array(C.cast(post, C.POINTER(f64)), (int(L.sum()), 11 + 6))
+    LL = np.ctypeslib.as_array(C.cast(ll, C.POINTER(f64)), (n,))
+    r0 = 0
+    for i, t in enumerate(ts):
+        want, ll_want = model.infer(t, [1, 0])
+        assert_close(P[r0:r0 + L[i]], want, "series %d from the packed file" % i)
+        assert_close(LL[i], ll_want, "series %d loglikelihood" % i)
+        r0 += L[i]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [vp]
+    for x in (post, ll, lens):
+        libc.free(x)
+    gpu.nip_gpu_release(model.h)
+
+
 def test_generate_set_dropin(libs, tmp_path):
     """nip_gpu_generate_set(): a whole set of fully observed series drawn on the device, usable by
     the reference's own code (here: its smoother reproduces the sampled hidden states when every
