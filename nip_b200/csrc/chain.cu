@@ -908,30 +908,67 @@ __global__ void k_chain_final(const double* __restrict__ alpha, const int* __res
   }
 }
 
-// NT = 4 / 8: every 8-sequence group on a pair of warps of one scheduler (chain_pair.cuh);
-// NIPGPU_CHAIN_PAIR=0 keeps the one-warp kernels (A/B timing)
-static bool use_pair(int NT) {
-  static const bool on = [] { const char* e = getenv("NIPGPU_CHAIN_PAIR"); return !(e && e[0] == '0'); }();
-  return on && (NT == 4 || NT == 8);
+#ifndef NIPGPU_TEAM4_MAX_SERIES
+#define NIPGPU_TEAM4_MAX_SERIES 3072
+#endif
+// NT = 4 / 8: every 8-sequence group on a team of warps (chain_pair.cuh): two warps of one
+// scheduler, or (8 state tiles) four warps on the SM's four schedulers.  NIPGPU_CHAIN_PAIR=0
+// keeps the one-warp kernels, NIPGPU_CHAIN_TEAM=2|4 forces the team width (A/B timing).
+static int team_width(int NT, int n_series) {
+  static const int forced = [] {
+    const char* p = getenv("NIPGPU_CHAIN_PAIR");
+    if (p && p[0] == '0') return 1;
+    const char* e = getenv("NIPGPU_CHAIN_TEAM");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 1 || (NT != 4 && NT != 8)) return 1;
+  if (NT == 4) return 2;
+  if (forced == 2 || forced == 4) return forced;
+  // measured on C2's model (profiles/r02_team_width.txt): four warps on four schedulers take
+  // 1.50 / 1.55 / 2.01 / 3.40 ms per smoothing pass of 512 / 1024 / 2048 / 4096 sequences, two
+  // warps on one scheduler 2.79 ms for any batch up to one group per scheduler (4736 sequences)
+  return n_series <= NIPGPU_TEAM4_MAX_SERIES ? 4 : 2;
+}
+template <int NT, int W>
+static int team_grid(int n_series) {
+  const int groups = (n_series + 7) / 8;
+  return (groups + TeamGeom<NT, W>::TEAMS - 1) / TeamGeom<NT, W>::TEAMS;
+}
+
+// runs f(std::integral_constant<int, W>) for the team width chosen for NT; false: one-warp kernels
+template <int NT, class F>
+static bool with_team(int n_series, F&& f, int* err) {
+  if constexpr (NT == 4 || NT == 8) {
+    const int w = team_width(NT, n_series);
+    if (w == 2) { *err = f(std::integral_constant<int, 2>{}); return true; }
+    if constexpr (NT == 8) {
+      if (w == 4) { *err = f(std::integral_constant<int, 4>{}); return true; }
+    }
+  }
+  return false;
 }
 
 template <int NT, bool FILT, bool WLL>
 int launch_forward_v(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a, double* alpha,
                      cudaStream_t st) {
-  if constexpr (NT == 4 || NT == 8) {
-    if (use_pair(NT)) {
-      const size_t smem = PairGeom<NT>::smem_bytes();
-      if (int e = set_smem(k_chain_forward_pair<NT, FILT, WLL>, smem)) return e;
-      k_chain_forward_pair<NT, FILT, WLL><<<(B.n_series + 31) / 32, 256, smem, st>>>(
-          C, B, alpha, a.d_post, a.post_stride, a.post_off, a.d_ll, a.d_status);
-      NIPGPU_LAUNCHED();
-      if (!FILT && B.n_series > 0) {   // a backward pass follows: its normalisers
-        k_chain_final<<<(B.n_series + 7) / 8, 256, 0, st>>>(alpha, B.fexp, B.row_off, B.order, B.len_sorted,
-                                                          B.n_series, C.SP, B.zc, B.zf);
-        NIPGPU_LAUNCHED();
-      }
-      return NIPGPU_OK;
-    }
+  {
+    int err = NIPGPU_OK;
+    if (with_team<NT>(B.n_series, [&](auto wc) -> int {
+          constexpr int W = decltype(wc)::value;
+          using G = TeamGeom<NT, W>;
+          const size_t smem = G::smem_bytes();
+          if (int e = set_smem(k_chain_forward_team<NT, W, FILT, WLL>, smem)) return e;
+          k_chain_forward_team<NT, W, FILT, WLL><<<team_grid<NT, W>(B.n_series), G::THREADS, smem, st>>>(
+              C, B, alpha, a.d_post, a.post_stride, a.post_off, a.d_ll, a.d_status);
+          NIPGPU_LAUNCHED();
+          if (!FILT && B.n_series > 0) {   // a backward pass follows: its normalisers
+            k_chain_final<<<(B.n_series + 7) / 8, 256, 0, st>>>(alpha, B.fexp, B.row_off, B.order, B.len_sorted,
+                                                              B.n_series, C.SP, B.zc, B.zf);
+            NIPGPU_LAUNCHED();
+          }
+          return NIPGPU_OK;
+        }, &err))
+      return err;
   }
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
   if (int e = set_smem(k_chain_forward<NT, FILT, WLL>, smem)) return e;
@@ -958,21 +995,26 @@ int launch_backward(const ChainDev& C, const ChainBatchDev& B, const ChainInferA
   const int grid = (B.n_series + 31) / 32;
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
   const bool vec = ((a.post_stride | a.post_off) & 1) == 0 && C.S == C.SP;
-  if constexpr (NT == 4 || NT == 8) {
-    if (use_pair(NT)) {
-      const size_t psm = PairGeom<NT>::smem_bytes();
-      if (vec) {
-        if (int e = set_smem(k_chain_backward_pair<NT, true, false>, psm)) return e;
-        k_chain_backward_pair<NT, true, false><<<grid, 256, psm, st>>>(C, B, alpha, a.d_post, a.post_stride,
-                                                                       a.post_off, nullptr, nullptr, nullptr);
-      } else {
-        if (int e = set_smem(k_chain_backward_pair<NT, false, false>, psm)) return e;
-        k_chain_backward_pair<NT, false, false><<<grid, 256, psm, st>>>(C, B, alpha, a.d_post, a.post_stride,
-                                                                        a.post_off, nullptr, nullptr, nullptr);
-      }
-      NIPGPU_LAUNCHED();
-      return NIPGPU_OK;
-    }
+  {
+    int err = NIPGPU_OK;
+    if (with_team<NT>(B.n_series, [&](auto wc) -> int {
+          constexpr int W = decltype(wc)::value;
+          using G = TeamGeom<NT, W>;
+          const size_t psm = G::smem_bytes();
+          const int tg = team_grid<NT, W>(B.n_series);
+          if (vec) {
+            if (int e = set_smem(k_chain_backward_team<NT, W, true, false>, psm)) return e;
+            k_chain_backward_team<NT, W, true, false><<<tg, G::THREADS, psm, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                                                   a.post_off, nullptr, nullptr, nullptr);
+          } else {
+            if (int e = set_smem(k_chain_backward_team<NT, W, false, false>, psm)) return e;
+            k_chain_backward_team<NT, W, false, false><<<tg, G::THREADS, psm, st>>>(C, B, alpha, a.d_post, a.post_stride,
+                                                                                    a.post_off, nullptr, nullptr, nullptr);
+          }
+          NIPGPU_LAUNCHED();
+          return NIPGPU_OK;
+        }, &err))
+      return err;
   }
   if (vec) {
     if (int e = set_smem(k_chain_backward<NT, true, false>, smem)) return e;
@@ -1002,15 +1044,17 @@ int launch_em(const ChainDev& C, const ChainBatchDev& B, const ChainInferArgs& a
   if (int e = launch_forward_v<NT, false, true>(C, B, a, alpha, st)) return e;
   const int grid = (B.n_series + 31) / 32;
   const size_t smem = sizeof(double) * (64 * NT * NT + 16 * NT);
-  bool paired = false;
-  if constexpr (NT == 4 || NT == 8) {
-    if (use_pair(NT)) {
-      const size_t psm = PairGeom<NT>::smem_bytes();
-      if (int e = set_smem(k_chain_backward_pair<NT, true, true>, psm)) return e;
-      k_chain_backward_pair<NT, true, true><<<grid, 256, psm, st>>>(C, B, alpha, nullptr, C.SP, 0, s.bt, s.r0, s.hv);
-      paired = true;
-    }
-  }
+  int err = NIPGPU_OK;
+  const bool paired = with_team<NT>(B.n_series, [&](auto wc) -> int {
+    constexpr int W = decltype(wc)::value;
+    using G = TeamGeom<NT, W>;
+    const size_t psm = G::smem_bytes();
+    if (int e = set_smem(k_chain_backward_team<NT, W, true, true>, psm)) return e;
+    k_chain_backward_team<NT, W, true, true><<<team_grid<NT, W>(B.n_series), G::THREADS, psm, st>>>(
+        C, B, alpha, nullptr, C.SP, 0, s.bt, s.r0, s.hv);
+    return NIPGPU_OK;
+  }, &err);
+  if (err) return err;
   if (!paired) {
     if (int e = set_smem(k_chain_backward<NT, true, true>, smem)) return e;
     k_chain_backward<NT, true, true><<<grid, 128, smem, st>>>(C, B, alpha, nullptr, C.SP, 0, s.bt, s.r0, s.hv);

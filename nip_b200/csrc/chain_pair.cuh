@@ -65,35 +65,46 @@
 #define NIPGPU_PAIR_BWD_B_END NIPGPU_PAIR_B_END
 #endif
 
-template <int NT>
-struct PairGeom {
-  static constexpr int SP = 8 * NT, NH = NT / 2;
+// W = 2: the two warps of a team sit on ONE scheduler (warps p and p + 4 of an 8-warp CTA, four
+//        teams per CTA); they fill each other's bubbles on that scheduler's pipe.
+// W = 4: the four warps of a team sit on the FOUR schedulers of an SM (a CTA is one team); a
+//        group's slice then takes a quarter of the tensor time, which is what a small batch
+//        needs (one group per SM still uses all four pipes), and a large batch puts four
+//        CTAs on an SM, i.e. four warps of four independent teams on every scheduler.
+template <int NT, int W>
+struct TeamGeom {
+  static constexpr int SP = 8 * NT, NH = NT / W;   // NH state tiles per warp
+  static constexpr int TEAMS = W == 2 ? 4 : 1;     // teams per CTA
+  static constexpr int THREADS = 32 * W * TEAMS;
   static constexpr int NS = 2 * NT * NH;           // tensor instructions (= side slots) per warp and sweep
-  static constexpr int MID = NS / 4;               // slot after which the partner's half is fetched
-  static constexpr int REC = NH + 1;               // double2 per lane in the exchange record: half + two partial sums
-  // exchange area in double2: [pair 4][parity 2][half 2][REC][32 lanes]
-  static constexpr int XCH = 4 * 2 * 2 * REC * 32;
+  static constexpr int OWN = 2 * NH * NH;          // of which on the warp's own part of the vector
+  static constexpr int MID = OWN / 2;              // slot after which the other parts are fetched
+  static constexpr int REC = NH + 1;               // double2 per lane in the exchange record: part + two partial sums
+  // exchange area in double2: [team][parity 2][part W][REC][32 lanes]
+  static constexpr int XCH = TEAMS * 2 * W * REC * 32;
   static size_t smem_bytes() { return sizeof(double) * (SP * SP + SP) + sizeof(double2) * XCH; }
 };
 
-__device__ __forceinline__ void pair_barrier(int pair) {
-  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+template <int W>
+__device__ __forceinline__ void team_barrier(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(32 * W) : "memory");
 }
 
-// acc[n] (tile h NH + n) = sum over all 2 NT k-steps; the k-steps of the own half first.
-//   fa / fb   B fragments of this warp's n-tiles for the own / the partner's k-steps
-//             (double2 pointers, lane already added)
+// acc[n] (tile h NH + n) = sum over all 2 NT k-steps; the k-steps of the warp's own part first,
+// then the other parts in the order h+1, h+2, ... (mod W).
+//   fp[i]     B fragments of this warp's n-tiles for the k-steps of part i (double2 pointers,
+//             lane already added)
 //   side(slot) after every tensor instruction; side(MID) must have filled `theirs`
-template <int NT, class Side>
-__device__ __forceinline__ void pair_sweep(double (&acc)[NT / 2][2], const double (&mine)[NT / 2][2],
-                                           const double (&theirs)[NT / 2][2], const double2* fa,
-                                           const double2* fb, Side side) {
-  constexpr int NH = NT / 2, H2 = NH / 2;          // H2 double2 loads bring the B fragments of a k-step
+template <int NT, int W, class Side>
+__device__ __forceinline__ void team_sweep(double (&acc)[NT / W][2], const double (&mine)[NT / W][2],
+                                           const double (&theirs)[W - 1][NT / W][2],
+                                           const double2* const (&fp)[W], Side side) {
+  constexpr int NH = NT / W, H2 = NH / 2, KP = 2 * NH;   // H2 double2 loads bring the B fragments of a k-step
   double b[2][NH];
   auto fetch = [&](auto ksc) {
     constexpr int ks = decltype(ksc)::value, buf = ks & 1;
-    constexpr int kl = ks % (2 * NH);              // k-step inside its half
-    const double2* p = (ks < 2 * NH ? fa : fb) + ((kl * (NT / 2)) << 5);
+    constexpr int part = ks / KP, kl = ks % KP;          // k-step inside its part
+    const double2* p = fp[part] + ((kl * (NT / 2)) << 5);
     static_for<0, H2>([&](auto mc) {
       constexpr int m = decltype(mc)::value;
       const double2 v = p[m << 5];
@@ -105,8 +116,10 @@ __device__ __forceinline__ void pair_sweep(double (&acc)[NT / 2][2], const doubl
   static_for<0, 2 * NT>([&](auto ksc) {
     constexpr int ks = decltype(ksc)::value;
     if constexpr (ks + 1 < 2 * NT) fetch(std::integral_constant<int, ks + 1>{});
-    constexpr int kl = ks % (2 * NH);
-    const double av = ks < 2 * NH ? mine[kl >> 1][kl & 1] : theirs[kl >> 1][kl & 1];
+    constexpr int part = ks / KP, kl = ks % KP;
+    double av;
+    if constexpr (part == 0) av = mine[kl >> 1][kl & 1];
+    else av = theirs[part - 1][kl >> 1][kl & 1];
     static_for<0, NH>([&](auto nc) {
       constexpr int n = decltype(nc)::value;
       if constexpr (ks == 0) dmma_init(acc[n][0], acc[n][1], av, b[0][n]);
@@ -175,13 +188,13 @@ __device__ __forceinline__ void logacc_add(LogAcc& L, double m1, double m2, bool
   if (on && (!p1ok || !p2ok || (pos && !L.zero))) L.bad = 1;
 }
 
-template <int NT, bool FILT, bool WLL>
-__global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, ChainBatchDev B,
+template <int NT, int W, bool FILT, bool WLL>
+__global__ void __launch_bounds__(32 * W * (W == 2 ? 4 : 1), W == 2 ? 1 : 4) k_chain_forward_team(ChainDev C, ChainBatchDev B,
                                                                double* __restrict__ alpha,
                                                                double* __restrict__ post, int post_stride,
                                                                int post_off, double* ll_out, int* status_out) {
-  using G = PairGeom<NT>;
-  constexpr int SP = G::SP, NH = G::NH, NS = G::NS, MID = G::MID, REC = G::REC;
+  using G = TeamGeom<NT, W>;
+  constexpr int SP = G::SP, NH = G::NH, NS = G::NS, MID = G::MID, REC = G::REC, TEAMS = G::TEAMS;
   constexpr bool SUMS = WLL || FILT;
   extern __shared__ double sB[];
   double* s_r1 = sB + SP * SP;
@@ -190,25 +203,26 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
   for (int i = threadIdx.x; i < SP; i += blockDim.x) s_r1[i] = C.R1[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-  const int wib = threadIdx.x >> 5, pair = wib & 3, h = wib >> 2;   // warps p and p + 4 share scheduler p
-  const int bp = (blockIdx.x * 4 + pair) * 8 + g;
+  const int wib = threadIdx.x >> 5, pair = wib % TEAMS, h = wib / TEAMS;   // W = 2: warps p and p + 4 share scheduler p
+  const int bp = (blockIdx.x * TEAMS + pair) * 8 + g;
   const bool valid = bp < B.n_series;
   const int T = valid ? B.len_sorted[bp] : 0;
   const int Tw = __shfl_sync(0xffffffffu, T, 0);  // sorted by length: row 0 is the longest
   const int orig = valid ? B.order[bp] : 0;
   const long long row0 = valid ? B.row_off[orig] : 0;
   const int* cfg = B.cfg + row0;
-  const int t0 = h * NH, t1 = (1 - h) * NH;       // first state tile of the own / the partner's half
+  const int t0 = h * NH;                          // first state tile of the warp's own part
   const double2* f2 = reinterpret_cast<const double2*>(sB) + lane + ((h * (NH / 2)) << 5);
-  const double2* fa = f2 + ((2 * t0 * (NT / 2)) << 5);
-  const double2* fb = f2 + ((2 * t1 * (NT / 2)) << 5);
+  const double2* fp[W];                           // B fragments for the k-steps of part h, h+1, ... (mod W)
+#pragma unroll
+  for (int i = 0; i < W; i++) fp[i] = f2 + ((2 * (((h + i) % W) * NH) * (NT / 2)) << 5);
   const double2* r1v = reinterpret_cast<const double2*>(s_r1);
-  // exchange records: xw(parity) is written by this warp, xr(parity) by the partner
-  double2* xbase = s_x + (size_t)pair * (2 * 2 * REC * 32) + lane;
-  auto xw = [&](int par) { return xbase + (par * 2 + h) * (REC * 32); };
-  auto xr = [&](int par) { return xbase + (par * 2 + (1 - h)) * (REC * 32); };
+  // exchange records: xw(parity) is written by this warp, xr(parity, part) by the warp owning `part`
+  double2* xbase = s_x + (size_t)pair * (2 * W * REC * 32) + lane;
+  auto xw = [&](int par) { return xbase + (par * W + h) * (REC * 32); };
+  auto xr = [&](int par, int part) { return xbase + (par * W + part) * (REC * 32); };
 
-  double mine[NH][2], theirs[NH][2], acc[NH][2], lam[NH][2];
+  double mine[NH][2], theirs[W - 1][NH][2], acc[NH][2], lam[NH][2];
   LogAcc L;
   auto load_lam = [&](int c, bool on) {   // own half of the evidence row
     const double2* p = reinterpret_cast<const double2*>(C.lam_comb + (long long)c * SP);
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
   constexpr int B_FILT = B_LL + 1;            // NH items : filtered marginal, own half
   constexpr int B_F = B_FILT + NH;            // 1 item   : rescale (rare)
   constexpr int WB = B_F + 1;
-  double pa[2], da[2], part_c = 0, part_d = 0, their_c = 0, their_d = 0, cs = 0, ds = 0, cinv = 1.0, fscale = 1.0;
+  double pa[2], da[2], part_c = 0, part_d = 0, cs = 0, ds = 0, cinv = 1.0, fscale = 1.0;
   int s_slice = 0, par = 0, mx = 0, fk = 0;
   bool need = false, scaled = false;
   auto item_a = [&](auto wc) {
@@ -286,25 +300,26 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
       for (int n = 0; n < NH; n++) mx = max(mx, max(hi_word(mine[n][0]), hi_word(mine[n][1])));
     }
   };
-  auto mid = [&]() {   // the partner's half of the vector being settled
-    pair_barrier(pair);
+  auto mid = [&]() {   // the other parts of the vector being settled
+    team_barrier<W>(pair);
 #pragma unroll
-    for (int n = 0; n < NH; n++) {
-      const double2 v = xr(par)[n << 5];
-      theirs[n][0] = v.x;
-      theirs[n][1] = v.y;
-    }
-    if constexpr (SUMS) {
-      const double2 v = xr(par)[NH << 5];
-      their_c = v.x;
-      their_d = v.y;
+    for (int i = 1; i < W; i++) {
+      const double2* rec = xr(par, (h + i) % W);
+#pragma unroll
+      for (int n = 0; n < NH; n++) {
+        const double2 v = rec[n << 5];
+        theirs[i - 1][n][0] = v.x;
+        theirs[i - 1][n][1] = v.y;
+      }
     }
   };
   auto item_b = [&](auto wc) {
     constexpr int w = decltype(wc)::value;
     if constexpr (w == B_EXP) {
 #pragma unroll
-      for (int n = 0; n < NH; n++) mx = max(mx, max(hi_word(theirs[n][0]), hi_word(theirs[n][1])));
+      for (int i = 0; i < W - 1; i++)
+#pragma unroll
+        for (int n = 0; n < NH; n++) mx = max(mx, max(hi_word(theirs[i][n][0]), hi_word(theirs[i][n][1])));
     } else if constexpr (w == B_EXP + 1) {
       mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     } else if constexpr (w == B_EXP + 2) {
@@ -312,13 +327,22 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
       fscale = pow2_rescale(mx, need);
       fk = pow2_rescale_exp(mx);
     } else if constexpr (w == B_RED) {
-      if constexpr (SUMS) cs = part_c + their_c;    // the same two numbers in both warps: a + b == b + a
+      if constexpr (SUMS) {   // the parts' partial sums in the order of the parts: the same sum in every warp
+        double c = 0, d = 0;
+#pragma unroll
+        for (int part = 0; part < W; part++) {
+          const double2 v = xr(par, part)[NH << 5];
+          c = part == 0 ? v.x : c + v.x;
+          d = part == 0 ? v.y : d + v.y;
+        }
+        cs = c;
+        ds = d;
+      }
     } else if constexpr (w == B_RED + 1) {
       if constexpr (SUMS) cs += __shfl_xor_sync(0xffffffffu, cs, 1);
     } else if constexpr (w == B_RED + 2) {
       if constexpr (SUMS) cs += __shfl_xor_sync(0xffffffffu, cs, 2);
     } else if constexpr (w == B_DRED) {
-      if constexpr (WLL) ds = part_d + their_d;
     } else if constexpr (w == B_DRED + 1) {
       if constexpr (WLL) ds += __shfl_xor_sync(0xffffffffu, ds, 1);
     } else if constexpr (w == B_DRED + 2) {
@@ -357,7 +381,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
     const bool on = t < T;
     s_slice = t - 1;
     par = (t - 1) & 1;
-    pair_sweep<NT>(acc, mine, theirs, fa, fb, side);
+    team_sweep<NT, W>(acc, mine, theirs, fp, side);
     noev_p = c_cur == C.c_miss; on_p = on;
 #pragma unroll
     for (int n = 0; n < NH; n++) { mine[n][0] = acc[n][0] * lam[n][0]; mine[n][1] = acc[n][1] * lam[n][1]; }
@@ -390,38 +414,39 @@ __global__ void __launch_bounds__(256, 1) k_chain_forward_pair(ChainDev C, Chain
 // r_t = lambda_t * beta_t (the sweep's A operand).
 // EM variant: stores the carried beta_t (rt[t]) and f_t (hvec[t]) instead of posteriors, and
 // r_0 / (phi0 . r_0) per series; see k_chain_backward and k_chain_stats.
-template <int NT, bool VEC, bool EM>
-__global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, ChainBatchDev B,
+template <int NT, int W, bool VEC, bool EM>
+__global__ void __launch_bounds__(32 * W * (W == 2 ? 4 : 1), W == 2 ? 1 : 4) k_chain_backward_team(ChainDev C, ChainBatchDev B,
                                                                 const double* __restrict__ alpha,
                                                                 double* __restrict__ post, int post_stride,
                                                                 int post_off, double* __restrict__ rt,
                                                                 double* __restrict__ r0,
                                                                 double* __restrict__ hvec) {
-  using G = PairGeom<NT>;
-  constexpr int SP = G::SP, NH = G::NH, NS = G::NS, MID = G::MID, REC = G::REC;
+  using G = TeamGeom<NT, W>;
+  constexpr int SP = G::SP, NH = G::NH, NS = G::NS, MID = G::MID, REC = G::REC, TEAMS = G::TEAMS;
   extern __shared__ double sB[];
   double2* s_x = reinterpret_cast<double2*>(sB + SP * SP + SP);
   for (int i = threadIdx.x; i < SP * SP; i += blockDim.x) sB[i] = C.Bb1[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-  const int wib = threadIdx.x >> 5, pair = wib & 3, h = wib >> 2;
-  const int bp = (blockIdx.x * 4 + pair) * 8 + g;
+  const int wib = threadIdx.x >> 5, pair = wib % TEAMS, h = wib / TEAMS;
+  const int bp = (blockIdx.x * TEAMS + pair) * 8 + g;
   const bool valid = bp < B.n_series;
   const int T = valid ? B.len_sorted[bp] : 0;
   const int Tw = __shfl_sync(0xffffffffu, T, 0);
   const int orig = valid ? B.order[bp] : 0;
   const long long row0 = valid ? B.row_off[orig] : 0;
   const int* cfg = B.cfg + row0;
-  const int t0 = h * NH, t1 = (1 - h) * NH;
+  const int t0 = h * NH;
   const double2* f2 = reinterpret_cast<const double2*>(sB) + lane + ((h * (NH / 2)) << 5);
-  const double2* fa = f2 + ((2 * t0 * (NT / 2)) << 5);
-  const double2* fb = f2 + ((2 * t1 * (NT / 2)) << 5);
-  double2* xbase = s_x + (size_t)pair * (2 * 2 * REC * 32) + lane;
-  auto xw = [&](int par) { return xbase + (par * 2 + h) * (REC * 32); };
-  auto xr = [&](int par) { return xbase + (par * 2 + (1 - h)) * (REC * 32); };
+  const double2* fp[W];
+#pragma unroll
+  for (int i = 0; i < W; i++) fp[i] = f2 + ((2 * (((h + i) % W) * NH) * (NT / 2)) << 5);
+  double2* xbase = s_x + (size_t)pair * (2 * W * REC * 32) + lane;
+  auto xw = [&](int par) { return xbase + (par * W + h) * (REC * 32); };
+  auto xr = [&](int par, int part) { return xbase + (par * W + part) * (REC * 32); };
 
   // own halves: beta_t, r_t = lambda_t * beta_t (A operand), alpha_t, evidence row of slice t-1
-  double beta[NH][2], r[NH][2], rth[NH][2], u[NH][2], lam[NH][2], a[NH][2], an[NH][2];
+  double beta[NH][2], r[NH][2], rth[W - 1][NH][2], u[NH][2], lam[NH][2], a[NH][2], an[NH][2];
   auto load_half = [&](const double* base, bool on, double (&dst)[NH][2]) {
     const double2* p = reinterpret_cast<const double2*>(base);
 #pragma unroll
@@ -480,19 +505,25 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
     }
   };
   auto mid = [&]() {
-    pair_barrier(pair);
+    team_barrier<W>(pair);
 #pragma unroll
-    for (int n = 0; n < NH; n++) {
-      const double2 v = xr(par)[n << 5];
-      rth[n][0] = v.x;
-      rth[n][1] = v.y;
+    for (int i = 1; i < W; i++) {
+      const double2* rec = xr(par, (h + i) % W);
+#pragma unroll
+      for (int n = 0; n < NH; n++) {
+        const double2 v = rec[n << 5];
+        rth[i - 1][n][0] = v.x;
+        rth[i - 1][n][1] = v.y;
+      }
     }
   };
   auto item_b = [&](auto wc) {
     constexpr int w = decltype(wc)::value;
     if constexpr (w == B_EXP) {
 #pragma unroll
-      for (int n = 0; n < NH; n++) mx = max(mx, max(hi_word(rth[n][0]), hi_word(rth[n][1])));
+      for (int i = 0; i < W - 1; i++)
+#pragma unroll
+        for (int n = 0; n < NH; n++) mx = max(mx, max(hi_word(rth[i][n][0]), hi_word(rth[i][n][1])));
     } else if constexpr (w == B_EXP + 1) {
       mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     } else if constexpr (w == B_EXP + 2) {
@@ -552,7 +583,7 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
     t_cur = t;
     par = t & 1;
     // u = r . A^T  (k = current state, n = previous state), own n-tiles
-    pair_sweep<NT>(u, r, rth, fa, fb, side);
+    team_sweep<NT, W>(u, r, rth, fp, side);
 #pragma unroll
     for (int n = 0; n < NH; n++) {
       beta[n][0] = first_next ? 1.0 : u[n][0];
@@ -597,8 +628,10 @@ __global__ void __launch_bounds__(256, 1) k_chain_backward_pair(ChainDev C, Chai
     static_for<B_ST, B_LD>(item_b);
     if constexpr (EM) {
       if (on && q == 0 && h == 0) B.rn_out[row0] = pinv;
-      const double ztheirs = xr(par)[NH << 5].x;
-      const double zinv = safe_rcp(quad_sum_full(zpart + ztheirs));
+      double z = 0;   // phi0 . r_0 from the parts' partials, in the order of the parts
+#pragma unroll
+      for (int part = 0; part < W; part++) z = part == 0 ? xr(par, part)[NH << 5].x : z + xr(par, part)[NH << 5].x;
+      const double zinv = safe_rcp(quad_sum_full(z));
       if (0 < T) {
         double2* out0 = reinterpret_cast<double2*>(r0 + (long long)orig * SP);
 #pragma unroll

@@ -800,11 +800,15 @@ int em_learn(time_series* ts, int n_ts, double threshold, nip_double_list learni
  * host code (model_prob_mass, get_probability, nipjoint's reads of clique->p, the next
  * nip_enter_evidence, finish/start_timeslice_message_pass) continues on exactly the state the
  * reference would have left. */
-static unsigned long long fnv1a(const void* p, size_t n) {
-  const unsigned char* s = (const unsigned char*)p;
-  unsigned long long h = 1469598103934665603ULL;
+/* hash of the request, eight bytes at a time (the request is an array of doubles) */
+static unsigned long long hash_doubles(const double* p, size_t n) {
+  unsigned long long h = 0x9e3779b97f4a7c15ULL, w;
   size_t i;
-  for (i = 0; i < n; i++) { h ^= s[i]; h *= 1099511628211ULL; }
+  for (i = 0; i < n; i++) {
+    memcpy(&w, p + i, sizeof w);
+    h = (h ^ w) * 0xff51afd7ed558ccdULL;
+    h ^= h >> 29;
+  }
   return h;
 }
 
@@ -830,7 +834,7 @@ void make_consistent(nip_model model) {
   }
   e->slice_calls++;
   if (e->memo_on) {
-    h = fnv1a(in, n_in * sizeof(double));
+    h = hash_doubles(in, n_in);
     for (slot = (int)(h & (MEMO_SLOTS - 1)); e->memo[slot].in; slot = (slot + 1) & (MEMO_SLOTS - 1))
       if (e->memo[slot].hash == h && memcmp(e->memo[slot].in, in, n_in * sizeof(double)) == 0) {
         memcpy(out, e->memo[slot].in + n_in, n_out * sizeof(double));
