@@ -616,3 +616,24 @@ def test_group_em_matches_one_device(gpu_lib, n_dev, name):
         mdl.close()
     sb.close()
     single.close()
+
+
+@pytest.mark.parametrize("env", [{"NIPGPU_CHAIN_TEAM": "2"}, {"NIPGPU_CHAIN_TEAM": "4"}, {"NIPGPU_CHAIN_PAIR": "0"}])
+def test_chain_kernel_flavours(gpu_lib, env):
+    """the chain engine's three kernel flavours — teams of two warps on one scheduler (what a
+    batch above 3072 sequences runs on), teams of four warps on four schedulers (small batches:
+    everything else in this suite), one warp per group (interfaces that are not 4 or 8 state
+    tiles wide) — forced one by one on the same ragged sets: 1e-9 against the oracle, and
+    bit-identical results from two runs (the warps of a team exchange halves of every vector
+    through shared memory behind a named barrier)"""
+    import os
+    import subprocess
+    import sys
+    helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "team_kernels_check.py")
+    outs = []
+    for _ in range(2):
+        r = subprocess.run([sys.executable, helper], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.strip().startswith("OK")
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1], "results differ from run to run"
