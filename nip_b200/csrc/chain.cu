@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(128, 1) k_chain_backward(ChainDev C, ChainBatc
 }
 
 #include "chain_pair.cuh"
+#include "chain_small.cuh"
 
 // ----------------------------------------------------------------- EM ----
 // Sufficient statistics of the whole batch in one pass over the two row stores
@@ -1248,6 +1249,11 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
     k_chain_mats<<<(S * S + 255) / 256, 256, 0, st>>>(d_base0 + tab_off[cm.c0], d_base1 + tab_off[cm.c0],
                                                       cm.d_ent_of, S, cm.NT, cm.d_Bf1, cm.d_Bb1, cm.d_Bb0);
     NIPGPU_LAUNCHED();
+    if (cm.NT == 1) {
+      if (!cm.d_As) NIPGPU_CUDA(cudaMalloc((void**)&cm.d_As, 64 * sizeof(double)));
+      k_chain_small_A<<<1, 64, 0, st>>>(cm.d_Bf1, S, cm.d_As);
+      NIPGPU_LAUNCHED();
+    }
   }
   k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base0 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_phi0);
   NIPGPU_LAUNCHED();
@@ -1273,7 +1279,7 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
 
 void chain_free(ChainModel& cm) {
   cudaFree(cm.d_ent_of); cudaFree(cm.d_Bf1); cudaFree(cm.d_Bb1); cudaFree(cm.d_Bb0);
-  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_miss_rows); cudaFree(cm.d_R1); cudaFree(cm.d_colsum); cudaFree(cm.d_ent_im); cudaFree(cm.d_ent_ip); cudaFree(cm.d_ip_to_s);
+  cudaFree(cm.d_phi0); cudaFree(cm.d_lam0); cudaFree(cm.d_lam); cudaFree(cm.d_leaf_meta); cudaFree(cm.d_miss_rows); cudaFree(cm.d_R1); cudaFree(cm.d_colsum); cudaFree(cm.d_ent_im); cudaFree(cm.d_ent_ip); cudaFree(cm.d_ip_to_s); cudaFree(cm.d_As);
   cm = ChainModel();
 }
 
@@ -1324,6 +1330,18 @@ int chain_batch_prepare(const ChainModel& cm, ChainBatch& cb, int n_series, cons
   for (int i = 0; i < n_series; i++) cb.len_sorted[i] = len[cb.order[i]];
   if (int e = upload(&cb.d_order, cb.order, st)) return e;
   if (int e = upload(&cb.d_len_sorted, cb.len_sorted, st)) return e;
+  if (cm.NT == 1 && !cm.dense) {   // time-major offsets of the thread-per-sequence kernels
+    const int tm = n_series > 0 ? std::max(cb.len_sorted[0], 0) : 0;
+    std::vector<long long> toff(tm + 1, 0);
+    int alive = n_series;
+    for (int t = 0; t < tm; t++) {
+      while (alive > 0 && cb.len_sorted[alive - 1] <= t) alive--;
+      toff[t + 1] = toff[t] + alive;
+    }
+    if (int e = upload(&cb.d_toff, toff, st)) return e;
+    NIPGPU_CUDA(cudaMalloc((void**)&cb.d_cfgT, std::max<long long>(rows, 1) * sizeof(int)));
+    NIPGPU_CUDA(cudaStreamSynchronize(st));   // `toff` dies here
+  }
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_alpha, std::max<long long>(rows, 1) * cm.SP * sizeof(double)));
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_fexp, std::max<long long>(rows, 1) * sizeof(int)));
   NIPGPU_CUDA(cudaMalloc((void**)&cb.d_zc, (size_t)std::max(n_series, 1) * sizeof(double)));
@@ -1340,7 +1358,7 @@ void chain_batch_free(ChainBatch& cb) {
   cudaFree(cb.d_fexp); cudaFree(cb.d_zc); cudaFree(cb.d_zf); cudaFree(cb.d_rn);
   cudaFree(cb.d_lam_static); cudaFree(cb.d_cols); cudaFree(cb.d_rows); cudaFree(cb.d_comb);
   cudaFree(cb.d_rt); cudaFree(cb.d_hvec); cudaFree(cb.d_first); cudaFree(cb.d_r0); cudaFree(cb.d_em_scratch);
-  cudaFree(cb.d_dense); cudaFree(cb.d_dense_i);
+  cudaFree(cb.d_dense); cudaFree(cb.d_dense_i); cudaFree(cb.d_toff); cudaFree(cb.d_cfgT);
   for (int k = 0; k < 3; k++) {
     if (cb.dense_stream[k]) cudaStreamDestroy(cb.dense_stream[k]);
     if (cb.dense_join[k]) cudaEventDestroy(cb.dense_join[k]);
@@ -1413,6 +1431,78 @@ static int chain_prepare_evidence(const ChainModel& cm, ChainBatch& cb, const Ch
   return NIPGPU_OK;
 }
 
+// ---- one-tile interfaces on large batches: one thread per sequence (chain_small.cuh) ----
+#ifndef NIPGPU_SMALL_MIN_SERIES
+#define NIPGPU_SMALL_MIN_SERIES 2048
+#endif
+// NIPGPU_CHAIN_SMALL=0 keeps the DMMA kernels, =1 forces the thread-per-sequence kernels
+static bool small_wanted(int n_series) {
+  static const int forced = [] {
+    const char* p = getenv("NIPGPU_CHAIN_SMALL");
+    return p ? (p[0] == '0' ? 0 : 1) : -1;
+  }();
+  if (forced >= 0) return forced == 1;
+  return n_series >= NIPGPU_SMALL_MIN_SERIES;
+}
+
+template <int S>
+static int small_launch(const SmallDev& D, int n_lam, size_t smem, const ChainInferArgs& a, double* alphaT,
+                        cudaStream_t st) {
+  const int grid = (D.n_series + 127) / 128;
+  const bool filt = a.forward_only && a.d_post;
+  const bool smooth = !a.forward_only && a.d_post;
+  constexpr int unit = SmallGeom<S>::V4 ? 4 : 2;
+  const int wide = (S % 2 == 0) && a.d_post && (a.post_stride % unit == 0) && (a.post_off % unit == 0) &&
+                   ((uintptr_t)a.d_post % (8 * unit) == 0);
+  auto fwd = [&](auto kernel) -> int {
+    if (int e = set_smem(kernel, smem)) return e;
+    kernel<<<grid, 128, smem, st>>>(D, n_lam, smooth ? 1 : 0, alphaT, a.d_post, a.post_stride, a.post_off, wide,
+                                    a.d_ll, a.d_status);
+    NIPGPU_LAUNCHED();
+    return NIPGPU_OK;
+  };
+  int e;
+  if (filt) e = a.want_ll ? fwd(k_chain_small_forward<S, true, true>) : fwd(k_chain_small_forward<S, true, false>);
+  else e = a.want_ll ? fwd(k_chain_small_forward<S, false, true>) : fwd(k_chain_small_forward<S, false, false>);
+  if (e) return e;
+  if (g_chain_mid_event) NIPGPU_CUDA(cudaEventRecord(g_chain_mid_event, st));
+  if (smooth) {
+    if (int e2 = set_smem(k_chain_small_backward<S>, smem)) return e2;
+    k_chain_small_backward<S><<<grid, 128, smem, st>>>(D, n_lam, alphaT, a.d_post, a.post_stride, a.post_off, wide);
+    NIPGPU_LAUNCHED();
+  }
+  return NIPGPU_OK;
+}
+
+static int small_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& plan, const ChainBatchDev& B,
+                       const ChainInferArgs& a, cudaStream_t st) {
+  if (cb.cfgT_key != cb.plan_key) {   // time-major copy of the evidence index, once per plan
+    k_chain_small_cfgT<<<(a.n_series + 127) / 128, 128, 0, st>>>(cb.d_cfg, cb.d_toff, a.d_row_off, cb.d_order,
+                                                                 cb.d_len_sorted, a.n_series, cb.d_cfgT);
+    NIPGPU_LAUNCHED();
+    cb.cfgT_key = cb.plan_key;
+  }
+  SmallDev D;
+  D.S = cm.S; D.SP = cm.SP; D.c_miss = plan.c_miss; D.n_comb = plan.n_comb; D.m1_0 = cm.m1_0;
+  D.A = cm.d_As; D.phi0 = cm.d_phi0; D.R1 = cm.d_R1; D.lam_comb = cb.d_comb;
+  D.toff = cb.d_toff; D.cfgT = cb.d_cfgT; D.n_series = a.n_series; D.order = B.order;
+  D.len_sorted = B.len_sorted; D.row_off = B.row_off;
+  const int n_lam = (size_t)plan.n_comb * cm.S * sizeof(double) <= 32768 ? plan.n_comb : 0;
+  const size_t smem = sizeof(double) * ((size_t)cm.S * cm.S + (size_t)n_lam * cm.S);
+  switch (cm.S) {
+    case 1: return small_launch<1>(D, n_lam, smem, a, cb.d_alpha, st);
+    case 2: return small_launch<2>(D, n_lam, smem, a, cb.d_alpha, st);
+    case 3: return small_launch<3>(D, n_lam, smem, a, cb.d_alpha, st);
+    case 4: return small_launch<4>(D, n_lam, smem, a, cb.d_alpha, st);
+    case 5: return small_launch<5>(D, n_lam, smem, a, cb.d_alpha, st);
+    case 6: return small_launch<6>(D, n_lam, smem, a, cb.d_alpha, st);
+    case 7: return small_launch<7>(D, n_lam, smem, a, cb.d_alpha, st);
+    case 8: return small_launch<8>(D, n_lam, smem, a, cb.d_alpha, st);
+  }
+  set_error("chain: unsupported interface size");
+  return NIPGPU_EUNSUPPORTED;
+}
+
 // instrumentation: when set, recorded between the forward and the backward kernel of chain_infer
 cudaEvent_t g_chain_mid_event = nullptr;
 
@@ -1437,6 +1527,12 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
     return NIPGPU_OK;
   }
   int e = NIPGPU_OK;
+  if (cm.NT == 1 && small_wanted(a.n_series)) {
+    e = small_infer(cm, cb, plan, B, a, st);
+    if (e) return e;
+    if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
+    return NIPGPU_OK;
+  }
   switch (cm.NT) {
     case 1: e = launch_forward<1>(C, B, a, cb.d_alpha, st); break;
     case 2: e = launch_forward<2>(C, B, a, cb.d_alpha, st); break;

@@ -48,6 +48,7 @@ struct ChainModel {
   int* d_ip_to_s = nullptr;                      // [n_real][S] state -> leaf sepset entry
   double *d_Bf1 = nullptr, *d_Bb1 = nullptr, *d_Bb0 = nullptr;  // fragment-ordered SPxSP
   double *d_phi0 = nullptr, *d_lam0 = nullptr, *d_R1 = nullptr, *d_colsum = nullptr; // [SP]
+  double* d_As = nullptr;      // [S][S] plain transition table (one-tile interfaces, chain_small.cuh)
   double m1_0 = 1.0;           // mass of the evidence-free first slice
   double* d_lam = nullptr;     // all Lambda tables
   long long lam_total = 0;
@@ -64,6 +65,10 @@ struct ChainBatch {
   int* d_order = nullptr;
   int* d_len_sorted = nullptr;
   int* d_cfg = nullptr;            // [rows] combined evidence index per data row
+  // thread-per-sequence kernels (chain_small.cuh): time-major offsets and evidence index
+  long long* d_toff = nullptr;     // [t_max + 1] (slice, sequence) pairs before slice t, sequences sorted by length
+  int* d_cfgT = nullptr;           // [rows]
+  std::vector<int> cfgT_key;       // evidence plan d_cfgT was built for
   double* d_alpha = nullptr;       // [rows][SP], same row order as the API
   // scale bookkeeping of the warp-pair kernels: binary exponent carried by every stored forward
   // row, and per series the sum of its last forward row with that row's exponent

@@ -6,8 +6,12 @@ Tolerance: 1e-9 RELATIVE on posterior marginals, log-likelihoods, expected count
 and re-estimated CPTs (BASELINE.json north star); exact zeros must stay exact
 zeros (atol = 0) and -DBL_MAX must be reproduced exactly.
 """
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from cases import (ALL_CASES, EM_CASES, LIKELIHOOD_CASES, SLICE_CASES, Case, assert_close, unhex)
 
@@ -637,3 +641,47 @@ def test_chain_kernel_flavours(gpu_lib, env):
         assert r.stdout.strip().startswith("OK")
         outs.append(r.stdout.strip())
     assert outs[0] == outs[1], "results differ from run to run"
+
+
+def test_thread_per_sequence_kernels(gpu_lib):
+    """interfaces of 1..8 joint states on the thread-per-sequence kernels (what a batch of 2048+
+    sequences of a one-tile model such as examples/model.net runs on), forced on small ragged sets
+    with missing data: 1e-9 against the oracle for smoothing, filtering, likelihood, queries
+    through the joint projection, and the E-step afterwards on the same batch"""
+    import os
+    import subprocess
+    import sys
+    helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "small_kernels_check.py")
+    r = subprocess.run([sys.executable, helper], env=dict(os.environ, NIPGPU_CHAIN_SMALL="1"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.strip().endswith("OK")
+
+
+def test_thread_per_sequence_kernels_large_batch_matches_dmma_kernels(gpu_lib):
+    """4096 sequences of the 4-state model.net shape: the automatic choice (thread per sequence)
+    against the DMMA kernels forced with NIPGPU_CHAIN_SMALL=0 in a subprocess, at 1e-12"""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import nip_b200.api as api\n"
+        "from nip_b200.synth import HmmSpec\n"
+        "h = HmmSpec(4, 5, seed=1); data = h.sample(4096, 30, seed=2, missing=0.05)\n"
+        "m = api.Model(h.flat()); b = m.batch(h.obs_vars, [d for d in data])\n"
+        "post, ll = b.infer(h.hidden_query)\n"
+        "np.save(sys.argv[1], np.concatenate([post.ravel(), ll.ravel()]))\n" % ROOT)
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for flag in (None, "0"):
+            env = dict(os.environ)
+            env.pop("NIPGPU_CHAIN_SMALL", None)
+            if flag is not None:
+                env["NIPGPU_CHAIN_SMALL"] = flag
+            f = os.path.join(d, "o%s.npy" % flag)
+            r = subprocess.run([sys.executable, "-c", code, f], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            outs.append(np.load(f))
+    assert_close(outs[0], outs[1], "thread-per-sequence vs DMMA kernels", rtol=1e-12)
