@@ -43,6 +43,8 @@ extern "C" {
 #define NIPGPU_ENGINE_AUTO   0
 #define NIPGPU_ENGINE_JTREE  1  /* generic join-tree schedule (any model)     */
 #define NIPGPU_ENGINE_CHAIN  2  /* interface-clique + leaves, DMMA contraction*/
+#define NIPGPU_ENGINE_FACTOR 3  /* join tree evaluated factor by factor: clique
+                                   tables never materialised (huge cliques)   */
 
 /* Flat description of one parsed time-slice model.  It is a by-value snapshot
  * of what parse_model() leaves in nip_model_struct (src/nip.h:71-112) and in

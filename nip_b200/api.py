@@ -18,7 +18,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 # NIPGPU_LIB_PATH: development only (A/B timing of kernel variants built side by side)
 LIB_PATH = os.environ.get("NIPGPU_LIB_PATH") or os.path.join(PKG, "libnipgpu.so")
 
-ENGINE_AUTO, ENGINE_JTREE, ENGINE_CHAIN = 0, 1, 2
+ENGINE_AUTO, ENGINE_JTREE, ENGINE_CHAIN, ENGINE_FACTOR = 0, 1, 2, 3
 EBADLUCK = 8
 
 # every symbol include/nipgpu.h declares (checked by tests/test_abi.py)

@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
     "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
 ]
-SOURCES = ["api.cu", "jtree.cu", "chain.cu", "dense.cu", "params.cu", "probe.cu", "group.cu", "model.cpp"]
+SOURCES = ["api.cu", "jtree.cu", "chain.cu", "dense.cu", "params.cu", "probe.cu", "group.cu", "factor.cu", "model.cpp"]
 
 
 def _nvcc():

@@ -135,7 +135,7 @@ int choose_launch(nipgpu_model* m) {
 }
 
 // base0/base1, calibration vectors and the chain-engine tables from d_orig / d_prior
-int refresh_derived(nipgpu_model* m) {
+int refresh_derived(nipgpu_model* m, bool from_counts = false) {
   const HostModel& hm = m->hm;
   cudaStream_t st = m->stream;
   const size_t tab_bytes = (size_t)m->prog.tab_total * sizeof(double);
@@ -160,6 +160,8 @@ int refresh_derived(nipgpu_model* m) {
   if (int e = jt_calibrate(m->prog, m->launch, m->d_R1, m->d_m10, st)) return e;
   if (m->chain.ok)
     if (int e = chain_refresh(hm, m->chain, m->d_base0, m->d_base1, m->tab_off, m->d_ipool, m->d_R1, m->d_m10, st)) return e;
+  if (m->fac.ok)   // engine 3: its factors are the CPTs themselves (after an M-step: the normalised counts)
+    if (int e = fac_refresh(hm, m->fac, m->d_prior, m->d_prior_flags, from_counts ? m->d_counts : nullptr, st)) return e;
   NIPGPU_CUDA(cudaStreamSynchronize(st));
   m->slice_consistent = false;
   return NIPGPU_OK;
@@ -228,6 +230,13 @@ int ensure_alpha(nipgpu_model* m, nipgpu_batch* b) {
   return NIPGPU_OK;
 }
 
+void fill_fac_args(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, FacRunArgs* a) {
+  a->n_series = b->n_series; a->n_obs = b->n_obs; a->t_max = b->t_max; a->rows = b->rows;
+  a->len = &b->len; a->row_off = &b->row_off; a->obs_vars = &b->obs_vars; a->use_evidence = use_evidence;
+  a->d_obs = b->d_obs; a->d_row_off = b->d_row_off; a->d_alpha = b->d_alpha; a->d_ll = b->d_ll;
+  a->d_status = b->d_status; a->d_R1 = m->d_R1; a->d_m10 = m->d_m10;
+}
+
 int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int nq,
                const int32_t* query, int forward_only, int want_ll, bool want_post) {
   if (!m || !b || b->m != m) return fail(NIPGPU_EINVAL, "model/batch mismatch");
@@ -286,6 +295,22 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
     return NIPGPU_OK;
   }
 
+  // ---- engine 3: factor by factor ----
+  if (m->engine == NIPGPU_ENGINE_FACTOR && m->fac.ok) {
+    if (int e = ensure_alpha(m, b)) return e;
+    FacRunArgs a{};
+    fill_fac_args(m, b, use_evidence, &a);
+    a.n_query = nq; a.query = query; a.post_row = Q.row; a.d_post = post;
+    a.want_ll = want_ll; a.forward_only = forward_only;
+    NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if (int e = fac_run(hm, m->fac, a, m->stream)) return e;
+    NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+    NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 0; }
+    return NIPGPU_OK;
+  }
+
   // ---- generic join-tree engine ----
   const int* obs_proj = nullptr;
   if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;
@@ -341,8 +366,10 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
     if (hm.clique_dim(c) > kMaxDims) { delete m; return fail(NIPGPU_EUNSUPPORTED, "clique with too many variables"); }
   const std::string why = chain_build(hm, m->chain);
   if (engine == NIPGPU_ENGINE_CHAIN && !m->chain.ok) { delete m; return fail(NIPGPU_EUNSUPPORTED, "chain engine: " + why); }
-  m->engine = engine == NIPGPU_ENGINE_JTREE ? NIPGPU_ENGINE_JTREE
-                                            : (m->chain.ok ? NIPGPU_ENGINE_CHAIN : NIPGPU_ENGINE_JTREE);
+  if (engine < NIPGPU_ENGINE_AUTO || engine > NIPGPU_ENGINE_FACTOR) { delete m; return fail(NIPGPU_EINVAL, "unknown engine"); }
+  m->engine = engine == NIPGPU_ENGINE_JTREE || engine == NIPGPU_ENGINE_FACTOR
+                  ? engine
+                  : (m->chain.ok ? NIPGPU_ENGINE_CHAIN : NIPGPU_ENGINE_JTREE);
   cudaDeviceProp prop;
   NIPGPU_CUDA(cudaGetDeviceProperties(&prop, device));
   m->sm_count = prop.multiProcessorCount;
@@ -415,7 +442,27 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
   P.path = m->d_path; P.base0 = m->d_base0; P.base1 = m->d_base1; P.R1 = m->d_R1; P.m1_0 = m->d_m10;
   P.proj_var = m->d_proj_var; P.proj_fam = m->d_proj_fam; P.coff = m->d_coff; P.var_flags = m->d_var_flags;
 
-  if ((e = choose_launch(m)) || (e = chain_upload_structure(hm, m->chain, st)) || (e = refresh_derived(m))) {
+  if ((e = choose_launch(m)) || (e = chain_upload_structure(hm, m->chain, st))) {
+    nipgpu_model_destroy(m);
+    return e;
+  }
+  // engine 3 on request, or by itself for models whose cliques would be streamed through HBM by
+  // the grid team (NIPGPU_FACTOR=0 keeps those on engine 1)
+  {
+    const char* fenv = getenv("NIPGPU_FACTOR");
+    const bool auto_fac = engine == NIPGPU_ENGINE_AUTO && !m->chain.ok && m->launch.mode == JT_MODE_GRID &&
+                          !(fenv && fenv[0] == '0');
+    if (engine == NIPGPU_ENGINE_FACTOR || auto_fac) {
+      fac_build(hm, m->fac);
+      if (m->fac.ok) m->engine = NIPGPU_ENGINE_FACTOR;
+      else if (engine == NIPGPU_ENGINE_FACTOR) {
+        const std::string why = m->fac.why;
+        nipgpu_model_destroy(m);
+        return fail(NIPGPU_EUNSUPPORTED, "factor engine: " + why);
+      }
+    }
+  }
+  if ((e = refresh_derived(m))) {
     nipgpu_model_destroy(m);
     return e;
   }
@@ -442,6 +489,7 @@ void nipgpu_model_destroy(nipgpu_model* m) {
   cudaFree(m->d_prop); cudaFree(m->d_vec);
   if (m->h_prop) cudaFreeHost(m->h_prop);
   chain_free(m->chain);
+  fac_free(m->fac);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->ev_mid) cudaEventDestroy(m->ev_mid);
@@ -461,6 +509,15 @@ int nipgpu_model_set_parameters(nipgpu_model* m, const double* tables, const dou
     NIPGPU_CUDA(cudaMemcpyAsync(m->d_prior, prior, (size_t)m->hm.prior_off[m->hm.nv] * sizeof(double),
                                 cudaMemcpyHostToDevice, m->stream));
   NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+  if (m->fac.ok) {   // engine 3 works on the factors of the new tables
+    std::copy(tables, tables + m->prog.tab_total, m->hm.tables.begin());
+    fac_free(m->fac);
+    fac_build(m->hm, m->fac);
+    if (!m->fac.ok) {
+      if (m->engine == NIPGPU_ENGINE_FACTOR) m->engine = NIPGPU_ENGINE_JTREE;
+      set_error("factor engine dropped: " + m->fac.why);
+    }
+  }
   return refresh_derived(m);
 }
 
@@ -617,6 +674,28 @@ int estep_enqueue(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence,
     if (rc == NIPGPU_OK) { m->last_kernel_n = 7; return NIPGPU_OK; }
     if (rc != NIPGPU_EUNSUPPORTED) return rc;
   }
+  if (m->engine == NIPGPU_ENGINE_FACTOR && m->fac.ok) {
+    if (int e = ensure_alpha(m, b)) return e;
+    const int slots = fac_slots(hm, m->fac, b->n_series);
+    if (m->acc_groups < (size_t)slots) {
+      cudaFree(m->d_acc);
+      m->d_acc = nullptr;
+      m->acc_groups = 0;
+      NIPGPU_CUDA(cudaMalloc((void**)&m->d_acc, (size_t)slots * (size_t)n * sizeof(double)));
+      m->acc_groups = slots;
+    }
+    NIPGPU_CUDA(cudaMemsetAsync(m->d_acc, 0, (size_t)slots * n * sizeof(double), m->stream));
+    FacRunArgs a{};
+    fill_fac_args(m, b, use_evidence, &a);
+    a.want_ll = 1; a.forward_only = 0; a.d_acc = m->d_acc; a.acc_stride = n; a.acc_slots = slots;
+    NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if (int e = fac_run(hm, m->fac, a, m->stream)) return e;
+    NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+    if (int e = finish_estep(m->d_acc, slots, n, n, add_pseudocount ? 1.0 : 0.0, b->d_ll, b->d_status,
+                             b->n_series, m->d_counts, m->stream)) return e;
+    m->last_kernel_n = 0;
+    return NIPGPU_OK;
+  }
   const int* obs_proj = nullptr;
   if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;
   if (int e = ensure_alpha(m, b)) return e;
@@ -699,7 +778,7 @@ int nipgpu_em_mstep(nipgpu_model* m, const double* counts) {
                                   (size_t)hm.card[v] * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
   }
-  return refresh_derived(m);
+  return refresh_derived(m, true);
 }
 
 int nipgpu_likelihood(nipgpu_model* m, nipgpu_batch* b, const uint8_t* evidence_off,

@@ -5,6 +5,7 @@
 
 #include "chain.cuh"
 #include "common.cuh"
+#include "factor.cuh"
 #include "jtree.cuh"
 #include "model.h"
 #include "params.cuh"
@@ -44,6 +45,7 @@ struct nipgpu_model {
   nipgpu::JtLaunch launch{};
 
   nipgpu::ChainModel chain;  // engine 2 (valid when hm.chain_ok)
+  nipgpu::FacEngine fac;     // engine 3 (valid when fac.ok)
 
   // ---- single-slice state (stateful API) ----
   std::vector<std::vector<double>> lik;  // host mirror of variable->likelihood

@@ -1,0 +1,1036 @@
+// factor.cu — engine 3, see factor.cuh: the join tree evaluated factor by factor.
+#include "factor.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <functional>
+#include <numeric>
+#include <set>
+
+namespace nipgpu {
+
+namespace {
+
+long long prod_card(const HostModel& hm, const std::vector<int>& vars) {
+  long long n = 1;
+  for (int v : vars) n *= hm.card[v];
+  return n;
+}
+
+bool has_var(const std::vector<int>& vs, int v) { return std::find(vs.begin(), vs.end(), v) != vs.end(); }
+
+// stride of variable v inside a tensor with the given variable order (0 when absent)
+long long stride_in(const HostModel& hm, const std::vector<int>& vars, int v) {
+  long long s = 1;
+  for (int u : vars) {
+    if (u == v) return s;
+    s *= hm.card[u];
+  }
+  return 0;
+}
+
+template <class T>
+int dev_up(T** dst, const std::vector<T>& src, cudaStream_t st) {
+  cudaFree(*dst);
+  *dst = nullptr;
+  NIPGPU_CUDA(cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+  if (!src.empty())
+    NIPGPU_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return NIPGPU_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// structure and factor extraction (host)
+// ------------------------------------------------------------------------------------------
+void fac_build(const HostModel& hm, FacEngine& fe, double rel_tol) {
+  fe = FacEngine();
+  const int nc = hm.nc, nv = hm.nv;
+  fe.root = hm.nif > 0 ? hm.out_clique : 0;
+  fe.parent.assign(nc, -1);
+  fe.psep.assign(nc, -1);
+  fe.children.assign(nc, {});
+  std::vector<char> seen(nc, 0);
+  std::vector<int> stack{fe.root};
+  seen[fe.root] = 1;
+  while (!stack.empty()) {   // pre-order
+    const int c = stack.back();
+    stack.pop_back();
+    fe.preorder.push_back(c);
+    for (int l = hm.adjoff[c]; l < hm.adjoff[c + 1]; l++) {
+      const int s = hm.adj[l];
+      const int nb = hm.scl[2 * s] == c ? hm.scl[2 * s + 1] : hm.scl[2 * s];
+      if (seen[nb]) continue;
+      seen[nb] = 1;
+      fe.parent[nb] = c;
+      fe.psep[nb] = s;
+      fe.children[c].push_back(nb);
+      stack.push_back(nb);
+    }
+  }
+  if ((int)fe.preorder.size() != nc) { fe.why = "join tree is not connected"; return; }
+
+  fe.cpt_tensor.assign(nv, -1);
+  fe.prior_tensor.assign(nv, -1);
+  fe.kappa_tensor.assign(nc, -1);
+  fe.local.assign(nc, {});
+  auto add_model = [&](const std::vector<int>& vars) {
+    FacTensor t;
+    t.vars = vars;
+    t.kind = FT_MODEL;
+    t.size = prod_card(hm, vars);
+    t.off = fe.fac_total;
+    fe.fac_total += (t.size + 15) / 16 * 16;
+    fe.tensors.push_back(t);
+    return (int)fe.tensors.size() - 1;
+  };
+  for (int v = 0; v < nv; v++) {
+    if (hm.nparents(v) > 0) {
+      std::vector<int> fv{v};
+      for (int j = hm.poff[v]; j < hm.poff[v + 1]; j++) fv.push_back(hm.parents[j]);
+      std::set<int> uniq(fv.begin(), fv.end());
+      if (uniq.size() != fv.size()) { fe.why = "a family lists a variable twice"; return; }
+      fe.cpt_tensor[v] = add_model(fv);
+      fe.local[hm.family[v]].push_back(FacOpRef{fe.cpt_tensor[v], false});
+    } else if (!(hm.flags[v] & NIPGPU_IF_OLD_OUTGOING)) {
+      fe.prior_tensor[v] = add_model({v});
+      fe.local[hm.family[v]].push_back(FacOpRef{fe.prior_tensor[v], false});
+    }
+  }
+  for (int c = 0; c < nc; c++) fe.kappa_tensor[c] = add_model({});
+  if (hm.nif > 0) fe.a0_tensor = add_model(hm.prev);
+  fe.n_model_tensors = (int)fe.tensors.size();
+  fe.h_fac.assign((size_t)fe.fac_total, 1.0);
+  if (!fac_extract(hm, fe, hm.tables.data(), rel_tol)) return;
+  for (int c = 0; c < nc; c++)
+    if (fe.h_fac[(size_t)fe.tensors[fe.kappa_tensor[c]].off] != 1.0)
+      fe.local[c].push_back(FacOpRef{fe.kappa_tensor[c], false});
+  fe.ok = true;
+}
+
+bool fac_extract(const HostModel& hm, FacEngine& fe, const double* tables, double rel_tol) {
+  const int nc = hm.nc;
+  for (int c = 0; c < nc; c++) {
+    const double* T = tables + hm.toff[c];
+    const long long n = hm.csize[c];
+    const int nd = hm.clique_dim(c);
+    const int* cv = hm.clique_vars(c);
+    std::vector<long long> cstride(nd);
+    {
+      long long s = 1;
+      for (int k = 0; k < nd; k++) { cstride[k] = s; s *= hm.card[cv[k]]; }
+    }
+    std::vector<int> fams;   // variables whose CPT lives here
+    for (int v = 0; v < hm.nv; v++)
+      if (hm.family[v] == c && fe.cpt_tensor[v] >= 0) fams.push_back(v);
+    // reference entry: the largest one
+    long long xs = 0;
+    for (long long e = 1; e < n; e++)
+      if (T[e] > T[xs]) xs = e;
+    if (!(T[xs] > 0)) { fe.why = "a clique table has no positive entry"; return false; }
+    std::vector<int> xdig(nd);
+    {
+      long long rem = xs;
+      for (int k = 0; k < nd; k++) { xdig[k] = (int)(rem % hm.card[cv[k]]); rem /= hm.card[cv[k]]; }
+    }
+    const int nf = (int)fams.size();
+    // per factor: for each clique dimension its stride inside the factor (0: not a family member)
+    std::vector<std::vector<long long>> fstride(nf, std::vector<long long>(nd, 0));
+    std::vector<double*> fval(nf);
+    for (int i = 0; i < nf; i++) {
+      const FacTensor& ft = fe.tensors[fe.cpt_tensor[fams[i]]];
+      for (int k = 0; k < nd; k++) fstride[i][k] = stride_in(hm, ft.vars, cv[k]);
+      fval[i] = fe.h_fac.data() + ft.off;
+    }
+    auto fidx = [&](int i, const std::vector<int>& dig) {
+      long long j = 0;
+      for (int k = 0; k < nd; k++) j += dig[k] * fstride[i][k];
+      return j;
+    };
+    // f_i(x_Fi) = T(x_Fi, x*) / prod_{j<i} f_j(...)   (0/0 -> 0)
+    for (int i = 0; i < nf; i++) {
+      const FacTensor& ft = fe.tensors[fe.cpt_tensor[fams[i]]];
+      std::vector<int> dig = xdig;
+      std::vector<int> pos(ft.vars.size());
+      for (size_t a = 0; a < ft.vars.size(); a++) pos[a] = hm.var_pos(c, ft.vars[a]);
+      for (long long j = 0; j < ft.size; j++) {
+        long long rem = j;
+        for (size_t a = 0; a < ft.vars.size(); a++) {
+          dig[pos[a]] = (int)(rem % hm.card[ft.vars[a]]);
+          rem /= hm.card[ft.vars[a]];
+        }
+        long long e = 0;
+        for (int k = 0; k < nd; k++) e += dig[k] * cstride[k];
+        double val = T[e];
+        for (int p = 0; p < i && val != 0; p++) {
+          const double d = fval[p][fidx(p, dig)];
+          val = d != 0 ? val / d : 0.0;
+        }
+        fval[i][j] = val;
+      }
+    }
+    double kappa = T[xs];
+    for (int i = 0; i < nf; i++) {
+      const double d = fval[i][fidx(i, xdig)];
+      kappa = d != 0 ? kappa / d : 0.0;
+    }
+    fe.h_fac[(size_t)fe.tensors[fe.kappa_tensor[c]].off] = kappa;
+    // verification over the whole table (odometer, no divisions)
+    std::vector<int> dig(nd, 0);
+    std::vector<long long> fi(nf, 0);
+    for (long long e = 0; e < n; e++) {
+      double p = kappa;
+      for (int i = 0; i < nf; i++) p *= fval[i][fi[i]];
+      const double t = T[e];
+      if (!(std::fabs(p - t) <= rel_tol * std::fabs(t))) {
+        fe.why = "clique " + std::to_string(c) + " is not the product of its families' tables";
+        return false;
+      }
+      for (int k = 0; k < nd; k++) {   // next entry
+        dig[k]++;
+        for (int i = 0; i < nf; i++) fi[i] += fstride[i][k];
+        if (dig[k] < hm.card[cv[k]]) break;
+        for (int i = 0; i < nf; i++) fi[i] -= fstride[i][k] * hm.card[cv[k]];
+        dig[k] = 0;
+      }
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct PriorJob {
+  int n;                      // unary prior tensors
+  long long dst[32];
+  int src[32], card[32], flag[32];
+};
+__global__ void k_fac_priors(PriorJob J, const double* prior, const int* flags, double* fac) {
+  for (int k = blockIdx.x; k < J.n; k += gridDim.x)
+    for (int i = threadIdx.x; i < J.card[k]; i += blockDim.x)
+      fac[J.dst[k] + i] = flags[J.flag[k]] ? prior[J.src[k] + i] : 1.0;
+}
+
+struct A0Job {
+  int nif, S;
+  int card[24], src[24], flag[24];   // src < 0: the interface variable has parents (no prior)
+};
+__global__ void k_fac_a0(A0Job J, const double* prior, const int* flags, double* out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J.S) return;
+  int rem = j;
+  double p = 1.0;
+  for (int k = 0; k < J.nif; k++) {
+    const int d = rem % J.card[k];
+    rem /= J.card[k];
+    if (J.src[k] >= 0 && flags[J.flag[k]]) p *= prior[J.src[k] + d];
+  }
+  out[j] = p;
+}
+
+__global__ void k_fac_fill(double* a, long long n, double v) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// what a kernel needs to find the data of "its" sequence
+struct SlotCtx {
+  double* slots;
+  long long slot_stride;
+  const double* fac;
+  const int* pool;
+  const int* obs;
+  int n_obs;
+  const long long* row_off;
+  const int* order;    // sorted position -> series
+  int wave0, t;
+};
+
+__device__ __forceinline__ double fac_inv(double x) { return x != 0 ? 1.0 / x : 0.0; }
+
+// out(o) [chunk] = prod_{O-only operands}(o) * sum_{r in chunk} prod_{k < NR} operand_k(o, r)
+template <int NR>
+__global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
+  extern __shared__ int s_roff[];   // [NR][Rc]
+  const int slot = blockIdx.z, chunk = blockIdx.y;
+  const int r0 = chunk * s.Rc, r1 = min(s.R, r0 + s.Rc), nr = r1 - r0;
+  for (int k = 0; k < NR; k++)
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) s_roff[k * s.Rc + i] = X.pool[s.opR[k].roff + r0 + i];
+  __syncthreads();
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= s.n_out) return;
+  const int oh = o / s.F, ol = o - oh * s.F;
+  double* area = X.slots + (long long)slot * X.slot_stride;
+  const long long row = X.row_off[X.order[X.wave0 + slot]] + X.t;
+  const double* ptr[NR > 0 ? NR : 1];
+  int ev[NR > 0 ? NR : 1];
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+    const FacOpDev& op = s.opR[k];
+    const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
+    if (op.kind == FT_EVID) {
+      const int obs = X.obs[row * X.n_obs + op.col];
+      ev[k] = obs < 0 ? INT_MIN : obs - ob;   // the operand is 1 where roff == ev (everywhere when missing)
+      ptr[k] = nullptr;
+    } else {
+      ev[k] = 0;
+      ptr[k] = (op.kind == FT_MODEL ? X.fac : area) + op.off + ob;
+    }
+  }
+  double acc = 0;
+  if (NR == 0) acc = 1.0;
+  else {
+    for (int r = 0; r < nr; r++) {
+      double term = 1.0;
+#pragma unroll
+      for (int k = 0; k < NR; k++) {
+        const int ro = s_roff[k * s.Rc + r];
+        double v;
+        if (ptr[k]) {
+          v = ptr[k][ro];
+          if (s.opR[k].inv) v = fac_inv(v);
+        } else {
+          v = (ev[k] == INT_MIN || ro == ev[k]) ? 1.0 : 0.0;
+        }
+        term = k == 0 ? v : term * v;
+      }
+      acc += term;
+    }
+  }
+  for (int k = 0; k < s.nO; k++) {
+    const FacOpDev& op = s.opO[k];
+    const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
+    double v;
+    if (op.kind == FT_EVID) {
+      const int obs = X.obs[row * X.n_obs + op.col];
+      v = (obs < 0 || obs == ob) ? 1.0 : 0.0;
+    } else {
+      v = ((op.kind == FT_MODEL ? X.fac : area) + op.off)[ob];
+      if (op.inv) v = fac_inv(v);
+    }
+    acc *= v;
+  }
+  if (s.n_chunks > 1) area[s.out_off + (long long)chunk * s.n_out + o] = acc;   // out_off = partial area
+  else area[s.out_off + o] = acc;
+}
+
+// out[o] = sum over chunks of partial[chunk][o], fixed order
+__global__ void k_fac_reduce(SlotCtx X, long long part_off, long long out_off, int n_out, int n_chunks) {
+  double* area = X.slots + (long long)blockIdx.y * X.slot_stride;
+  const double* part = area + part_off;
+  if (n_chunks >= 32) {   // a warp per output
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (o >= n_out) return;
+    double s = 0;
+    for (int c = lane; c < n_chunks; c += 32) s += part[(long long)c * n_out + o];
+    s = warp_sum(s);
+    if (lane == 0) area[out_off + o] = s;
+  } else {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    double s = 0;
+    for (int c = 0; c < n_chunks; c++) s += part[(long long)c * n_out + o];
+    area[out_off + o] = s;
+  }
+}
+
+// start of a slice: alpha_in <- alpha_{t-1} (or the prior product on first slices); backward:
+// beta <- 1 on the last slice of a sequence
+__global__ void k_fac_prepare(SlotCtx X, const int* len_sorted, const double* alpha, int S, long long o_alpha_in,
+                              long long o_beta, long long a0_off, int set_beta /*0 no, 1 where last, 2 all*/,
+                              double* ll_run, int* bad_run, int reset_ll) {
+  const int slot = blockIdx.y;
+  double* area = X.slots + (long long)slot * X.slot_stride;
+  const int p = X.wave0 + slot;
+  const long long row0 = X.row_off[X.order[p]];
+  const double* src = X.t == 0 ? X.fac + a0_off : alpha + (row0 + X.t - 1) * S;
+  const bool beta1 = set_beta == 2 || (set_beta == 1 && len_sorted[p] - 1 == X.t);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+    area[o_alpha_in + i] = src[i];
+    if (beta1) area[o_beta + i] = 1.0;
+  }
+  if (reset_ll && blockIdx.x == 0 && threadIdx.x == 0) { ll_run[slot] = 0.0; bad_run[slot] = 0; }
+}
+
+// end of a forward slice: masses, log-likelihood bookkeeping (src/nip.c:1458-1474, 1827-1831),
+// alpha_t = normalise(alpha_new) into the row store
+__global__ void __launch_bounds__(1024) k_fac_settle_fwd(SlotCtx X, const int* len_sorted, const int* marked, int S,
+                                                         long long o_alpha_in, long long o_alpha_new,
+                                                         const double* R1, const double* m1_0, double* alpha,
+                                                         int want_ll, int nif, double* ll_run, int* bad_run,
+                                                         double* ll_out, int* status_out) {
+  __shared__ double red[40];
+  const int slot = blockIdx.x;
+  double* area = X.slots + (long long)slot * X.slot_stride;
+  const int p = X.wave0 + slot, seq = X.order[p];
+  const long long row0 = X.row_off[seq];
+  const double* an = area + o_alpha_new;
+  double s = 0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) s += an[i];
+  double m2 = block_sum(s, red);
+  const double inv = m2 != 0 ? 1.0 / m2 : 1.0;      // zero sum: untouched (nip_normalise_array)
+  for (int i = threadIdx.x; i < S; i += blockDim.x) alpha[(row0 + X.t) * S + i] = an[i] * inv;
+  if (want_ll) {
+    double m1;
+    if (X.t == 0) m1 = *m1_0;
+    else if (nif == 0) m1 = R1[0];
+    else {
+      double d = 0;
+      for (int i = threadIdx.x; i < S; i += blockDim.x) d += area[o_alpha_in + i] * R1[i];
+      m1 = block_sum(d, red);
+    }
+    if (threadIdx.x == 0) {
+      int entered = 0;
+      const int* obs = X.obs + (row0 + X.t) * X.n_obs;
+      for (int k = 0; k < X.n_obs; k++) entered += marked[k] && obs[k] >= 0;
+      if (entered == 0) m2 = m1;   // an evidence-free slice has m2 == m1 by definition
+      double ll = ll_run[slot];
+      int bad = bad_run[slot];
+      if (m1 > 0 && m2 > 0) ll += log(m2) - log(m1);
+      if (m2 == 0) ll = -DBL_MAX;
+      if (m1 <= 0 || m2 <= 0 || ll > 0) bad = 1;
+      ll_run[slot] = ll;
+      bad_run[slot] = bad;
+      if (X.t == len_sorted[p] - 1) {
+        if (ll_out) ll_out[seq] = ll;
+        if (status_out) status_out[seq] = bad;
+      }
+    }
+  } else if (threadIdx.x == 0 && X.t == len_sorted[p] - 1) {
+    if (ll_out) ll_out[seq] = 0.0;
+    if (status_out) status_out[seq] = 0;
+  }
+}
+
+// beta_{t-1} = b / sum(b)   (any positive scale gives the same posteriors; this keeps it O(1))
+__global__ void __launch_bounds__(1024) k_fac_beta_norm(SlotCtx X, int S, long long o_bprev, long long o_beta) {
+  __shared__ double red[40];
+  double* area = X.slots + (long long)blockIdx.x * X.slot_stride;
+  double s = 0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) s += area[o_bprev + i];
+  s = block_sum(s, red);
+  const double inv = s != 0 ? 1.0 / s : 1.0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) area[o_beta + i] = area[o_bprev + i] * inv;
+}
+
+// expected counts: acc[slot][dst + i] += v[i] / sum(v)   (src/nip.c:1925-1967; zero mass: skipped)
+__global__ void __launch_bounds__(1024) k_fac_count(SlotCtx X, long long src_off, int n, double* acc,
+                                                    long long acc_stride, long long dst) {
+  __shared__ double red[40];
+  const double* v = X.slots + (long long)blockIdx.x * X.slot_stride + src_off;
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_sum(s, red);
+  if (s == 0) return;
+  double* a = acc + (long long)blockIdx.x * acc_stride + dst;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] += v[i] / s;
+}
+
+// posterior of a queried variable into the caller's row
+__global__ void __launch_bounds__(256) k_fac_query(SlotCtx X, long long src_off, int n, double* post, int post_row,
+                                                   long long dst) {
+  __shared__ double red[40];
+  const double* v = X.slots + (long long)blockIdx.x * X.slot_stride + src_off;
+  const long long row = X.row_off[X.order[X.wave0 + blockIdx.x]] + X.t;
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_sum(s, red);
+  const double inv = s != 0 ? 1.0 / s : 1.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) post[row * post_row + dst + i] = v[i] * inv;
+}
+
+}  // namespace
+
+int fac_refresh(const HostModel& hm, FacEngine& fe, const double* d_prior, const int* d_prior_flags,
+                const double* d_counts, cudaStream_t st) {
+  if (!fe.ok) return NIPGPU_OK;
+  if (!fe.d_fac) NIPGPU_CUDA(cudaMalloc((void**)&fe.d_fac, std::max<long long>(fe.fac_total, 1) * sizeof(double)));
+  if (!d_counts) {
+    NIPGPU_CUDA(cudaMemcpyAsync(fe.d_fac, fe.h_fac.data(), (size_t)fe.fac_total * sizeof(double),
+                                cudaMemcpyHostToDevice, st));
+  } else {
+    for (int v = 0; v < hm.nv; v++)
+      if (fe.cpt_tensor[v] >= 0) {
+        const FacTensor& t = fe.tensors[fe.cpt_tensor[v]];
+        NIPGPU_CUDA(cudaMemcpyAsync(fe.d_fac + t.off, d_counts + hm.coff[v], (size_t)t.size * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+      }
+    for (int c = 0; c < hm.nc; c++) {   // tables rebuilt by init_potential from all-ones: no constant left
+      k_fac_fill<<<1, 32, 0, st>>>(fe.d_fac + fe.tensors[fe.kappa_tensor[c]].off, 1, 1.0);
+      NIPGPU_LAUNCHED();
+    }
+  }
+  // priors: entered only when some entry is positive (nip_enter_prior, src/nipjointree.c:917-927)
+  std::vector<int> flag_of(hm.nv, -1);
+  for (size_t k = 0; k < hm.prior_vars.size(); k++) flag_of[hm.prior_vars[k]] = (int)k;
+  PriorJob J;
+  J.n = 0;
+  auto flush = [&]() -> int {
+    if (J.n == 0) return NIPGPU_OK;
+    k_fac_priors<<<J.n, 64, 0, st>>>(J, d_prior, d_prior_flags, fe.d_fac);
+    NIPGPU_LAUNCHED();
+    J.n = 0;
+    return NIPGPU_OK;
+  };
+  for (int v = 0; v < hm.nv; v++) {
+    if (fe.prior_tensor[v] < 0) continue;
+    J.dst[J.n] = fe.tensors[fe.prior_tensor[v]].off;
+    J.src[J.n] = hm.prior_off[v];
+    J.card[J.n] = hm.card[v];
+    J.flag[J.n] = flag_of[v];
+    if (++J.n == 32)
+      if (int e = flush()) return e;
+  }
+  if (int e = flush()) return e;
+  if (fe.a0_tensor >= 0) {
+    if (hm.nif > 24) { set_error("factor engine: more than 24 interface variables"); return NIPGPU_EUNSUPPORTED; }
+    A0Job A;
+    A.nif = hm.nif;
+    A.S = hm.S;
+    for (int k = 0; k < hm.nif; k++) {
+      const int v = hm.prev[k];
+      A.card[k] = hm.card[v];
+      A.src[k] = hm.nparents(v) == 0 ? hm.prior_off[v] : -1;
+      A.flag[k] = hm.nparents(v) == 0 ? flag_of[v] : 0;
+    }
+    k_fac_a0<<<(hm.S + 255) / 256, 256, 0, st>>>(A, d_prior, d_prior_flags, fe.d_fac + fe.tensors[fe.a0_tensor].off);
+    NIPGPU_LAUNCHED();
+  }
+  return NIPGPU_OK;
+}
+
+void fac_free(FacEngine& fe) {
+  cudaFree(fe.d_fac);
+  cudaFree(fe.d_slots);
+  cudaFree(fe.d_ll_run);
+  cudaFree(fe.d_bad_run);
+  for (auto& kv : fe.programs) {
+    cudaFree(kv.second.d_pool);
+    cudaFree(kv.second.d_marked);
+  }
+  fe = FacEngine();
+}
+
+// ------------------------------------------------------------------------------------------
+// program compilation (host)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Compiler {
+  const HostModel& hm;
+  const FacEngine& fe;
+  std::vector<FacTensor> T;
+  std::vector<int> pool;
+  long long slot_top = 0;
+  long long partial_max = 0;
+
+  Compiler(const HostModel& h, const FacEngine& f) : hm(h), fe(f), T(f.tensors.begin(), f.tensors.begin() + f.n_model_tensors) {}
+
+  int slot_tensor(const std::vector<int>& vars) {
+    FacTensor t;
+    t.vars = vars;
+    t.kind = FT_SLOT;
+    t.size = prod_card(hm, vars);
+    t.off = slot_top;
+    slot_top += (t.size + 15) / 16 * 16;
+    T.push_back(t);
+    return (int)T.size() - 1;
+  }
+  int evid_tensor(int v, int col) {
+    FacTensor t;
+    t.vars = {v};
+    t.kind = FT_EVID;
+    t.size = hm.card[v];
+    t.col = col;
+    T.push_back(t);
+    return (int)T.size() - 1;
+  }
+
+  // tables of one operand: offset as a function of the output index (split o = oh * F + ol) and of
+  // the summed index
+  void tables(const FacTensor& t, const std::vector<int>& ovars, int F, long long n_out,
+              const std::vector<int>& rvars, long long R, FacOpDev& d) {
+    auto fill = [&](const std::vector<int>& vars, long long from, long long count, long long unit) {
+      // offsets of indices from, from+unit, ... (count of them) over `vars`
+      const int pos = (int)pool.size();
+      for (long long x = 0; x < count; x++) {
+        long long rem = from + x * unit, o = 0;
+        for (int v : vars) {
+          o += (rem % hm.card[v]) * stride_in(hm, t.vars, v);
+          rem /= hm.card[v];
+        }
+        pool.push_back((int)o);
+      }
+      return pos;
+    };
+    d.olo = fill(ovars, 0, F, 1);
+    d.ohi = fill(ovars, 0, (n_out + F - 1) / F, F);
+    d.roff = fill(rvars, 0, R, 1);
+  }
+
+  FacInstr contract(int out, const std::vector<FacOpRef>& ops) {
+    FacInstr ins;
+    ins.kind = FI_CONTRACT;
+    FacStepDev& s = ins.step;
+    const std::vector<int>& ovars = T[out].vars;
+    std::vector<int> rvars;
+    for (const FacOpRef& o : ops)
+      for (int v : T[o.tensor].vars)
+        if (!has_var(ovars, v) && !has_var(rvars, v)) rvars.push_back(v);
+    // the summed digits run fastest over the variable that is fastest in the biggest operand
+    const long long n_out = T[out].size, R = prod_card(hm, rvars);
+    int F = 1;
+    for (int v : ovars) {
+      if (F >= 128) break;
+      F *= hm.card[v];
+    }
+    if (n_out > INT32_MAX || R > INT32_MAX) { ins.kind = -1; return ins; }
+    s.n_out = (int)n_out;
+    s.F = F;
+    s.R = (int)R;
+    s.nR = s.nO = 0;
+    for (const FacOpRef& o : ops) {
+      const FacTensor& t = T[o.tensor];
+      bool dep = false;
+      for (int v : t.vars) dep = dep || has_var(rvars, v);
+      FacOpDev d{};
+      d.off = t.off;
+      d.kind = t.kind;
+      d.inv = o.inv ? 1 : 0;
+      d.col = t.col;
+      tables(t, ovars, F, n_out, rvars, dep ? R : 0, d);
+      if (dep) {
+        if (s.nR >= kFacMaxOps) { ins.kind = -1; return ins; }
+        s.opR[s.nR++] = d;
+      } else {
+        if (s.nO >= kFacMaxOps) { ins.kind = -1; return ins; }
+        s.opO[s.nO++] = d;
+      }
+    }
+    // split the summed range so that a slot has at least ~64k threads, at least 8 terms each
+    const long long want = 65536;
+    long long chunks = std::max<long long>(1, std::min<long long>((want + n_out - 1) / n_out, R / 8));
+    chunks = std::max(chunks, (R + 1023) / 1024);
+    if (s.nR == 0) chunks = 1;
+    s.Rc = (int)((R + chunks - 1) / chunks);
+    s.n_chunks = (int)((R + s.Rc - 1) / s.Rc);
+    s.out_off = T[out].off;
+    if (s.n_chunks > 1) partial_max = std::max(partial_max, (long long)s.n_chunks * n_out);
+    ins.flops = (double)n_out * (double)R * std::max(1, s.nR);
+    return ins;
+  }
+};
+
+std::vector<int> plan_key(const FacRunArgs& a, const HostModel& hm, bool counts) {
+  std::vector<int> key;
+  key.push_back(a.n_obs);
+  for (int k = 0; k < a.n_obs; k++) {
+    const int v = (*a.obs_vars)[k];
+    key.push_back((a.use_evidence ? a.use_evidence[v] != 0 : true) ? v : -1);
+  }
+  key.push_back(-2);
+  key.push_back(counts ? 1 : 0);
+  key.push_back(a.d_post ? a.n_query : 0);
+  if (a.d_post)
+    for (int q = 0; q < a.n_query; q++) key.push_back(a.query[q]);
+  (void)hm;
+  return key;
+}
+
+int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts, FacProgram& P, cudaStream_t st) {
+  Compiler C(hm, fe);
+  const int nc = hm.nc;
+  const bool queries = a.d_post && a.n_query > 0;
+  // ---- per-clique operand lists ----
+  std::vector<std::vector<FacOpRef>> L = fe.local;
+  std::vector<int> marked(std::max(a.n_obs, 1), 0);
+  std::vector<char> var_seen(hm.nv, 0);
+  for (int k = 0; k < a.n_obs; k++) {
+    const int v = (*a.obs_vars)[k];
+    if (v < 0 || v >= hm.nv) { set_error("factor engine: observed variable out of range"); return NIPGPU_EINVAL; }
+    const bool on = a.use_evidence ? a.use_evidence[v] != 0 : true;
+    if (!on) continue;
+    marked[k] = 1;
+    L[hm.family[v]].push_back(FacOpRef{C.evid_tensor(v, k), false});
+    var_seen[v] = 1;
+  }
+  const int S = hm.S;
+  int t_alpha_in = -1, t_beta = -1, t_alpha_new = -1, t_bprev = -1;
+  if (hm.nif > 0) {
+    t_alpha_in = C.slot_tensor(hm.prev);
+    t_beta = C.slot_tensor(hm.outg);
+    t_alpha_new = C.slot_tensor(hm.outg);
+    t_bprev = C.slot_tensor(hm.prev);
+    P.o_alpha_in = C.T[t_alpha_in].off;
+    P.o_beta = C.T[t_beta].off;
+    P.o_alpha_new = C.T[t_alpha_new].off;
+    P.o_bprev = C.T[t_bprev].off;
+  }
+  auto sep_vars = [&](int s) { return std::vector<int>(hm.sepset_vars(s), hm.sepset_vars(s) + hm.sepset_dim(s)); };
+  // ---- upward messages (towards the root = out_clique), children before parents ----
+  std::vector<int> up(nc, -1), down(nc, -1);
+  std::vector<FacInstr> ups;
+  for (int i = nc - 1; i >= 0; i--) {
+    const int c = fe.preorder[i];
+    if (c == fe.root) continue;
+    up[c] = C.slot_tensor(sep_vars(fe.psep[c]));
+    std::vector<FacOpRef> ops = L[c];
+    if (hm.nif > 0 && c == hm.in_clique) ops.push_back(FacOpRef{t_alpha_in, false});
+    for (int d : fe.children[c]) ops.push_back(FacOpRef{up[d], false});
+    ups.push_back(C.contract(up[c], ops));
+  }
+  // ---- forward program ----
+  P.fwd = ups;
+  if (hm.nif == 0) {   // no interface: only the mass of the slice (a 0-dimensional "alpha")
+    t_alpha_new = C.slot_tensor({});
+    P.o_alpha_new = C.T[t_alpha_new].off;
+  }
+  {
+    std::vector<FacOpRef> ops = L[fe.root];
+    if (hm.nif > 0 && fe.root == hm.in_clique) ops.push_back(FacOpRef{t_alpha_in, false});
+    for (int d : fe.children[fe.root]) ops.push_back(FacOpRef{up[d], false});
+    P.fwd.push_back(C.contract(t_alpha_new, ops));
+    FacInstr s;
+    s.kind = FI_SETTLE_FWD;
+    P.fwd.push_back(s);
+  }
+  // ---- backward program: targets, their host cliques ----
+  struct Target { std::vector<int> vars; int kind, var; long long dst; bool only_t0; int clique; };
+  std::vector<Target> targets;
+  if (counts)
+    for (int v = 0; v < hm.nv; v++) {
+      Target t;
+      t.vars = {v};
+      for (int j = hm.poff[v]; j < hm.poff[v + 1]; j++) t.vars.push_back(hm.parents[j]);
+      t.kind = FI_COUNT; t.var = v; t.dst = hm.coff[v];
+      t.only_t0 = (hm.flags[v] & NIPGPU_IF_OLD_OUTGOING) != 0;
+      t.clique = -1;
+      targets.push_back(t);
+    }
+  if (queries) {
+    long long off = 0;
+    for (int q = 0; q < a.n_query; q++) {
+      Target t;
+      t.vars = {a.query[q]};
+      t.kind = FI_QUERY; t.var = q; t.dst = off; t.only_t0 = false; t.clique = -1;
+      off += hm.card[a.query[q]];
+      targets.push_back(t);
+    }
+  }
+  // place every target in the clique whose belief grows least (largest targets first)
+  std::vector<std::vector<int>> U(nc);
+  auto grown = [&](int c, const std::vector<int>& vars) {
+    long long n = prod_card(hm, U[c]);
+    for (int v : vars)
+      if (!has_var(U[c], v)) n *= hm.card[v];
+    return n;
+  };
+  std::vector<int> order(targets.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    return prod_card(hm, targets[x].vars) > prod_card(hm, targets[y].vars);
+  });
+  for (int ti : order) {
+    Target& t = targets[ti];
+    long long best = -1;
+    for (int c = 0; c < nc; c++) {
+      bool holds = true;
+      for (int v : t.vars) holds = holds && hm.var_pos(c, v) >= 0;
+      if (!holds) continue;
+      // cost: entries of the grown belief; the clique table itself bounds it
+      const long long g = grown(c, t.vars);
+      const bool better = best < 0 || g < best || (g == best && c == hm.family[t.vars[0]]);
+      if (better) { best = g; t.clique = c; }
+    }
+    if (t.clique < 0) { set_error("factor engine: a target is held by no clique"); return NIPGPU_EINVAL; }
+    for (int v : t.vars)
+      if (!has_var(U[t.clique], v)) U[t.clique].push_back(v);
+  }
+  // which subtrees need a downward message
+  std::vector<char> needed(nc, 0);
+  for (int i = nc - 1; i >= 0; i--) {
+    const int c = fe.preorder[i];
+    bool n = !U[c].empty() || (hm.nif > 0 && c == hm.in_clique);
+    for (int d : fe.children[c]) n = n || needed[d];
+    needed[c] = n;
+  }
+  P.bwd = ups;
+  for (int c : fe.preorder) {
+    if (!needed[c]) continue;
+    std::vector<FacOpRef> all = L[c];   // every operand of the clique's belief
+    if (hm.nif > 0 && c == hm.in_clique) all.push_back(FacOpRef{t_alpha_in, false});
+    if (hm.nif > 0 && c == fe.root) all.push_back(FacOpRef{t_beta, false});
+    if (c != fe.root) all.push_back(FacOpRef{down[c], false});
+    for (int d : fe.children[c]) all.push_back(FacOpRef{up[d], false});
+    // leaf children that need a message get it from the belief (Hugin division by what they sent)
+    std::vector<int> leaf_kids, inner_kids;
+    for (int d : fe.children[c]) {
+      if (!needed[d]) continue;
+      const bool leaf = fe.children[d].empty() && !(hm.nif > 0 && d == hm.in_clique);
+      (leaf ? leaf_kids : inner_kids).push_back(d);
+    }
+    for (int d : leaf_kids)
+      for (int v : sep_vars(fe.psep[d]))
+        if (!has_var(U[c], v)) U[c].push_back(v);
+    int belief = -1;
+    if (!U[c].empty()) {
+      std::vector<int> uv;   // clique order
+      for (int k = 0; k < hm.clique_dim(c); k++)
+        if (has_var(U[c], hm.clique_vars(c)[k])) uv.push_back(hm.clique_vars(c)[k]);
+      belief = C.slot_tensor(uv);
+      P.bwd.push_back(C.contract(belief, all));
+      for (const Target& t : targets) {
+        if (t.clique != c) continue;
+        int src = belief;
+        if (t.vars != uv) {
+          src = C.slot_tensor(t.vars);
+          P.bwd.push_back(C.contract(src, {FacOpRef{belief, false}}));
+        }
+        FacInstr ins;
+        ins.kind = t.kind;
+        ins.src_off = C.T[src].off;
+        ins.n = (int)C.T[src].size;
+        ins.var = t.var;
+        ins.dst_off = t.dst;
+        ins.only_t0 = t.only_t0;
+        P.bwd.push_back(ins);
+      }
+      for (int d : leaf_kids) {
+        down[d] = C.slot_tensor(sep_vars(fe.psep[d]));
+        P.bwd.push_back(C.contract(down[d], {FacOpRef{belief, false}, FacOpRef{up[d], true}}));
+      }
+    }
+    for (int d : inner_kids) {
+      down[d] = C.slot_tensor(sep_vars(fe.psep[d]));
+      std::vector<FacOpRef> ops;
+      for (const FacOpRef& o : all)
+        if (o.tensor != up[d]) ops.push_back(o);
+      P.bwd.push_back(C.contract(down[d], ops));
+    }
+    if (hm.nif > 0 && c == hm.in_clique) {   // message to slice t-1: everything but alpha_{t-1}
+      std::vector<FacOpRef> ops;
+      for (const FacOpRef& o : all)
+        if (o.tensor != t_alpha_in) ops.push_back(o);
+      FacInstr ins = C.contract(t_bprev, ops);
+      ins.needs_history = true;
+      P.bwd.push_back(ins);
+      FacInstr nb;
+      nb.kind = FI_BETA_NORM;
+      nb.needs_history = true;
+      P.bwd.push_back(nb);
+    }
+  }
+  for (const std::vector<FacInstr>* v : {&P.fwd, &P.bwd})
+    for (const FacInstr& i : *v)
+      if (i.kind < 0) { set_error("factor engine: a contraction exceeds the engine's limits"); return NIPGPU_EUNSUPPORTED; }
+  // partial sums of split contractions live behind the tensors
+  P.o_partial = C.slot_top;
+  P.partial_doubles = (C.partial_max + 15) / 16 * 16;
+  P.slot_doubles = P.o_partial + P.partial_doubles + 16;
+  for (std::vector<FacInstr>* v : {&P.fwd, &P.bwd})
+    for (FacInstr& i : *v) {
+      if (i.kind != FI_CONTRACT) continue;
+      (v == &P.fwd ? P.flops_fwd : P.flops_bwd) += i.flops;
+    }
+  P.n_obs = a.n_obs;
+  if (int e = dev_up(&P.d_pool, C.pool, st)) return e;
+  if (int e = dev_up(&P.d_marked, marked, st)) return e;
+  NIPGPU_CUDA(cudaStreamSynchronize(st));
+  (void)S;
+  return NIPGPU_OK;
+}
+
+template <int NR>
+void launch_contract_n(const FacStepDev& s, const SlotCtx& X, int alive, cudaStream_t st) {
+  const dim3 grid((s.n_out + 127) / 128, s.n_chunks, alive);
+  const size_t smem = (size_t)std::max(NR, 1) * s.Rc * sizeof(int);
+  k_fac_contract<NR><<<grid, 128, smem, st>>>(s, X);
+}
+
+struct RunCtx {
+  const FacProgram* P;
+  const FacRunArgs* a;
+  FacEngine* fe;
+  const int* d_len_sorted;
+  int S, nif;
+  bool no_beta_update;   // filtering: beta stays 1, no message to slice t-1
+};
+
+int run_instr(const RunCtx& R, const FacInstr& ins, const SlotCtx& X, int alive, cudaStream_t st) {
+  const FacProgram& P = *R.P;
+  const FacRunArgs& a = *R.a;
+  switch (ins.kind) {
+    case FI_CONTRACT: {
+      if (ins.needs_history && (X.t == 0 || R.no_beta_update)) return NIPGPU_OK;
+      FacStepDev s = ins.step;
+      const long long final_off = s.out_off;
+      if (s.n_chunks > 1) s.out_off = P.o_partial;
+      switch (s.nR) {
+        case 0: launch_contract_n<0>(s, X, alive, st); break;
+        case 1: launch_contract_n<1>(s, X, alive, st); break;
+        case 2: launch_contract_n<2>(s, X, alive, st); break;
+        case 3: launch_contract_n<3>(s, X, alive, st); break;
+        case 4: launch_contract_n<4>(s, X, alive, st); break;
+        case 5: launch_contract_n<5>(s, X, alive, st); break;
+        case 6: launch_contract_n<6>(s, X, alive, st); break;
+        case 7: launch_contract_n<7>(s, X, alive, st); break;
+        default: launch_contract_n<8>(s, X, alive, st); break;
+      }
+      NIPGPU_LAUNCHED();
+      if (s.n_chunks > 1) {
+        const int per = s.n_chunks >= 32 ? 8 : 256;   // outputs per 256-thread CTA
+        k_fac_reduce<<<dim3((s.n_out + per - 1) / per, alive), 256, 0, st>>>(X, P.o_partial, final_off, s.n_out,
+                                                                             s.n_chunks);
+        NIPGPU_LAUNCHED();
+      }
+      return NIPGPU_OK;
+    }
+    case FI_SETTLE_FWD:
+      k_fac_settle_fwd<<<alive, 1024, 0, st>>>(X, R.d_len_sorted, P.d_marked, R.S, P.o_alpha_in, P.o_alpha_new,
+                                               a.d_R1, a.d_m10, a.d_alpha, a.want_ll, R.nif, R.fe->d_ll_run,
+                                               R.fe->d_bad_run, a.d_ll, a.d_status);
+      NIPGPU_LAUNCHED();
+      return NIPGPU_OK;
+    case FI_BETA_NORM:
+      if (X.t == 0 || R.no_beta_update) return NIPGPU_OK;
+      k_fac_beta_norm<<<alive, 1024, 0, st>>>(X, R.S, P.o_bprev, P.o_beta);
+      NIPGPU_LAUNCHED();
+      return NIPGPU_OK;
+    case FI_COUNT:
+      if (!a.d_acc || (ins.only_t0 && X.t > 0)) return NIPGPU_OK;
+      k_fac_count<<<alive, 1024, 0, st>>>(X, ins.src_off, ins.n, a.d_acc, a.acc_stride, ins.dst_off);
+      NIPGPU_LAUNCHED();
+      return NIPGPU_OK;
+    case FI_QUERY:
+      if (!a.d_post) return NIPGPU_OK;
+      k_fac_query<<<alive, 256, 0, st>>>(X, ins.src_off, ins.n, a.d_post, a.post_row, ins.dst_off);
+      NIPGPU_LAUNCHED();
+      return NIPGPU_OK;
+  }
+  return NIPGPU_OK;
+}
+
+}  // namespace
+
+#ifndef NIPGPU_FACTOR_MAX_SLOTS
+#define NIPGPU_FACTOR_MAX_SLOTS 32
+#endif
+int fac_slots(const HostModel& hm, const FacEngine& fe, int n_series) {
+  (void)hm; (void)fe;
+  static const int cap = [] {
+    const char* p = getenv("NIPGPU_FACTOR_SLOTS");
+    const int v = p ? atoi(p) : 0;
+    return v > 0 ? v : NIPGPU_FACTOR_MAX_SLOTS;
+  }();
+  return std::max(1, std::min(cap, n_series));
+}
+
+int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_t st) {
+  if (!fe.ok) { set_error("factor engine: " + fe.why); return NIPGPU_EUNSUPPORTED; }
+  if (a.n_series == 0) return NIPGPU_OK;
+  const bool counts = a.d_acc != nullptr;
+  const bool queries = a.d_post && a.n_query > 0;
+  const std::vector<int> key = plan_key(a, hm, counts);
+  auto it = fe.programs.find(key);
+  if (it == fe.programs.end()) {
+    FacProgram P;
+    if (int e = compile(hm, fe, a, counts, P, st)) { cudaFree(P.d_pool); cudaFree(P.d_marked); return e; }
+    it = fe.programs.emplace(key, P).first;
+  }
+  const FacProgram& P = it->second;
+  // ---- sequences sorted by length, longest first; W of them in flight ----
+  std::vector<int> order(a.n_series);
+  std::iota(order.begin(), order.end(), 0);
+  const std::vector<int>& len = *a.len;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return len[x] > len[y]; });
+  std::vector<int> len_sorted(a.n_series);
+  for (int i = 0; i < a.n_series; i++) len_sorted[i] = len[order[i]];
+  int W = fac_slots(hm, fe, a.n_series);
+  if (counts) W = std::min(W, a.acc_slots);
+  const size_t slot_bytes = (size_t)P.slot_doubles * sizeof(double);
+  const size_t budget = (size_t)24 << 30;
+  while (W > 1 && (size_t)W * slot_bytes > budget) W--;
+  if (fe.slots_cap < (size_t)W * P.slot_doubles) {
+    cudaFree(fe.d_slots);
+    fe.d_slots = nullptr;
+    fe.slots_cap = 0;
+    NIPGPU_CUDA(cudaMalloc((void**)&fe.d_slots, (size_t)W * slot_bytes));
+    fe.slots_cap = (size_t)W * P.slot_doubles;
+  }
+  if (fe.max_slots < W) {
+    cudaFree(fe.d_ll_run); cudaFree(fe.d_bad_run);
+    fe.d_ll_run = nullptr; fe.d_bad_run = nullptr;
+    NIPGPU_CUDA(cudaMalloc((void**)&fe.d_ll_run, W * sizeof(double)));
+    NIPGPU_CUDA(cudaMalloc((void**)&fe.d_bad_run, W * sizeof(int)));
+    fe.max_slots = W;
+  }
+  int *d_order = nullptr, *d_len_sorted = nullptr;
+  if (int e = dev_up(&d_order, order, st)) return e;
+  if (int e = dev_up(&d_len_sorted, len_sorted, st)) { cudaFree(d_order); return e; }
+  auto done = [&](int rc) {
+    cudaStreamSynchronize(st);
+    cudaFree(d_order);
+    cudaFree(d_len_sorted);
+    return rc;
+  };
+  RunCtx R{&P, &a, &fe, d_len_sorted, hm.S, hm.nif, false};
+  SlotCtx X;
+  X.slots = fe.d_slots; X.slot_stride = P.slot_doubles; X.fac = fe.d_fac; X.pool = P.d_pool;
+  X.obs = a.d_obs; X.n_obs = a.n_obs; X.row_off = a.d_row_off; X.order = d_order;
+  const long long a0_off = fe.a0_tensor >= 0 ? fe.tensors[fe.a0_tensor].off : 0;
+  const bool filtered = a.forward_only && queries;
+  const bool backward = !a.forward_only && (queries || counts);
+  const int S = hm.S;
+  const int prep_blocks = std::max(1, std::min(64, (S + 255) / 256));
+  auto alive_at = [&](int wave0, int nslots, int t) {
+    int n = 0;
+    while (n < nslots && len_sorted[wave0 + n] > t) n++;
+    return n;
+  };
+  for (int wave0 = 0; wave0 < a.n_series; wave0 += W) {
+    const int nslots = std::min(W, a.n_series - wave0);
+    const int Tw = len_sorted[wave0];
+    X.wave0 = wave0;
+    for (int t = 0; t < Tw; t++) {
+      const int alive = alive_at(wave0, nslots, t);
+      if (alive == 0) break;
+      X.t = t;
+      k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, a.d_alpha, hm.nif > 0 ? S : 0,
+                                                              P.o_alpha_in, P.o_beta, a0_off, filtered ? 2 : 0,
+                                                              fe.d_ll_run, fe.d_bad_run, t == 0);
+      NIPGPU_LAUNCHED();
+      R.no_beta_update = false;
+      for (const FacInstr& ins : P.fwd)
+        if (int e = run_instr(R, ins, X, alive, st)) return done(e);
+      if (filtered || (hm.nif == 0 && (queries || counts))) {
+        // filtered marginals (or a model without an interface): beliefs of this slice alone
+        R.no_beta_update = true;
+        for (const FacInstr& ins : P.bwd)
+          if (int e = run_instr(R, ins, X, alive, st)) return done(e);
+      }
+    }
+    if (backward && hm.nif > 0) {
+      R.no_beta_update = false;
+      for (int t = Tw - 1; t >= 0; t--) {
+        const int alive = alive_at(wave0, nslots, t);
+        if (alive == 0) continue;
+        X.t = t;
+        k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, a.d_alpha, S, P.o_alpha_in, P.o_beta,
+                                                                a0_off, 1, fe.d_ll_run, fe.d_bad_run, 0);
+        NIPGPU_LAUNCHED();
+        for (const FacInstr& ins : P.bwd)
+          if (int e = run_instr(R, ins, X, alive, st)) return done(e);
+      }
+    }
+  }
+  return done(NIPGPU_OK);
+}
+
+}  // namespace nipgpu

@@ -18,9 +18,10 @@ from cases import (ALL_CASES, EM_CASES, LIKELIHOOD_CASES, SLICE_CASES, Case, ass
 pytestmark = pytest.mark.gpu
 
 ENGINES = [1, 0]  # NIPGPU_ENGINE_JTREE, NIPGPU_ENGINE_AUTO (chain engine when the model allows)
+ENGINES3 = [1, 0, 3]  # ... and NIPGPU_ENGINE_FACTOR (the join tree factor by factor, any model)
 
 
-@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("engine", ENGINES3)
 @pytest.mark.parametrize("name", ALL_CASES)
 def test_inference_golden(gpu_lib, name, engine):
     c = Case(name)
@@ -47,7 +48,7 @@ def test_inference_golden(gpu_lib, name, engine):
     m.close()
 
 
-@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("engine", ENGINES3)
 def test_unmarked_columns_are_ignored(gpu_lib, oracle_lib, engine):
     """NIP_MARK semantics (src/nip.c:993): only marked variables enter evidence"""
     c = Case("hmm12_two_leaves")
@@ -205,7 +206,7 @@ def test_empty_and_single_slice(gpu_lib, engine, mode, monkeypatch):
     assert st == 0 and L == 0.0 and np.all(counts == 1.0)      # only the pseudo-count
 
 
-@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("engine", ENGINES3)
 @pytest.mark.parametrize("name", EM_CASES)
 def test_em_golden(gpu_lib, name, engine):
     """each EM iteration from the reference's own inputs: M-step tables/priors, then
@@ -228,7 +229,7 @@ def test_em_golden(gpu_lib, name, engine):
         counts_in = unhex(it["counts"])
 
 
-@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("engine", ENGINES3)
 def test_bad_luck_is_reported(gpu_lib, oracle_lib, engine):
     """an impossible observation (m2 == 0) must surface as NIP_ERROR_BAD_LUCK
     (src/nip.c:1827-1854), a clean set must not"""
@@ -315,13 +316,13 @@ def test_launches_are_counted(gpu_lib):
 
 # ---- factorial DBN (config C3): cliques too large for shared memory ------------------------
 @pytest.mark.parametrize("coupled", [True, False])
-@pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None), (8, "grid")])
+@pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None), (8, "grid"), (6, "factor"), (8, "factor")])
 def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, coupled, monkeypatch):
     """4 ring-coupled chains (C3's topology) with cliques too large for shared memory, in the
     per-CTA HBM workspace and with the whole grid streaming one sequence: smoothing, filtering
     and the E-step against the oracle"""
     from nip_b200.synth import FactorialSpec
-    if mode:
+    if mode and mode != "factor":
         monkeypatch.setenv("NIPGPU_JT_MODE", mode)
     sp = FactorialSpec(ns, 3, seed=4, coupled=coupled)
     fm = sp.flat()
@@ -330,7 +331,8 @@ def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, coupled, monkeypatch
     series = [data[0], data[1][:2], data[2][:1]]
     query = [4, 7, 9, 2]                            # X0, X3, W1, Y2
     om = oracle_lib.model(fm)
-    m = gpu_lib.Model(fm, engine=1)
+    m = gpu_lib.Model(fm, engine=3 if mode == "factor" else 1)
+    assert m.engine == (3 if mode == "factor" else 1)
     b = m.batch(sp.obs_vars, series)
     for fwd in (False, True):
         post, ll = b.infer(query, forward_only=fwd)
@@ -345,7 +347,8 @@ def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, coupled, monkeypatch
     assert_close(L, ll_want, "factorial ns=%d EM loglik" % ns)
 
 
-def test_c3_full_size_vs_oracle(gpu_lib, oracle_lib):
+@pytest.mark.parametrize("engine", [1, 0])
+def test_c3_full_size_vs_oracle(gpu_lib, oracle_lib, engine):
     """config C3 at its real size — 16 states per chain, three 16^6-entry cliques (403 MB of
     tables), interface of 65 536 states — one short series against the oracle (which needs
     about ten seconds per slice), plus the size-independent checks"""
@@ -354,7 +357,8 @@ def test_c3_full_size_vs_oracle(gpu_lib, oracle_lib):
     fm = sp.flat()
     series = [sp.sample(1, 2, seed=2)[0]]
     query = [4, 6, 9]                               # X0, X2, W1
-    m = gpu_lib.Model(fm, engine=1)
+    m = gpu_lib.Model(fm, engine=engine)
+    assert m.engine == (1 if engine == 1 else 3)    # left to itself the library evaluates C3 factor by factor
     b = m.batch(sp.obs_vars, series)
     post, ll = b.infer(query)
     want, llw = oracle_lib.model(fm).infer(sp.obs_vars, series[0], query)
