@@ -251,79 +251,109 @@ struct SlotCtx {
   const long long* row_off;
   const int* order;    // sorted position -> series
   int wave0, t;
+  long long saved_off; // where this slice's saved tensors start inside the slot area
 };
 
 __device__ __forceinline__ double fac_inv(double x) { return x != 0 ? 1.0 / x : 0.0; }
 
-// out(o) [chunk] = prod_{O-only operands}(o) * sum_{r in chunk} prod_{k < NR} operand_k(o, r)
-template <int NR>
+// result(o) [chunk] = prod_{epilogue operands}(o) * sum_{r in chunk} prod_k operand_k(o, r)
+// for the TJ results of a thread at once: `NSH` in-loop operands do not depend on the tile
+// variable (one load per term of the tile), `NV` do (TJ loads).
+template <int NSH, int NV, int TJ>
 __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
-  extern __shared__ int s_roff[];   // [NR][Rc]
-  const int slot = blockIdx.z, chunk = blockIdx.y;
-  const int r0 = chunk * s.Rc, r1 = min(s.R, r0 + s.Rc), nr = r1 - r0;
+  constexpr int NR = NSH + NV;
+  extern __shared__ int s_roff[];   // [NR][cpc * Rc]
+  const int slot = blockIdx.z;
+  const int span = s.cpc * s.Rc;                       // summed indices covered by this CTA
+  const int rb0 = blockIdx.y * span, rb1 = min(s.R, rb0 + span);
   for (int k = 0; k < NR; k++)
-    for (int i = threadIdx.x; i < nr; i += blockDim.x) s_roff[k * s.Rc + i] = X.pool[s.opR[k].roff + r0 + i];
+    for (int i = threadIdx.x; i < rb1 - rb0; i += blockDim.x) s_roff[k * span + i] = X.pool[s.opR[k].roff + rb0 + i];
   __syncthreads();
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= s.n_out) return;
+  int o, chunk;
+  if (s.cpc > 1) { o = threadIdx.x % s.othr; chunk = blockIdx.y * s.cpc + threadIdx.x / s.othr; }
+  else { o = blockIdx.x * blockDim.x + threadIdx.x; chunk = blockIdx.y; }
+  if (o >= s.n_thr || chunk >= s.n_chunks || (s.cpc > 1 && threadIdx.x / s.othr >= s.cpc)) return;
+  const int r0 = chunk * s.Rc, r1 = min(s.R, r0 + s.Rc), nr = r1 - r0;
+  const int* roff = s_roff + (r0 - rb0);
   const int oh = o / s.F, ol = o - oh * s.F;
   double* area = X.slots + (long long)slot * X.slot_stride;
   const long long row = X.row_off[X.order[X.wave0 + slot]] + X.t;
   const double* ptr[NR > 0 ? NR : 1];
-  int ev[NR > 0 ? NR : 1];
+  int ev[NR > 0 ? NR : 1], ts[NR > 0 ? NR : 1];
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     const FacOpDev& op = s.opR[k];
     const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
+    ts[k] = op.tstride;
     if (op.kind == FT_EVID) {
       const int obs = X.obs[row * X.n_obs + op.col];
-      ev[k] = obs < 0 ? INT_MIN : obs - ob;   // the operand is 1 where roff == ev (everywhere when missing)
+      ev[k] = obs < 0 ? INT_MIN : obs - ob;   // the operand is 1 where its offset == ev (everywhere when missing)
       ptr[k] = nullptr;
     } else {
       ev[k] = 0;
-      ptr[k] = (op.kind == FT_MODEL ? X.fac : area) + op.off + ob;
+      ptr[k] = (op.kind == FT_MODEL ? X.fac : area + (op.kind == FT_SAVED ? X.saved_off : 0)) + op.off + ob;
     }
   }
-  double acc = 0;
-  if (NR == 0) acc = 1.0;
-  else {
-    for (int r = 0; r < nr; r++) {
-      double term = 1.0;
+  double acc[TJ];
 #pragma unroll
-      for (int k = 0; k < NR; k++) {
-        const int ro = s_roff[k * s.Rc + r];
-        double v;
-        if (ptr[k]) {
-          v = ptr[k][ro];
-          if (s.opR[k].inv) v = fac_inv(v);
-        } else {
-          v = (ev[k] == INT_MIN || ro == ev[k]) ? 1.0 : 0.0;
-        }
-        term = k == 0 ? v : term * v;
+  for (int j = 0; j < TJ; j++) acc[j] = NR == 0 ? 1.0 : 0.0;
+  if (NR > 0) {
+#pragma unroll 4
+    for (int r = 0; r < nr; r++) {
+      double sh = 1.0;
+#pragma unroll
+      for (int k = 0; k < NSH; k++) {
+        const int ro = roff[k * span + r];
+        const double v = ptr[k] ? ptr[k][ro] : ((ev[k] == INT_MIN || ro == ev[k]) ? 1.0 : 0.0);
+        sh = k == 0 ? v : sh * v;
       }
-      acc += term;
+      double term[TJ];
+#pragma unroll
+      for (int j = 0; j < TJ; j++) term[j] = sh;
+#pragma unroll
+      for (int k = NSH; k < NR; k++) {
+        const int ro = roff[k * span + r];
+#pragma unroll
+        for (int j = 0; j < TJ; j++) {
+          const int off = ro + j * ts[k];
+          const double v = ptr[k] ? ptr[k][off] : ((ev[k] == INT_MIN || off == ev[k]) ? 1.0 : 0.0);
+          term[j] = (NSH == 0 && k == NSH) ? v : term[j] * v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TJ; j++) acc[j] += term[j];
     }
   }
   for (int k = 0; k < s.nO; k++) {
     const FacOpDev& op = s.opO[k];
     const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
-    double v;
-    if (op.kind == FT_EVID) {
-      const int obs = X.obs[row * X.n_obs + op.col];
-      v = (obs < 0 || obs == ob) ? 1.0 : 0.0;
-    } else {
-      v = ((op.kind == FT_MODEL ? X.fac : area) + op.off)[ob];
-      if (op.inv) v = fac_inv(v);
+    int obs = 0;
+    const double* q = nullptr;
+    if (op.kind == FT_EVID) obs = X.obs[row * X.n_obs + op.col];
+    else q = (op.kind == FT_MODEL ? X.fac : area + (op.kind == FT_SAVED ? X.saved_off : 0)) + op.off;
+#pragma unroll
+    for (int j = 0; j < TJ; j++) {
+      const int off = ob + j * op.tstride;
+      double v;
+      if (op.kind == FT_EVID) v = (obs < 0 || obs == off) ? 1.0 : 0.0;
+      else {
+        v = q[off];
+        if (op.inv) v = fac_inv(v);
+      }
+      acc[j] *= v;
     }
-    acc *= v;
   }
-  if (s.n_chunks > 1) area[s.out_off + (long long)chunk * s.n_out + o] = acc;   // out_off = partial area
-  else area[s.out_off + o] = acc;
+  // the result (or this chunk's partial sums, laid out like the result)
+  const int oo = X.pool[s.out.ohi + oh] + X.pool[s.out.olo + ol];
+  double* dst = area + (s.out.kind == FT_SAVED ? X.saved_off : 0) + s.out.off +
+                (s.n_chunks > 1 ? (long long)chunk * s.n_out : 0);
+#pragma unroll
+  for (int j = 0; j < TJ; j++) dst[oo + j * s.out.tstride] = acc[j];
 }
 
 // out[o] = sum over chunks of partial[chunk][o], fixed order
 __global__ void k_fac_reduce(SlotCtx X, long long part_off, long long out_off, int n_out, int n_chunks) {
-  double* area = X.slots + (long long)blockIdx.y * X.slot_stride;
+  double* area = X.slots + (long long)blockIdx.y * X.slot_stride;   // out_off already holds the saved shift
   const double* part = area + part_off;
   if (n_chunks >= 32) {   // a warp per output
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -528,18 +558,22 @@ struct Compiler {
   const FacEngine& fe;
   std::vector<FacTensor> T;
   std::vector<int> pool;
-  long long slot_top = 0;
+  long long slot_top = 0, saved_top = 0;
   long long partial_max = 0;
+  bool failed = false;
+  bool saving = false;      // tensors created now go to the per-slice saved region
+  std::map<std::vector<int>, int> relayouts;   // (tensor, first variable) -> permuted copy, valid in the current section
 
   Compiler(const HostModel& h, const FacEngine& f) : hm(h), fe(f), T(f.tensors.begin(), f.tensors.begin() + f.n_model_tensors) {}
 
   int slot_tensor(const std::vector<int>& vars) {
     FacTensor t;
     t.vars = vars;
-    t.kind = FT_SLOT;
+    t.kind = saving ? FT_SAVED : FT_SLOT;
     t.size = prod_card(hm, vars);
-    t.off = slot_top;
-    slot_top += (t.size + 15) / 16 * 16;
+    long long& top = saving ? saved_top : slot_top;
+    t.off = top;
+    top += (t.size + 15) / 16 * 16;
     T.push_back(t);
     return (int)T.size() - 1;
   }
@@ -553,78 +587,166 @@ struct Compiler {
     return (int)T.size() - 1;
   }
 
-  // tables of one operand: offset as a function of the output index (split o = oh * F + ol) and of
-  // the summed index
-  void tables(const FacTensor& t, const std::vector<int>& ovars, int F, long long n_out,
+  // index tables of one tensor over the thread space (variables `tv`, the last one scaled by
+  // `last_mult` when it is the tile variable) and over the summed variables
+  void tables(const FacTensor& t, const std::vector<int>& tv, int last_mult, int F, long long n_thr,
               const std::vector<int>& rvars, long long R, FacOpDev& d) {
-    auto fill = [&](const std::vector<int>& vars, long long from, long long count, long long unit) {
-      // offsets of indices from, from+unit, ... (count of them) over `vars`
+    auto fill = [&](const std::vector<int>& vars, int lm, long long count, long long unit) {
       const int pos = (int)pool.size();
       for (long long x = 0; x < count; x++) {
-        long long rem = from + x * unit, o = 0;
-        for (int v : vars) {
-          o += (rem % hm.card[v]) * stride_in(hm, t.vars, v);
-          rem /= hm.card[v];
+        long long rem = x * unit, o = 0;
+        for (size_t a = 0; a < vars.size(); a++) {
+          const int v = vars[a];
+          const int c = (a + 1 == vars.size() && lm > 1) ? hm.card[v] / lm : hm.card[v];
+          const long long dig = (rem % c) * ((a + 1 == vars.size() && lm > 1) ? lm : 1);
+          o += dig * stride_in(hm, t.vars, v);
+          rem /= c;
         }
         pool.push_back((int)o);
       }
       return pos;
     };
-    d.olo = fill(ovars, 0, F, 1);
-    d.ohi = fill(ovars, 0, (n_out + F - 1) / F, F);
-    d.roff = fill(rvars, 0, R, 1);
+    d.olo = fill(tv, last_mult, F, 1);
+    d.ohi = fill(tv, last_mult, (n_thr + F - 1) / F, F);
+    d.roff = fill(rvars, 1, R, 1);
   }
 
-  FacInstr contract(int out, const std::vector<FacOpRef>& ops) {
-    FacInstr ins;
-    ins.kind = FI_CONTRACT;
-    FacStepDev& s = ins.step;
-    const std::vector<int>& ovars = T[out].vars;
+  // Adds to `prog` the contraction out(ovars) = sum over the other variables of prod(ops).
+  // fixed: the result keeps the variable order of `ovars`; otherwise the order is chosen here
+  // (the variable along which consecutive threads run comes first).  Returns the result tensor.
+  int contract(std::vector<FacInstr>& prog, const std::vector<int>& ovars_in, bool fixed, std::vector<FacOpRef> ops,
+               bool needs_history = false, bool relayout = true) {
     std::vector<int> rvars;
     for (const FacOpRef& o : ops)
       for (int v : T[o.tensor].vars)
-        if (!has_var(ovars, v) && !has_var(rvars, v)) rvars.push_back(v);
-    // the summed digits run fastest over the variable that is fastest in the biggest operand
-    const long long n_out = T[out].size, R = prod_card(hm, rvars);
-    int F = 1;
-    for (int v : ovars) {
-      if (F >= 128) break;
-      F *= hm.card[v];
-    }
-    if (n_out > INT32_MAX || R > INT32_MAX) { ins.kind = -1; return ins; }
-    s.n_out = (int)n_out;
-    s.F = F;
-    s.R = (int)R;
-    s.nR = s.nO = 0;
-    for (const FacOpRef& o : ops) {
-      const FacTensor& t = T[o.tensor];
-      bool dep = false;
-      for (int v : t.vars) dep = dep || has_var(rvars, v);
-      FacOpDev d{};
-      d.off = t.off;
-      d.kind = t.kind;
-      d.inv = o.inv ? 1 : 0;
-      d.col = t.col;
-      tables(t, ovars, F, n_out, rvars, dep ? R : 0, d);
-      if (dep) {
-        if (s.nR >= kFacMaxOps) { ins.kind = -1; return ins; }
-        s.opR[s.nR++] = d;
-      } else {
-        if (s.nO >= kFacMaxOps) { ins.kind = -1; return ins; }
-        s.opO[s.nO++] = d;
+        if (!has_var(ovars_in, v) && !has_var(rvars, v)) rvars.push_back(v);
+    const long long R = prod_card(hm, rvars);
+    auto depends = [&](const FacTensor& t) {
+      for (int v : t.vars)
+        if (has_var(rvars, v)) return true;
+      return false;
+    };
+    // ---- the variable consecutive threads run along ----
+    const long long kBig = 1 << 17;     // tensors above this are not copied into another order
+    int v0 = ovars_in.empty() ? -1 : ovars_in[0];
+    if (!fixed && ovars_in.size() > 1) {
+      double best = -1;
+      for (int v : ovars_in) {
+        double sc = 0;
+        for (const FacOpRef& o : ops) {
+          const FacTensor& t = T[o.tensor];
+          if (t.kind == FT_EVID || !has_var(t.vars, v) || t.vars[0] == v) continue;
+          sc += t.size > kBig ? 64.0 * t.size * (depends(t) ? (double)R : 1.0) : (double)t.size;
+        }
+        if (best < 0 || sc < best) { best = sc; v0 = v; }
       }
     }
+    // operands that hold v0 but not as their fastest variable: a copy in another order, if small
+    if (v0 >= 0 && relayout)
+      for (FacOpRef& o : ops) {
+        const FacTensor t = T[o.tensor];
+        if (t.kind == FT_EVID || !has_var(t.vars, v0) || t.vars[0] == v0 || t.size > kBig || t.vars.size() < 2) continue;
+        const std::vector<int> key{o.tensor, v0};
+        auto it = relayouts.find(key);
+        if (it == relayouts.end()) {
+          std::vector<int> nv{v0};
+          for (int v : t.vars)
+            if (v != v0) nv.push_back(v);
+          const int copy = contract(prog, nv, true, {FacOpRef{o.tensor, false}}, false, false);
+          it = relayouts.emplace(key, copy).first;
+        }
+        o.tensor = it->second;
+      }
+    std::vector<int> ovars = ovars_in;
+    if (!fixed && v0 >= 0) {
+      ovars.clear();
+      ovars.push_back(v0);
+      for (int v : ovars_in)
+        if (v != v0) ovars.push_back(v);
+    }
+    const int out = slot_tensor(ovars);
+    // ---- the tile variable: the output variable the in-loop operands depend on least ----
+    int vt = -1, TJ = 1;
+    if (R > 1) {
+      double best = -1;
+      for (int v : ovars) {
+        if (v == v0 && ovars.size() > 1) continue;
+        if (hm.card[v] % 4 != 0) continue;
+        double sc = 0;
+        int nvar = 0;
+        for (const FacOpRef& o : ops) {
+          const FacTensor& t = T[o.tensor];
+          if (!depends(t) || !has_var(t.vars, v)) continue;
+          sc += (double)t.size;
+          nvar++;
+        }
+        if (nvar > kFacMaxVar) continue;
+        if (best < 0 || sc < best) { best = sc; vt = v; }
+      }
+      if (vt >= 0) TJ = 4;
+    }
+    std::vector<int> tv;      // thread space: v0 first, the tile variable last
+    for (int v : ovars)
+      if (v != vt) tv.push_back(v);
+    if (vt >= 0) tv.push_back(vt);
+    const long long n_out = T[out].size, n_thr = n_out / TJ;
+    FacInstr ins;
+    ins.kind = FI_CONTRACT;
+    ins.needs_history = needs_history;
+    FacStepDev& s = ins.step;
+    int F = 1;
+    for (size_t a = 0; a < tv.size(); a++) {
+      if (F >= 128) break;
+      F *= (tv[a] == vt) ? hm.card[tv[a]] / TJ : hm.card[tv[a]];
+    }
+    if (n_out > INT32_MAX || R > INT32_MAX) { failed = true; return out; }
+    s.n_thr = (int)n_thr; s.n_out = (int)n_out; s.F = F; s.R = (int)R; s.TJ = TJ;
+    s.nSh = s.nVar = s.nO = 0;
+    auto dev = [&](const FacTensor& t, bool inv, bool dep) {
+      FacOpDev d{};
+      d.off = t.off; d.kind = t.kind; d.inv = inv ? 1 : 0; d.col = t.col;
+      d.tstride = vt >= 0 ? (int)stride_in(hm, t.vars, vt) : 0;
+      tables(t, tv, vt >= 0 ? TJ : 1, F, n_thr, rvars, dep ? R : 0, d);
+      return d;
+    };
+    std::vector<FacOpDev> shared, varying;
+    for (const FacOpRef& o : ops) {
+      const FacTensor& t = T[o.tensor];
+      const bool dep = depends(t);
+      const FacOpDev d = dev(t, o.inv, dep);
+      if (!dep) {
+        if (s.nO >= kFacMaxOps) { failed = true; return out; }
+        s.opO[s.nO++] = d;
+      } else {
+        if (o.inv) { failed = true; return out; }
+        (d.tstride != 0 ? varying : shared).push_back(d);
+      }
+    }
+    if ((int)(shared.size() + varying.size()) > kFacMaxOps || (int)varying.size() > kFacMaxVar) { failed = true; return out; }
+    if (TJ > 1 && (int)shared.size() > 4) { failed = true; return out; }
+    for (const FacOpDev& d : shared) s.opR[s.nSh++] = d;
+    for (const FacOpDev& d : varying) s.opR[s.nSh + s.nVar++] = d;
+    s.out = dev(T[out], false, false);
     // split the summed range so that a slot has at least ~64k threads, at least 8 terms each
     const long long want = 65536;
-    long long chunks = std::max<long long>(1, std::min<long long>((want + n_out - 1) / n_out, R / 8));
+    long long chunks = std::max<long long>(1, std::min<long long>((want + n_thr - 1) / n_thr, R / 8));
+    chunks = std::min<long long>(chunks, 2048);     // the partial sums are added up by one warp per result
     chunks = std::max(chunks, (R + 1023) / 1024);
-    if (s.nR == 0) chunks = 1;
+    if (s.nSh + s.nVar == 0) chunks = 1;
     s.Rc = (int)((R + chunks - 1) / chunks);
     s.n_chunks = (int)((R + s.Rc - 1) / s.Rc);
-    s.out_off = T[out].off;
+    s.cpc = 1;
+    s.othr = 128;
+    if (n_thr < 128 && s.n_chunks > 1) {   // few results: several chunks share a CTA
+      int p2 = 1;
+      while (p2 < n_thr) p2 *= 2;
+      s.othr = p2;
+      s.cpc = std::max(1, std::min(128 / p2, 2048 / std::max(s.Rc, 1)));
+    }
     if (s.n_chunks > 1) partial_max = std::max(partial_max, (long long)s.n_chunks * n_out);
-    ins.flops = (double)n_out * (double)R * std::max(1, s.nR);
-    return ins;
+    ins.flops = (double)n_out * (double)R * std::max(1, s.nSh + s.nVar);
+    prog.push_back(ins);
+    return out;
   }
 };
 
@@ -661,46 +783,42 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
     L[hm.family[v]].push_back(FacOpRef{C.evid_tensor(v, k), false});
     var_seen[v] = 1;
   }
-  const int S = hm.S;
-  int t_alpha_in = -1, t_beta = -1, t_alpha_new = -1, t_bprev = -1;
+  int t_alpha_in = -1, t_beta = -1;
   if (hm.nif > 0) {
     t_alpha_in = C.slot_tensor(hm.prev);
     t_beta = C.slot_tensor(hm.outg);
-    t_alpha_new = C.slot_tensor(hm.outg);
-    t_bprev = C.slot_tensor(hm.prev);
     P.o_alpha_in = C.T[t_alpha_in].off;
     P.o_beta = C.T[t_beta].off;
-    P.o_alpha_new = C.T[t_alpha_new].off;
-    P.o_bprev = C.T[t_bprev].off;
   }
   auto sep_vars = [&](int s) { return std::vector<int>(hm.sepset_vars(s), hm.sepset_vars(s) + hm.sepset_dim(s)); };
   // ---- upward messages (towards the root = out_clique), children before parents ----
   std::vector<int> up(nc, -1), down(nc, -1);
   std::vector<FacInstr> ups;
+  C.saving = true;
   for (int i = nc - 1; i >= 0; i--) {
     const int c = fe.preorder[i];
     if (c == fe.root) continue;
-    up[c] = C.slot_tensor(sep_vars(fe.psep[c]));
     std::vector<FacOpRef> ops = L[c];
     if (hm.nif > 0 && c == hm.in_clique) ops.push_back(FacOpRef{t_alpha_in, false});
     for (int d : fe.children[c]) ops.push_back(FacOpRef{up[d], false});
-    ups.push_back(C.contract(up[c], ops));
+    up[c] = C.contract(ups, sep_vars(fe.psep[c]), false, ops);
   }
-  // ---- forward program ----
+  C.saving = false;
+  P.n_ups = (int)ups.size();
+  const std::map<std::vector<int>, int> relayouts_after_ups = C.relayouts;
+  // ---- forward program: the messages, then alpha_t (or, without an interface, the slice's mass) ----
   P.fwd = ups;
-  if (hm.nif == 0) {   // no interface: only the mass of the slice (a 0-dimensional "alpha")
-    t_alpha_new = C.slot_tensor({});
-    P.o_alpha_new = C.T[t_alpha_new].off;
-  }
   {
     std::vector<FacOpRef> ops = L[fe.root];
     if (hm.nif > 0 && fe.root == hm.in_clique) ops.push_back(FacOpRef{t_alpha_in, false});
     for (int d : fe.children[fe.root]) ops.push_back(FacOpRef{up[d], false});
-    P.fwd.push_back(C.contract(t_alpha_new, ops));
+    const int t_alpha_new = C.contract(P.fwd, hm.nif > 0 ? hm.outg : std::vector<int>{}, true, ops);
+    P.o_alpha_new = C.T[t_alpha_new].off;
     FacInstr s;
     s.kind = FI_SETTLE_FWD;
     P.fwd.push_back(s);
   }
+  C.relayouts = relayouts_after_ups;
   // ---- backward program: targets, their host cliques ----
   struct Target { std::vector<int> vars; int kind, var; long long dst; bool only_t0; int clique; };
   std::vector<Target> targets;
@@ -724,13 +842,27 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
       targets.push_back(t);
     }
   }
-  // place every target in the clique whose belief grows least (largest targets first)
+  // Place every target (largest first) where it costs least.  A belief costs one pass over the
+  // whole clique whatever it keeps (terms = clique entries), so targets gather in cliques that
+  // already need a belief; a leaf clique gets its message from its parent's belief, so placing
+  // a target there also makes the parent keep the sepset's variables.
   std::vector<std::vector<int>> U(nc);
   auto grown = [&](int c, const std::vector<int>& vars) {
     long long n = prod_card(hm, U[c]);
     for (int v : vars)
       if (!has_var(U[c], v)) n *= hm.card[v];
-    return n;
+    return (double)n;
+  };
+  auto is_leaf_kid = [&](int c) {
+    return c != fe.root && fe.children[c].empty() && !(hm.nif > 0 && c == hm.in_clique);
+  };
+  auto place_cost = [&](int c, const std::vector<int>& vars) {
+    double cost = (U[c].empty() ? (double)hm.csize[c] : 0.0) + grown(c, vars);
+    if (is_leaf_kid(c)) {
+      const int p = fe.parent[c];
+      cost += (U[p].empty() ? (double)hm.csize[p] : 0.0) + grown(p, sep_vars(fe.psep[c]));
+    }
+    return cost;
   };
   std::vector<int> order(targets.size());
   std::iota(order.begin(), order.end(), 0);
@@ -739,19 +871,21 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
   });
   for (int ti : order) {
     Target& t = targets[ti];
-    long long best = -1;
+    double best = -1;
     for (int c = 0; c < nc; c++) {
       bool holds = true;
       for (int v : t.vars) holds = holds && hm.var_pos(c, v) >= 0;
       if (!holds) continue;
-      // cost: entries of the grown belief; the clique table itself bounds it
-      const long long g = grown(c, t.vars);
+      const double g = place_cost(c, t.vars);
       const bool better = best < 0 || g < best || (g == best && c == hm.family[t.vars[0]]);
       if (better) { best = g; t.clique = c; }
     }
     if (t.clique < 0) { set_error("factor engine: a target is held by no clique"); return NIPGPU_EINVAL; }
     for (int v : t.vars)
       if (!has_var(U[t.clique], v)) U[t.clique].push_back(v);
+    if (is_leaf_kid(t.clique))
+      for (int v : sep_vars(fe.psep[t.clique]))
+        if (!has_var(U[fe.parent[t.clique]], v)) U[fe.parent[t.clique]].push_back(v);
   }
   // which subtrees need a downward message
   std::vector<char> needed(nc, 0);
@@ -784,15 +918,11 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
       std::vector<int> uv;   // clique order
       for (int k = 0; k < hm.clique_dim(c); k++)
         if (has_var(U[c], hm.clique_vars(c)[k])) uv.push_back(hm.clique_vars(c)[k]);
-      belief = C.slot_tensor(uv);
-      P.bwd.push_back(C.contract(belief, all));
+      belief = C.contract(P.bwd, uv, false, all);
       for (const Target& t : targets) {
         if (t.clique != c) continue;
         int src = belief;
-        if (t.vars != uv) {
-          src = C.slot_tensor(t.vars);
-          P.bwd.push_back(C.contract(src, {FacOpRef{belief, false}}));
-        }
+        if (t.vars != C.T[belief].vars) src = C.contract(P.bwd, t.vars, true, {FacOpRef{belief, false}});
         FacInstr ins;
         ins.kind = t.kind;
         ins.src_off = C.T[src].off;
@@ -802,38 +932,33 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
         ins.only_t0 = t.only_t0;
         P.bwd.push_back(ins);
       }
-      for (int d : leaf_kids) {
-        down[d] = C.slot_tensor(sep_vars(fe.psep[d]));
-        P.bwd.push_back(C.contract(down[d], {FacOpRef{belief, false}, FacOpRef{up[d], true}}));
-      }
+      for (int d : leaf_kids)
+        down[d] = C.contract(P.bwd, sep_vars(fe.psep[d]), false, {FacOpRef{belief, false}, FacOpRef{up[d], true}});
     }
     for (int d : inner_kids) {
-      down[d] = C.slot_tensor(sep_vars(fe.psep[d]));
       std::vector<FacOpRef> ops;
       for (const FacOpRef& o : all)
         if (o.tensor != up[d]) ops.push_back(o);
-      P.bwd.push_back(C.contract(down[d], ops));
+      down[d] = C.contract(P.bwd, sep_vars(fe.psep[d]), false, ops);
     }
     if (hm.nif > 0 && c == hm.in_clique) {   // message to slice t-1: everything but alpha_{t-1}
       std::vector<FacOpRef> ops;
       for (const FacOpRef& o : all)
         if (o.tensor != t_alpha_in) ops.push_back(o);
-      FacInstr ins = C.contract(t_bprev, ops);
-      ins.needs_history = true;
-      P.bwd.push_back(ins);
+      const int t_bprev = C.contract(P.bwd, hm.prev, true, ops, true);
+      P.o_bprev = C.T[t_bprev].off;
       FacInstr nb;
       nb.kind = FI_BETA_NORM;
       nb.needs_history = true;
       P.bwd.push_back(nb);
     }
   }
-  for (const std::vector<FacInstr>* v : {&P.fwd, &P.bwd})
-    for (const FacInstr& i : *v)
-      if (i.kind < 0) { set_error("factor engine: a contraction exceeds the engine's limits"); return NIPGPU_EUNSUPPORTED; }
+  if (C.failed) { set_error("factor engine: a contraction exceeds the engine's limits"); return NIPGPU_EUNSUPPORTED; }
   // partial sums of split contractions live behind the tensors
   P.o_partial = C.slot_top;
   P.partial_doubles = (C.partial_max + 15) / 16 * 16;
   P.slot_doubles = P.o_partial + P.partial_doubles + 16;
+  P.saved_doubles = (C.saved_top + 15) / 16 * 16;
   for (std::vector<FacInstr>* v : {&P.fwd, &P.bwd})
     for (FacInstr& i : *v) {
       if (i.kind != FI_CONTRACT) continue;
@@ -843,15 +968,64 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
   if (int e = dev_up(&P.d_pool, C.pool, st)) return e;
   if (int e = dev_up(&P.d_marked, marked, st)) return e;
   NIPGPU_CUDA(cudaStreamSynchronize(st));
-  (void)S;
   return NIPGPU_OK;
 }
 
-template <int NR>
+template <int NSH, int NV, int TJ>
 void launch_contract_n(const FacStepDev& s, const SlotCtx& X, int alive, cudaStream_t st) {
-  const dim3 grid((s.n_out + 127) / 128, s.n_chunks, alive);
-  const size_t smem = (size_t)std::max(NR, 1) * s.Rc * sizeof(int);
-  k_fac_contract<NR><<<grid, 128, smem, st>>>(s, X);
+  const dim3 grid(s.cpc > 1 ? 1 : (s.n_thr + 127) / 128, (s.n_chunks + s.cpc - 1) / s.cpc, alive);
+  const size_t smem = (size_t)std::max(NSH + NV, 1) * s.cpc * s.Rc * sizeof(int);
+  k_fac_contract<NSH, NV, TJ><<<grid, 128, smem, st>>>(s, X);
+}
+
+template <int NSH, int TJ>
+void launch_contract_v(const FacStepDev& s, const SlotCtx& X, int alive, cudaStream_t st) {
+  if constexpr (TJ == 1) {
+    launch_contract_n<NSH, 0, 1>(s, X, alive, st);
+  } else {
+    switch (s.nVar) {
+      case 1: launch_contract_n<NSH, 1, TJ>(s, X, alive, st); break;
+      case 2: launch_contract_n<NSH, 2, TJ>(s, X, alive, st); break;
+      case 3: launch_contract_n<NSH, 3, TJ>(s, X, alive, st); break;
+      default: launch_contract_n<NSH, 4, TJ>(s, X, alive, st); break;
+    }
+  }
+}
+
+void launch_contract(FacStepDev s, const SlotCtx& X, int alive, cudaStream_t st) {
+  if (s.TJ == 1 || s.nVar == 0) {
+    // no tile (or nothing varies along it: every result of the tile equals the first one, still correct
+    // to compute one by one): all in-loop operands are "shared"
+    if (s.TJ != 1) {   // nVar == 0 with a tile: run it as TJ results per thread of the same sum
+      switch (s.nSh) {
+        case 0: launch_contract_n<0, 0, 4>(s, X, alive, st); break;
+        case 1: launch_contract_n<1, 0, 4>(s, X, alive, st); break;
+        case 2: launch_contract_n<2, 0, 4>(s, X, alive, st); break;
+        case 3: launch_contract_n<3, 0, 4>(s, X, alive, st); break;
+        default: launch_contract_n<4, 0, 4>(s, X, alive, st); break;
+      }
+      return;
+    }
+    switch (s.nSh) {
+      case 0: launch_contract_n<0, 0, 1>(s, X, alive, st); break;
+      case 1: launch_contract_n<1, 0, 1>(s, X, alive, st); break;
+      case 2: launch_contract_n<2, 0, 1>(s, X, alive, st); break;
+      case 3: launch_contract_n<3, 0, 1>(s, X, alive, st); break;
+      case 4: launch_contract_n<4, 0, 1>(s, X, alive, st); break;
+      case 5: launch_contract_n<5, 0, 1>(s, X, alive, st); break;
+      case 6: launch_contract_n<6, 0, 1>(s, X, alive, st); break;
+      case 7: launch_contract_n<7, 0, 1>(s, X, alive, st); break;
+      default: launch_contract_n<8, 0, 1>(s, X, alive, st); break;
+    }
+    return;
+  }
+  switch (s.nSh) {
+    case 0: launch_contract_v<0, 4>(s, X, alive, st); break;
+    case 1: launch_contract_v<1, 4>(s, X, alive, st); break;
+    case 2: launch_contract_v<2, 4>(s, X, alive, st); break;
+    case 3: launch_contract_v<3, 4>(s, X, alive, st); break;
+    default: launch_contract_v<4, 4>(s, X, alive, st); break;
+  }
 }
 
 struct RunCtx {
@@ -870,19 +1044,9 @@ int run_instr(const RunCtx& R, const FacInstr& ins, const SlotCtx& X, int alive,
     case FI_CONTRACT: {
       if (ins.needs_history && (X.t == 0 || R.no_beta_update)) return NIPGPU_OK;
       FacStepDev s = ins.step;
-      const long long final_off = s.out_off;
-      if (s.n_chunks > 1) s.out_off = P.o_partial;
-      switch (s.nR) {
-        case 0: launch_contract_n<0>(s, X, alive, st); break;
-        case 1: launch_contract_n<1>(s, X, alive, st); break;
-        case 2: launch_contract_n<2>(s, X, alive, st); break;
-        case 3: launch_contract_n<3>(s, X, alive, st); break;
-        case 4: launch_contract_n<4>(s, X, alive, st); break;
-        case 5: launch_contract_n<5>(s, X, alive, st); break;
-        case 6: launch_contract_n<6>(s, X, alive, st); break;
-        case 7: launch_contract_n<7>(s, X, alive, st); break;
-        default: launch_contract_n<8>(s, X, alive, st); break;
-      }
+      const long long final_off = s.out.off + (s.out.kind == FT_SAVED ? X.saved_off : 0);
+      if (s.n_chunks > 1) { s.out.off = P.o_partial; s.out.kind = FT_SLOT; }
+      launch_contract(s, X, alive, st);
       NIPGPU_LAUNCHED();
       if (s.n_chunks > 1) {
         const int per = s.n_chunks >= 32 ? 8 : 256;   // outputs per 256-thread CTA
@@ -920,7 +1084,7 @@ int run_instr(const RunCtx& R, const FacInstr& ins, const SlotCtx& X, int alive,
 }  // namespace
 
 #ifndef NIPGPU_FACTOR_MAX_SLOTS
-#define NIPGPU_FACTOR_MAX_SLOTS 32
+#define NIPGPU_FACTOR_MAX_SLOTS 64
 #endif
 int fac_slots(const HostModel& hm, const FacEngine& fe, int n_series) {
   (void)hm; (void)fe;
@@ -954,15 +1118,25 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
   for (int i = 0; i < a.n_series; i++) len_sorted[i] = len[order[i]];
   int W = fac_slots(hm, fe, a.n_series);
   if (counts) W = std::min(W, a.acc_slots);
-  const size_t slot_bytes = (size_t)P.slot_doubles * sizeof(double);
+  // the upward messages of every slice are kept for the backward pass when that fits
+  const bool backward_pass = !a.forward_only && (queries || counts) && hm.nif > 0;
   const size_t budget = (size_t)24 << 30;
+  const int t_longest = std::max(1, len_sorted[0]);
+  bool keep_ups = backward_pass;
+  {
+    static const bool off = [] { const char* p = getenv("NIPGPU_FACTOR_KEEP_UPS"); return p && p[0] == '0'; }();
+    const size_t full = (size_t)(P.slot_doubles + P.saved_doubles * t_longest) * sizeof(double);
+    if (off || (size_t)std::min(W, 16) * full > budget) keep_ups = false;
+  }
+  const long long slot_doubles = P.slot_doubles + P.saved_doubles * (keep_ups ? t_longest : 1);
+  const size_t slot_bytes = (size_t)slot_doubles * sizeof(double);
   while (W > 1 && (size_t)W * slot_bytes > budget) W--;
-  if (fe.slots_cap < (size_t)W * P.slot_doubles) {
+  if (fe.slots_cap < (size_t)W * slot_doubles) {
     cudaFree(fe.d_slots);
     fe.d_slots = nullptr;
     fe.slots_cap = 0;
     NIPGPU_CUDA(cudaMalloc((void**)&fe.d_slots, (size_t)W * slot_bytes));
-    fe.slots_cap = (size_t)W * P.slot_doubles;
+    fe.slots_cap = (size_t)W * slot_doubles;
   }
   if (fe.max_slots < W) {
     cudaFree(fe.d_ll_run); cudaFree(fe.d_bad_run);
@@ -981,8 +1155,25 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
     return rc;
   };
   RunCtx R{&P, &a, &fe, d_len_sorted, hm.S, hm.nif, false};
+  // NIPGPU_FACTOR_TRACE=1: device time of every instruction of the first wave's slices (stderr)
+  static const bool trace = [] { const char* p = getenv("NIPGPU_FACTOR_TRACE"); return p && p[0] == '1'; }();
+  std::vector<double> tr_f(P.fwd.size(), 0.0), tr_b(P.bwd.size(), 0.0);
+  cudaEvent_t te0 = nullptr, te1 = nullptr;
+  if (trace) { cudaEventCreate(&te0); cudaEventCreate(&te1); }
+  auto timed = [&](const FacInstr& ins, const SlotCtx& Xc, int alive, double* slot) -> int {
+    if (!trace) return run_instr(R, ins, Xc, alive, st);
+    cudaEventRecord(te0, st);
+    const int e = run_instr(R, ins, Xc, alive, st);
+    cudaEventRecord(te1, st);
+    cudaEventSynchronize(te1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, te0, te1);
+    *slot += ms;
+    return e;
+  };
   SlotCtx X;
-  X.slots = fe.d_slots; X.slot_stride = P.slot_doubles; X.fac = fe.d_fac; X.pool = P.d_pool;
+  X.slots = fe.d_slots; X.slot_stride = slot_doubles; X.fac = fe.d_fac; X.pool = P.d_pool;
+  X.saved_off = P.slot_doubles;
   X.obs = a.d_obs; X.n_obs = a.n_obs; X.row_off = a.d_row_off; X.order = d_order;
   const long long a0_off = fe.a0_tensor >= 0 ? fe.tensors[fe.a0_tensor].off : 0;
   const bool filtered = a.forward_only && queries;
@@ -1002,18 +1193,19 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
       const int alive = alive_at(wave0, nslots, t);
       if (alive == 0) break;
       X.t = t;
+      X.saved_off = P.slot_doubles + (keep_ups ? (long long)t * P.saved_doubles : 0);
       k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, a.d_alpha, hm.nif > 0 ? S : 0,
                                                               P.o_alpha_in, P.o_beta, a0_off, filtered ? 2 : 0,
                                                               fe.d_ll_run, fe.d_bad_run, t == 0);
       NIPGPU_LAUNCHED();
       R.no_beta_update = false;
-      for (const FacInstr& ins : P.fwd)
-        if (int e = run_instr(R, ins, X, alive, st)) return done(e);
+      for (size_t i = 0; i < P.fwd.size(); i++)
+        if (int e = timed(P.fwd[i], X, alive, &tr_f[i])) return done(e);
       if (filtered || (hm.nif == 0 && (queries || counts))) {
         // filtered marginals (or a model without an interface): beliefs of this slice alone
-        R.no_beta_update = true;
-        for (const FacInstr& ins : P.bwd)
-          if (int e = run_instr(R, ins, X, alive, st)) return done(e);
+        R.no_beta_update = true;    // (the upward messages of this slice were just computed)
+        for (size_t i = P.n_ups; i < P.bwd.size(); i++)
+          if (int e = timed(P.bwd[i], X, alive, &tr_b[i])) return done(e);
       }
     }
     if (backward && hm.nif > 0) {
@@ -1022,13 +1214,30 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
         const int alive = alive_at(wave0, nslots, t);
         if (alive == 0) continue;
         X.t = t;
+        X.saved_off = P.slot_doubles + (keep_ups ? (long long)t * P.saved_doubles : 0);
         k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, a.d_alpha, S, P.o_alpha_in, P.o_beta,
                                                                 a0_off, 1, fe.d_ll_run, fe.d_bad_run, 0);
         NIPGPU_LAUNCHED();
-        for (const FacInstr& ins : P.bwd)
-          if (int e = run_instr(R, ins, X, alive, st)) return done(e);
+        for (size_t i = keep_ups ? P.n_ups : 0; i < P.bwd.size(); i++)
+          if (int e = timed(P.bwd[i], X, alive, &tr_b[i])) return done(e);
       }
     }
+  }
+  if (trace) {
+    auto dump = [&](const char* name, const std::vector<FacInstr>& v, const std::vector<double>& ms) {
+      for (size_t i = 0; i < v.size(); i++) {
+        const FacStepDev& s = v[i].step;
+        if (v[i].kind == FI_CONTRACT)
+          fprintf(stderr, "[factor] %s %2zu contract n_out %8d R %6d chunks %4d TJ %d nSh %d nVar %d nO %d  %9.3f ms  %.2f GFLOP\n", name, i,
+                  s.n_out, s.R, s.n_chunks, s.TJ, s.nSh, s.nVar, s.nO, ms[i], v[i].flops * 1e-9);
+        else
+          fprintf(stderr, "[factor] %s %2zu kind %d n %d  %9.3f ms\n", name, i, v[i].kind, v[i].n, ms[i]);
+      }
+    };
+    dump("fwd", P.fwd, tr_f);
+    dump("bwd", P.bwd, tr_b);
+    cudaEventDestroy(te0);
+    cudaEventDestroy(te1);
   }
   return done(NIPGPU_OK);
 }

@@ -29,7 +29,8 @@
 
 namespace nipgpu {
 
-enum { FT_MODEL = 0, FT_SLOT = 1, FT_EVID = 2 };
+enum { FT_MODEL = 0, FT_SLOT = 1, FT_EVID = 2, FT_SAVED = 3 };   // SAVED: slot tensor kept per slice (the
+                                                                 // upward messages, reused by the backward pass)
 
 struct FacTensor {
   std::vector<int> vars;   // dimension 0 first (fastest)
@@ -44,20 +45,28 @@ struct FacOpRef {
   bool inv;                // use 1/x (x == 0 -> 0): the Hugin division for messages to leaf cliques
 };
 
-// device form of one operand of a contraction
+// device form of one operand of a contraction (or of its result)
 struct FacOpDev {
   long long off;           // offset of the tensor (MODEL: in d_fac, SLOT: in the slot area)
   int kind, inv, col;
   int olo, ohi, roff;      // positions of its index tables in the int pool
+  int tstride;             // step along the tile variable (0: the operand does not hold it)
 };
 
 constexpr int kFacMaxOps = 8;
+constexpr int kFacMaxVar = 4;   // operands that vary along the register tile
 
+// One contraction.  A thread owns TJ results that differ in ONE output variable (the tile
+// variable, chosen so that the heavy operands do not hold it and are loaded once per term);
+// thread index -> (offset of every operand, offset of the result) through the olo/ohi tables,
+// consecutive threads run along the variable that is fastest in the heavy operands' memory.
 struct FacStepDev {
-  int n_out, F, R, Rc, n_chunks;
-  int nR, nO;              // operands that depend on a summed variable / on output variables only
-  FacOpDev opR[kFacMaxOps], opO[kFacMaxOps];
-  long long out_off;       // SLOT offset of the result
+  int n_thr, F, R, Rc, n_chunks, TJ;
+  int cpc, othr;           // results of few threads: a CTA covers `cpc` consecutive chunks, `othr` threads each
+  int n_out;               // entries of the result tensor
+  int nSh, nVar, nO;       // in-loop operands shared by the tile / varying along it; epilogue operands
+  FacOpDev opR[kFacMaxOps], opO[kFacMaxOps];   // opR: shared ones first
+  FacOpDev out;
 };
 
 enum { FI_CONTRACT = 0, FI_SETTLE_FWD, FI_BETA_NORM, FI_COUNT, FI_QUERY };
@@ -76,7 +85,9 @@ struct FacInstr {
 
 struct FacProgram {
   std::vector<FacInstr> fwd, bwd;
-  long long slot_doubles = 0;      // per-slot work area
+  long long slot_doubles = 0;      // per-slot work area without the saved region
+  long long saved_doubles = 0;     // upward messages of one slice (kept per slice when memory allows)
+  int n_ups = 0;                   // leading instructions of fwd / bwd that compute them
   long long o_alpha_in = 0, o_beta = 0, o_alpha_new = 0, o_bprev = 0, o_partial = 0;
   long long partial_doubles = 0;
   int n_obs = 0;
