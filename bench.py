@@ -356,18 +356,21 @@ class SmallModelConfig:
 class FactorialConfig:
     """C3: 4 ring-coupled chains x 16 states (three 16^6-entry cliques, 403 MB of tables), the
     E-step that niptrain's em_learn runs.  One step = the E-step over this GPU's series; the
-    time is linear in the number of series (one or eight sequences are streamed at a time), so a
-    bounded per-GPU sample stands for the 16 384-series set."""
+    time is linear in the number of series (64 sequences are in flight at a time), so a
+    bounded per-GPU sample stands for the 16 384-series set.  Engine 3 evaluates the join tree
+    factor by factor (the cliques are never materialised); NIPGPU_FACTOR=0 / engine 1 streams
+    the materialised tables instead (round 1: 572 slice-steps/s)."""
 
-    def __init__(self, name="C3", n_series=16, T=8):
+    def __init__(self, name="C3", n_series=128, T=8):
         self.name, self.n_series, self.T = name, n_series, T
         self.metric, self.unit = "slice-steps/sec (EM E-step)", "slice-steps/s"
         self.workload = ("%s: factorial DBN 4 x 16 states ring-coupled, E-step over %d series x %d slices per GPU "
                          "(sample of the 16384-series set)" % (name, n_series, T))
-        self.bound = "hbm"
-        self.b_alg = 6.2e9     # materialised 16^6 cliques: ~46 passes of 134 MB per slice-step (DESIGN.md §4)
-        self.kernel = "k_jt_forward<GridTeam> + k_jt_backward<GridTeam> (cooperative, up to 8 groups)"
-        self.engine = "generic join tree, grid team (clique tables streamed through HBM)"
+        self.bound = "fp64"
+        self.f_alg = 2 * 1.3e8  # SURVEY §8d: 4 stages x 2 x 16^6 flops per direction, factored evaluation
+        self.b_alg = 1.0e6      # 16 |I| bytes of forward rows per slice-step
+        self.kernel = "k_fac_contract (multi-operand contractions, ~12 of 16^6 terms per slice-step)"
+        self.engine = "engine 3: join tree factor by factor (clique tables never materialised)"
 
     def build(self, seed_data):
         from nip_b200.synth import FactorialSpec
@@ -384,15 +387,20 @@ class FactorialConfig:
         return model.last_kernel_ms()[0]
 
     def roofline(self, k_ms, peaks):
-        gbs = self.b_alg * self.units() / (k_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": gbs / peaks["hbm_gbs"], "kernel": self.kernel, "kernel_ms_per_pass": k_ms,
-                "bytes_per_unit": self.b_alg, "peak_source": peaks["hbm_source"]}
+        tf = self.f_alg * self.units() / (k_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": tf, "peak": peaks["dfma_tf"], "unit": "TFLOP/s",
+                "frac": tf / peaks["dfma_tf"], "kernel": self.kernel, "kernel_ms_per_pass": k_ms,
+                "flops_per_slice_step": self.f_alg,
+                "note": "FP64 FMA pipe (no FP64 tensor shape fits these 16-wide gathers); the kernels execute "
+                        "~9e8 flops per slice-step (every message is one 16^6-term multi-operand contraction) "
+                        "and are issue-bound on index arithmetic, not on either roof",
+                "peak_source": "DFMA rate measured live by nipgpu_probe_peaks"}
 
     def parity(self, api, model, batch):
         return {"checked_series": 0, "ok": None,
                 "note": "the reference needs ~50 s per slice-step at this shape; parity at full size is "
-                        "tests/test_gpu_parity.py::test_c3_full_size_vs_oracle, at 3 states factorial4x3.json"}
+                        "tests/test_gpu_parity.py::test_c3_full_size_vs_oracle (engines 1 and 3 against the "
+                        "oracle), at 3/6/8 states test_factorial_vs_oracle and the factorial4x3.json fixture"}
 
 
 def make_config(name):
@@ -428,8 +436,7 @@ def side_config(name, api, device, peaks, steps=3):
     if name == "C1":
         pass
     fm = cfg.build(2)
-    engine = api.ENGINE_JTREE if name == "C3" else api.ENGINE_AUTO
-    model = api.Model(fm, device=device, engine=engine)
+    model = api.Model(fm, device=device, engine=api.ENGINE_AUTO)
     batch = model.batch(cfg.obs_vars, cfg.data)
     if name == "C3":
         model.mstep(np.random.default_rng(7).random(model.counts_size()) + 0.1)
@@ -585,8 +592,7 @@ def main():
     api.load_library()                      # raises if the CUDA library is missing: no fallback
 
     fm = cfg.build(2 + rank)                # weak scaling: every rank works on its own set
-    engine = api.ENGINE_JTREE if args.config == "C3" else api.ENGINE_AUTO
-    model = api.Model(fm, device=local_rank, engine=engine)
+    model = api.Model(fm, device=local_rank, engine=api.ENGINE_AUTO)
     batch = model.batch(cfg.obs_vars, cfg.data)
     if args.config == "C3":
         model.mstep(np.random.default_rng(7).random(model.counts_size()) + 0.1)

@@ -25,7 +25,7 @@ per = N // world
 sp = FactorialSpec(16, 4, seed=1)
 fm = sp.flat()
 data = sp.sample(per, T, seed=100 + rank)                 # this rank's shard
-m = api.Model(fm, device=local, engine=1)
+m = api.Model(fm, device=local, engine=int(os.environ.get("ENGINE", 0)))   # 0: engine 3 by itself, 1: grid team
 b = m.batch(sp.obs_vars, data)
 m.mstep(np.random.default_rng(1234).random(m.counts_size()) + 0.1)   # same initial parameters on every rank
 w = EmWorker(GpuEmBackend(m, b), rank, world)
