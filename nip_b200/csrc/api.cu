@@ -446,12 +446,14 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
     nipgpu_model_destroy(m);
     return e;
   }
-  // engine 3 on request, or by itself for models whose cliques would be streamed through HBM by
-  // the grid team (NIPGPU_FACTOR=0 keeps those on engine 1)
+  // engine 3 on request, or by itself for models whose clique tables do not fit shared memory
+  // (engine 1 would keep them in per-CTA HBM workspaces or stream them with the whole grid;
+  // measured, tools/dev_midsize.py: engine 3 is 5x faster at 6^6-entry cliques, 15x at 8^6 and
+  // 12^6).  NIPGPU_FACTOR=0 keeps those models on engine 1.
   {
     const char* fenv = getenv("NIPGPU_FACTOR");
-    const bool auto_fac = engine == NIPGPU_ENGINE_AUTO && !m->chain.ok && m->launch.mode == JT_MODE_GRID &&
-                          !(fenv && fenv[0] == '0');
+    const bool in_hbm = m->launch.mode == JT_MODE_GRID || (m->launch.mode == JT_MODE_CTA && m->launch.gwork != nullptr);
+    const bool auto_fac = engine == NIPGPU_ENGINE_AUTO && !m->chain.ok && in_hbm && !(fenv && fenv[0] == '0');
     if (engine == NIPGPU_ENGINE_FACTOR || auto_fac) {
       fac_build(hm, m->fac);
       if (m->fac.ok) m->engine = NIPGPU_ENGINE_FACTOR;

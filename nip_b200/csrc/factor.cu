@@ -1087,13 +1087,19 @@ int run_instr(const RunCtx& R, const FacInstr& ins, const SlotCtx& X, int alive,
 #define NIPGPU_FACTOR_MAX_SLOTS 64
 #endif
 int fac_slots(const HostModel& hm, const FacEngine& fe, int n_series) {
-  (void)hm; (void)fe;
-  static const int cap = [] {
+  (void)fe;
+  static const int forced = [] {
     const char* p = getenv("NIPGPU_FACTOR_SLOTS");
-    const int v = p ? atoi(p) : 0;
-    return v > 0 ? v : NIPGPU_FACTOR_MAX_SLOTS;
+    return p ? atoi(p) : 0;
   }();
-  return std::max(1, std::min(cap, n_series));
+  // sequences in flight: NIPGPU_FACTOR_MAX_SLOTS for models whose messages are megabytes (one
+  // contraction of one sequence already fills the machine), more for small models, where the
+  // launches of a slice have to be shared by many sequences: about 2 GB of work areas
+  const double per_slot = 8.0 * (4.0 * hm.msg_total + 6.0 * hm.S + 1024.0);
+  long long w = (long long)(2147483648.0 / per_slot);
+  w = std::max<long long>(NIPGPU_FACTOR_MAX_SLOTS, std::min<long long>(w, 4096));
+  if (forced > 0) w = forced;
+  return (int)std::max<long long>(1, std::min<long long>(w, n_series));
 }
 
 int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_t st) {
