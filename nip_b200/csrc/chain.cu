@@ -1487,8 +1487,10 @@ static int small_infer(const ChainModel& cm, ChainBatch& cb, const ChainPlan& pl
   D.A = cm.d_As; D.phi0 = cm.d_phi0; D.R1 = cm.d_R1; D.lam_comb = cb.d_comb;
   D.toff = cb.d_toff; D.cfgT = cb.d_cfgT; D.n_series = a.n_series; D.order = B.order;
   D.len_sorted = B.len_sorted; D.row_off = B.row_off;
-  const int n_lam = (size_t)plan.n_comb * cm.S * sizeof(double) <= 32768 ? plan.n_comb : 0;
-  const size_t smem = sizeof(double) * ((size_t)cm.S * cm.S + (size_t)n_lam * cm.S);
+  const int n_lam = (size_t)plan.n_comb * cm.S * sizeof(double) <= 16384 ? plan.n_comb : 0;
+  const int t_longest = a.n_series > 0 ? std::max(cb.len_sorted[0], 0) : 0;
+  D.n_toff = t_longest + 1 <= 1024 ? t_longest + 1 : 0;
+  const size_t smem = sizeof(double) * ((size_t)cm.S * cm.S + (size_t)n_lam * cm.S + (size_t)D.n_toff);
   switch (cm.S) {
     case 1: return small_launch<1>(D, n_lam, smem, a, cb.d_alpha, st);
     case 2: return small_launch<2>(D, n_lam, smem, a, cb.d_alpha, st);

@@ -76,6 +76,7 @@ struct SmallDev {
   const double *A;        // [S][S] row = previous state, column = current state (base1)
   const double *phi0, *R1, *lam_comb;   // [SP], [SP], [n_comb][SP]
   const long long* toff;  // [t_max + 1]
+  int n_toff;             // entries of toff staged in shared memory (0: read from global)
   const int* cfgT;        // time-major evidence index
   int n_series;
   const int* order;       // sorted position -> series
@@ -83,9 +84,10 @@ struct SmallDev {
   const long long* row_off;
 };
 
-// shared memory: A [S*S] | lam_comb [n_lam][S] (when it fits: n_lam = n_comb, else 0)
+// shared memory: A [S*S] | lam_comb [n_lam][S] (when it fits: n_lam = n_comb, else 0) | toff [n_toff]
+// (the time-major offsets, when they fit: otherwise every slice's address waits for a global load)
 template <int S, bool FILT, bool WLL>
-__global__ void __launch_bounds__(128) k_chain_small_forward(SmallDev C, int n_lam, int store_alpha,
+__global__ void __launch_bounds__(128, S <= 4 ? (WLL ? 6 : 8) : 4) k_chain_small_forward(SmallDev C, int n_lam, int store_alpha,
                                                              double* __restrict__ alphaT,
                                                              double* __restrict__ post, int post_stride,
                                                              int post_off, int post_wide, double* ll_out,
@@ -96,6 +98,9 @@ __global__ void __launch_bounds__(128) k_chain_small_forward(SmallDev C, int n_l
   double* sL = sm + S * S;
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) sA[i] = C.A[i];
   for (int i = threadIdx.x; i < n_lam * S; i += blockDim.x) sL[i] = C.lam_comb[(long long)(i / S) * C.SP + i % S];
+  long long* sT = reinterpret_cast<long long*>(sL + n_lam * S);
+  for (int i = threadIdx.x; i < C.n_toff; i += blockDim.x) sT[i] = C.toff[i];
+  const long long* toff = C.n_toff ? sT : C.toff;
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= C.n_series) return;
@@ -134,8 +139,8 @@ __global__ void __launch_bounds__(128) k_chain_small_forward(SmallDev C, int n_l
   LogAcc L;
   double a[AS];
   if constexpr (AS > S) a[S] = 0.0;
-  int c = __ldg(C.cfgT + C.toff[0] + p);
-  int c_next = T > 1 ? __ldg(C.cfgT + C.toff[1] + p) : 0;
+  int c = __ldg(C.cfgT + toff[0] + p);
+  int c_next = T > 1 ? __ldg(C.cfgT + toff[1] + p) : 0;
   {  // slice 0: alpha_0 = normalise(phi0 * lambda_0), m1 = mass of the evidence-free slice
     double lam[S], s = 0;
     lam_row(c, lam);
@@ -147,11 +152,11 @@ __global__ void __launch_bounds__(128) k_chain_small_forward(SmallDev C, int n_l
     for (int i = 0; i < S; i++) a[i] *= inv;
   }
   for (int t = 0;; t++) {
-    if (store_alpha) small_store_row<AS>(alphaT + (C.toff[t] + p) * AS, a);
+    if (store_alpha) small_store_row<AS>(alphaT + (toff[t] + p) * AS, a);
     if (FILT) small_store_post<S>(post + (row0 + t) * post_stride + post_off, a, post_wide);
     if (t + 1 >= T) break;
     c = c_next;
-    if (t + 2 < T) c_next = __ldg(C.cfgT + C.toff[t + 2] + p);
+    if (t + 2 < T) c_next = __ldg(C.cfgT + toff[t + 2] + p);
     double lam[S], u[S], s = 0, m1 = 0;
     lam_row(c, lam);
 #pragma unroll
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(128) k_chain_small_forward(SmallDev C, int n_l
 }
 
 template <int S>
-__global__ void __launch_bounds__(128) k_chain_small_backward(SmallDev C, int n_lam, const double* __restrict__ alphaT,
+__global__ void __launch_bounds__(128, S <= 4 ? 7 : 4) k_chain_small_backward(SmallDev C, int n_lam, const double* __restrict__ alphaT,
                                                               double* __restrict__ post, int post_stride,
                                                               int post_off, int post_wide) {
   constexpr int AS = SmallGeom<S>::AS;
@@ -185,6 +190,9 @@ __global__ void __launch_bounds__(128) k_chain_small_backward(SmallDev C, int n_
   double* sL = sm + S * S;
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) sA[i] = C.A[i];
   for (int i = threadIdx.x; i < n_lam * S; i += blockDim.x) sL[i] = C.lam_comb[(long long)(i / S) * C.SP + i % S];
+  long long* sT = reinterpret_cast<long long*>(sL + n_lam * S);
+  for (int i = threadIdx.x; i < C.n_toff; i += blockDim.x) sT[i] = C.toff[i];
+  const long long* toff = C.n_toff ? sT : C.toff;
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= C.n_series) return;
@@ -214,14 +222,14 @@ __global__ void __launch_bounds__(128) k_chain_small_backward(SmallDev C, int n_
   double beta[S], a[AS], an[AS];
 #pragma unroll
   for (int i = 0; i < S; i++) beta[i] = 1.0;
-  small_load_row<AS>(alphaT + (C.toff[T - 1] + p) * AS, a);
-  int c = __ldg(C.cfgT + C.toff[T - 1] + p);
+  small_load_row<AS>(alphaT + (toff[T - 1] + p) * AS, a);
+  int c = __ldg(C.cfgT + toff[T - 1] + p);
   for (int t = T - 1;; t--) {
     // requests of the next iteration first: they do not depend on the recursion
     int c_prev = 0;
     if (t >= 1) {
-      small_load_row<AS>(alphaT + (C.toff[t - 1] + p) * AS, an);
-      c_prev = __ldg(C.cfgT + C.toff[t - 1] + p);
+      small_load_row<AS>(alphaT + (toff[t - 1] + p) * AS, an);
+      c_prev = __ldg(C.cfgT + toff[t - 1] + p);
     }
     double g[AS], s = 0;
     if constexpr (AS > S) g[S] = 0.0;

@@ -298,30 +298,27 @@ __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
 #pragma unroll
   for (int j = 0; j < TJ; j++) acc[j] = NR == 0 ? 1.0 : 0.0;
   if (NR > 0) {
+    auto value = [&](int k, int off) -> double {
+      return ptr[k] ? ptr[k][off] : ((ev[k] == INT_MIN || off == ev[k]) ? 1.0 : 0.0);
+    };
 #pragma unroll 4
     for (int r = 0; r < nr; r++) {
       double sh = 1.0;
 #pragma unroll
       for (int k = 0; k < NSH; k++) {
-        const int ro = roff[k * span + r];
-        const double v = ptr[k] ? ptr[k][ro] : ((ev[k] == INT_MIN || ro == ev[k]) ? 1.0 : 0.0);
+        const double v = value(k, roff[k * span + r]);
         sh = k == 0 ? v : sh * v;
       }
-      double term[TJ];
 #pragma unroll
-      for (int j = 0; j < TJ; j++) term[j] = sh;
+      for (int j = 0; j < TJ; j++) {
+        double term = sh;
 #pragma unroll
-      for (int k = NSH; k < NR; k++) {
-        const int ro = roff[k * span + r];
-#pragma unroll
-        for (int j = 0; j < TJ; j++) {
-          const int off = ro + j * ts[k];
-          const double v = ptr[k] ? ptr[k][off] : ((ev[k] == INT_MIN || off == ev[k]) ? 1.0 : 0.0);
-          term[j] = (NSH == 0 && k == NSH) ? v : term[j] * v;
+        for (int k = NSH; k < NR; k++) {
+          const double v = value(k, roff[k * span + r] + j * ts[k]);
+          term = (NSH == 0 && k == NSH) ? v : term * v;
         }
+        acc[j] += term;
       }
-#pragma unroll
-      for (int j = 0; j < TJ; j++) acc[j] += term[j];
     }
   }
   for (int k = 0; k < s.nO; k++) {
@@ -349,6 +346,110 @@ __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
                 (s.n_chunks > 1 ? (long long)chunk * s.n_out : 0);
 #pragma unroll
   for (int j = 0; j < TJ; j++) dst[oo + j * s.out.tstride] = acc[j];
+}
+
+// The same contraction with a 2-D register tile: TJ x TK results per thread along two output
+// variables such that no in-loop operand holds both.  Per term of the summed index a thread
+// loads TJ values of the operands that hold the first variable and TK of those that hold the
+// second, and forms their outer product: (TJ + TK) loads for TJ * TK multiply-adds.
+template <int NSH, int NV, int NV2, int TJ, int TK>
+__global__ void __launch_bounds__(128) k_fac_contract2(FacStepDev s, SlotCtx X) {
+  constexpr int NR = NSH + NV + NV2;
+  extern __shared__ int s_roff[];   // [NR][cpc * Rc]
+  const int slot = blockIdx.z;
+  const int span = s.cpc * s.Rc;
+  const int rb0 = blockIdx.y * span, rb1 = min(s.R, rb0 + span);
+  for (int k = 0; k < NR; k++)
+    for (int i = threadIdx.x; i < rb1 - rb0; i += blockDim.x) s_roff[k * span + i] = X.pool[s.opR[k].roff + rb0 + i];
+  __syncthreads();
+  int o, chunk;
+  if (s.cpc > 1) { o = threadIdx.x % s.othr; chunk = blockIdx.y * s.cpc + threadIdx.x / s.othr; }
+  else { o = blockIdx.x * blockDim.x + threadIdx.x; chunk = blockIdx.y; }
+  if (o >= s.n_thr || chunk >= s.n_chunks || (s.cpc > 1 && threadIdx.x / s.othr >= s.cpc)) return;
+  const int r0 = chunk * s.Rc, r1 = min(s.R, r0 + s.Rc), nr = r1 - r0;
+  const int* roff = s_roff + (r0 - rb0);
+  const int oh = o / s.F, ol = o - oh * s.F;
+  double* area = X.slots + (long long)slot * X.slot_stride;
+  const long long row = X.row_off[X.order[X.wave0 + slot]] + X.t;
+  const double* ptr[NR];
+  int ev[NR], ts[NR];
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+    const FacOpDev& op = s.opR[k];
+    const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
+    ts[k] = k < NSH + NV ? op.tstride : op.tstride2;
+    if (op.kind == FT_EVID) {
+      const int obs = X.obs[row * X.n_obs + op.col];
+      ev[k] = obs < 0 ? INT_MIN : obs - ob;
+      ptr[k] = nullptr;
+    } else {
+      ev[k] = 0;
+      ptr[k] = (op.kind == FT_MODEL ? X.fac : area + (op.kind == FT_SAVED ? X.saved_off : 0)) + op.off + ob;
+    }
+  }
+  auto value = [&](int k, int off) -> double {
+    return ptr[k] ? ptr[k][off] : ((ev[k] == INT_MIN || off == ev[k]) ? 1.0 : 0.0);
+  };
+  double acc[TJ][TK];
+#pragma unroll
+  for (int j = 0; j < TJ; j++)
+#pragma unroll
+    for (int q = 0; q < TK; q++) acc[j][q] = 0.0;
+#pragma unroll 2
+  for (int r = 0; r < nr; r++) {
+    double a[TJ], b[TK];
+#pragma unroll
+    for (int j = 0; j < TJ; j++) {
+      a[j] = value(NSH, roff[NSH * span + r] + j * ts[NSH]);
+#pragma unroll
+      for (int k = NSH + 1; k < NSH + NV; k++) a[j] *= value(k, roff[k * span + r] + j * ts[k]);
+    }
+#pragma unroll
+    for (int q = 0; q < TK; q++) {
+      b[q] = value(NSH + NV, roff[(NSH + NV) * span + r] + q * ts[NSH + NV]);
+#pragma unroll
+      for (int k = NSH + NV + 1; k < NR; k++) b[q] *= value(k, roff[k * span + r] + q * ts[k]);
+    }
+    if (NSH > 0) {
+      double sh = value(0, roff[r]);
+#pragma unroll
+      for (int k = 1; k < NSH; k++) sh *= value(k, roff[k * span + r]);
+#pragma unroll
+      for (int q = 0; q < TK; q++) b[q] *= sh;
+    }
+#pragma unroll
+    for (int j = 0; j < TJ; j++)
+#pragma unroll
+      for (int q = 0; q < TK; q++) acc[j][q] = fma(a[j], b[q], acc[j][q]);
+  }
+  for (int k = 0; k < s.nO; k++) {
+    const FacOpDev& op = s.opO[k];
+    const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
+    int obs = 0;
+    const double* qp = nullptr;
+    if (op.kind == FT_EVID) obs = X.obs[row * X.n_obs + op.col];
+    else qp = (op.kind == FT_MODEL ? X.fac : area + (op.kind == FT_SAVED ? X.saved_off : 0)) + op.off;
+#pragma unroll
+    for (int j = 0; j < TJ; j++)
+#pragma unroll
+      for (int q = 0; q < TK; q++) {
+        const int off = ob + j * op.tstride + q * op.tstride2;
+        double v;
+        if (op.kind == FT_EVID) v = (obs < 0 || obs == off) ? 1.0 : 0.0;
+        else {
+          v = qp[off];
+          if (op.inv) v = fac_inv(v);
+        }
+        acc[j][q] *= v;
+      }
+  }
+  const int oo = X.pool[s.out.ohi + oh] + X.pool[s.out.olo + ol];
+  double* dst = area + (s.out.kind == FT_SAVED ? X.saved_off : 0) + s.out.off +
+                (s.n_chunks > 1 ? (long long)chunk * s.n_out : 0);
+#pragma unroll
+  for (int j = 0; j < TJ; j++)
+#pragma unroll
+    for (int q = 0; q < TK; q++) dst[oo + j * s.out.tstride + q * s.out.tstride2] = acc[j][q];
 }
 
 // out[o] = sum over chunks of partial[chunk][o], fixed order
@@ -587,28 +688,28 @@ struct Compiler {
     return (int)T.size() - 1;
   }
 
-  // index tables of one tensor over the thread space (variables `tv`, the last one scaled by
-  // `last_mult` when it is the tile variable) and over the summed variables
-  void tables(const FacTensor& t, const std::vector<int>& tv, int last_mult, int F, long long n_thr,
+  // index tables of one tensor over the thread space (variables `tv`; a tile variable's digit counts
+  // blocks of `tmult[a]` states) and over the summed variables
+  void tables(const FacTensor& t, const std::vector<int>& tv, const std::vector<int>& tmult, int F, long long n_thr,
               const std::vector<int>& rvars, long long R, FacOpDev& d) {
-    auto fill = [&](const std::vector<int>& vars, int lm, long long count, long long unit) {
+    auto fill = [&](const std::vector<int>& vars, const std::vector<int>* mult, long long count, long long unit) {
       const int pos = (int)pool.size();
       for (long long x = 0; x < count; x++) {
         long long rem = x * unit, o = 0;
         for (size_t a = 0; a < vars.size(); a++) {
           const int v = vars[a];
-          const int c = (a + 1 == vars.size() && lm > 1) ? hm.card[v] / lm : hm.card[v];
-          const long long dig = (rem % c) * ((a + 1 == vars.size() && lm > 1) ? lm : 1);
-          o += dig * stride_in(hm, t.vars, v);
+          const int lm = mult ? (*mult)[a] : 1;
+          const int c = hm.card[v] / lm;
+          o += (rem % c) * lm * stride_in(hm, t.vars, v);
           rem /= c;
         }
         pool.push_back((int)o);
       }
       return pos;
     };
-    d.olo = fill(tv, last_mult, F, 1);
-    d.ohi = fill(tv, last_mult, (n_thr + F - 1) / F, F);
-    d.roff = fill(rvars, 1, R, 1);
+    d.olo = fill(tv, &tmult, F, 1);
+    d.ohi = fill(tv, &tmult, (n_thr + F - 1) / F, F);
+    d.roff = fill(rvars, nullptr, R, 1);
   }
 
   // Adds to `prog` the contraction out(ovars) = sum over the other variables of prod(ops).
@@ -629,16 +730,34 @@ struct Compiler {
     // ---- the variable consecutive threads run along ----
     const long long kBig = 1 << 17;     // tensors above this are not copied into another order
     int v0 = ovars_in.empty() ? -1 : ovars_in[0];
-    if (!fixed && ovars_in.size() > 1) {
+    if (ovars_in.size() > 1) {
+      // the heaviest in-loop operand: among equally good directions, run along its fastest variable
+      const FacTensor* heavy = nullptr;
+      for (const FacOpRef& o : ops) {
+        const FacTensor& t = T[o.tensor];
+        if (t.kind != FT_EVID && depends(t) && (!heavy || t.size > heavy->size)) heavy = &t;
+      }
       double best = -1;
+      bool best_heavy = false;
       for (int v : ovars_in) {
         double sc = 0;
         for (const FacOpRef& o : ops) {
           const FacTensor& t = T[o.tensor];
-          if (t.kind == FT_EVID || !has_var(t.vars, v) || t.vars[0] == v) continue;
+          if (t.kind == FT_EVID || t.vars.empty() || t.vars[0] == v) continue;
+          if (!has_var(t.vars, v)) {
+            // absent: every lane reads the same entry.  Fine when the operand's fastest variable is
+            // summed (a thread then walks along a line); when it is another result variable, a big
+            // operand is fetched one 8-byte entry per 32-byte sector
+            if (t.size > kBig && has_var(ovars_in, t.vars[0])) sc += 4.0 * t.size;
+            continue;
+          }
           sc += t.size > kBig ? 64.0 * t.size * (depends(t) ? (double)R : 1.0) : (double)t.size;
         }
-        if (best < 0 || sc < best) { best = sc; v0 = v; }
+        // a result whose order is fixed is written with a stride when the threads run along
+        // another variable: one scattered store per result, nothing against the R terms behind it
+        if (fixed && v != ovars_in[0]) sc += 2.0 * (double)prod_card(hm, ovars_in);
+        const bool on_heavy = heavy && !heavy->vars.empty() && heavy->vars[0] == v;
+        if (best < 0 || sc < best || (sc == best && on_heavy && !best_heavy)) { best = sc; v0 = v; best_heavy = on_heavy; }
       }
     }
     // operands that hold v0 but not as their fastest variable: a copy in another order, if small
@@ -685,11 +804,44 @@ struct Compiler {
       }
       if (vt >= 0) TJ = 4;
     }
-    std::vector<int> tv;      // thread space: v0 first, the tile variable last
+    // ---- a second tile variable: no in-loop operand may hold both (outer product of two slices) ----
+    int vt2 = -1, TK = 1;
+    static const bool no_2d = [] { const char* p = getenv("NIPGPU_FACTOR_TILE2"); return p && p[0] == '0'; }();
+    if (vt >= 0 && !no_2d) {
+      int n1 = 0, nsh = 0;
+      for (const FacOpRef& o : ops) {
+        const FacTensor& t = T[o.tensor];
+        if (!depends(t)) continue;
+        (has_var(t.vars, vt) ? n1 : nsh)++;
+      }
+      double best = -1;
+      for (int v : ovars) {
+        if (v == v0 || v == vt || hm.card[v] % 4 != 0) continue;
+        double sc = 0;
+        int n2 = 0;
+        bool both = false;
+        for (const FacOpRef& o : ops) {
+          const FacTensor& t = T[o.tensor];
+          if (!depends(t) || !has_var(t.vars, v)) continue;
+          if (has_var(t.vars, vt)) both = true;
+          sc += (double)t.size;
+          n2++;
+        }
+        // templates exist for 1..2 operands per tile variable and up to 2 shared ones
+        if (both || n2 < 1 || n2 > 2 || n1 < 1 || n1 > 2 || nsh - n2 > 2 || nsh - n2 < 0) continue;
+        if (best < 0 || sc < best) { best = sc; vt2 = v; }
+      }
+      if (vt2 >= 0) TK = 4;
+    }
+    // thread space: v0 first, then the blocks of the tile variables (threads that share the heavy
+    // operands' entries sit next to each other: one trip to HBM, the rest L1/L2 hits), then the rest
+    std::vector<int> tv, tmult;
+    if (v0 >= 0 && v0 != vt) { tv.push_back(v0); tmult.push_back(1); }
+    if (vt >= 0) { tv.push_back(vt); tmult.push_back(TJ); }
+    if (vt2 >= 0) { tv.push_back(vt2); tmult.push_back(TK); }
     for (int v : ovars)
-      if (v != vt) tv.push_back(v);
-    if (vt >= 0) tv.push_back(vt);
-    const long long n_out = T[out].size, n_thr = n_out / TJ;
+      if (v != vt && v != v0 && v != vt2) { tv.push_back(v); tmult.push_back(1); }
+    const long long n_out = T[out].size, n_thr = n_out / (TJ * TK);
     FacInstr ins;
     ins.kind = FI_CONTRACT;
     ins.needs_history = needs_history;
@@ -697,19 +849,20 @@ struct Compiler {
     int F = 1;
     for (size_t a = 0; a < tv.size(); a++) {
       if (F >= 128) break;
-      F *= (tv[a] == vt) ? hm.card[tv[a]] / TJ : hm.card[tv[a]];
+      F *= hm.card[tv[a]] / tmult[a];
     }
     if (n_out > INT32_MAX || R > INT32_MAX) { failed = true; return out; }
-    s.n_thr = (int)n_thr; s.n_out = (int)n_out; s.F = F; s.R = (int)R; s.TJ = TJ;
-    s.nSh = s.nVar = s.nO = 0;
+    s.n_thr = (int)n_thr; s.n_out = (int)n_out; s.F = F; s.R = (int)R; s.TJ = TJ; s.TK = TK;
+    s.nSh = s.nVar = s.nVar2 = s.nO = 0;
     auto dev = [&](const FacTensor& t, bool inv, bool dep) {
       FacOpDev d{};
       d.off = t.off; d.kind = t.kind; d.inv = inv ? 1 : 0; d.col = t.col;
       d.tstride = vt >= 0 ? (int)stride_in(hm, t.vars, vt) : 0;
-      tables(t, tv, vt >= 0 ? TJ : 1, F, n_thr, rvars, dep ? R : 0, d);
+      d.tstride2 = vt2 >= 0 ? (int)stride_in(hm, t.vars, vt2) : 0;
+      tables(t, tv, tmult, F, n_thr, rvars, dep ? R : 0, d);
       return d;
     };
-    std::vector<FacOpDev> shared, varying;
+    std::vector<FacOpDev> shared, varying, varying2;
     for (const FacOpRef& o : ops) {
       const FacTensor& t = T[o.tensor];
       const bool dep = depends(t);
@@ -719,20 +872,21 @@ struct Compiler {
         s.opO[s.nO++] = d;
       } else {
         if (o.inv) { failed = true; return out; }
-        (d.tstride != 0 ? varying : shared).push_back(d);
+        (d.tstride != 0 ? varying : d.tstride2 != 0 ? varying2 : shared).push_back(d);
       }
     }
-    if ((int)(shared.size() + varying.size()) > kFacMaxOps || (int)varying.size() > kFacMaxVar) { failed = true; return out; }
-    if (TJ > 1 && (int)shared.size() > 4) { failed = true; return out; }
+    if ((int)(shared.size() + varying.size() + varying2.size()) > kFacMaxOps || (int)varying.size() > kFacMaxVar) { failed = true; return out; }
+    if (TJ > 1 && TK == 1 && (int)shared.size() > 4) { failed = true; return out; }
     for (const FacOpDev& d : shared) s.opR[s.nSh++] = d;
     for (const FacOpDev& d : varying) s.opR[s.nSh + s.nVar++] = d;
+    for (const FacOpDev& d : varying2) s.opR[s.nSh + s.nVar + s.nVar2++] = d;
     s.out = dev(T[out], false, false);
     // split the summed range so that a slot has at least ~64k threads, at least 8 terms each
     const long long want = 65536;
     long long chunks = std::max<long long>(1, std::min<long long>((want + n_thr - 1) / n_thr, R / 8));
     chunks = std::min<long long>(chunks, 2048);     // the partial sums are added up by one warp per result
     chunks = std::max(chunks, (R + 1023) / 1024);
-    if (s.nSh + s.nVar == 0) chunks = 1;
+    if (s.nSh + s.nVar + s.nVar2 == 0) chunks = 1;
     s.Rc = (int)((R + chunks - 1) / chunks);
     s.n_chunks = (int)((R + s.Rc - 1) / s.Rc);
     s.cpc = 1;
@@ -744,7 +898,12 @@ struct Compiler {
       s.cpc = std::max(1, std::min(128 / p2, 2048 / std::max(s.Rc, 1)));
     }
     if (s.n_chunks > 1) partial_max = std::max(partial_max, (long long)s.n_chunks * n_out);
-    ins.flops = (double)n_out * (double)R * std::max(1, s.nSh + s.nVar);
+    ins.flops = (double)n_out * (double)R * std::max(1, s.nSh + s.nVar + s.nVar2);
+    {
+      auto vs = [&](const std::vector<int>& v) { std::string r = "("; for (int x : v) r += std::to_string(x) + " "; return r + ")"; };
+      ins.note = "out" + vs(ovars) + " v0=" + std::to_string(v0) + " vt=" + std::to_string(vt) + " vt2=" + std::to_string(vt2) + " :";
+      for (const FacOpRef& o : ops) ins.note += " " + std::string(T[o.tensor].kind == FT_MODEL ? "M" : T[o.tensor].kind == FT_EVID ? "E" : "S") + vs(T[o.tensor].vars);
+    }
     prog.push_back(ins);
     return out;
   }
@@ -992,7 +1151,32 @@ void launch_contract_v(const FacStepDev& s, const SlotCtx& X, int alive, cudaStr
   }
 }
 
+template <int NSH, int NV, int NV2>
+void launch_contract_2d(const FacStepDev& s, const SlotCtx& X, int alive, cudaStream_t st) {
+  const dim3 grid(s.cpc > 1 ? 1 : (s.n_thr + 127) / 128, (s.n_chunks + s.cpc - 1) / s.cpc, alive);
+  const size_t smem = (size_t)(NSH + NV + NV2) * s.cpc * s.Rc * sizeof(int);
+  k_fac_contract2<NSH, NV, NV2, 4, 4><<<grid, 128, smem, st>>>(s, X);
+}
+
 void launch_contract(FacStepDev s, const SlotCtx& X, int alive, cudaStream_t st) {
+  if (s.TK > 1) {   // 2-D register tile: 1..2 operands per tile variable, 0..2 shared (the planner checked)
+    const int key = s.nSh * 100 + s.nVar * 10 + s.nVar2;
+    switch (key) {
+      case 11: launch_contract_2d<0, 1, 1>(s, X, alive, st); break;
+      case 12: launch_contract_2d<0, 1, 2>(s, X, alive, st); break;
+      case 21: launch_contract_2d<0, 2, 1>(s, X, alive, st); break;
+      case 22: launch_contract_2d<0, 2, 2>(s, X, alive, st); break;
+      case 111: launch_contract_2d<1, 1, 1>(s, X, alive, st); break;
+      case 112: launch_contract_2d<1, 1, 2>(s, X, alive, st); break;
+      case 121: launch_contract_2d<1, 2, 1>(s, X, alive, st); break;
+      case 122: launch_contract_2d<1, 2, 2>(s, X, alive, st); break;
+      case 211: launch_contract_2d<2, 1, 1>(s, X, alive, st); break;
+      case 212: launch_contract_2d<2, 1, 2>(s, X, alive, st); break;
+      case 221: launch_contract_2d<2, 2, 1>(s, X, alive, st); break;
+      default: launch_contract_2d<2, 2, 2>(s, X, alive, st); break;
+    }
+    return;
+  }
   if (s.TJ == 1 || s.nVar == 0) {
     // no tile (or nothing varies along it: every result of the tile equals the first one, still correct
     // to compute one by one): all in-loop operands are "shared"
@@ -1234,8 +1418,9 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
       for (size_t i = 0; i < v.size(); i++) {
         const FacStepDev& s = v[i].step;
         if (v[i].kind == FI_CONTRACT)
-          fprintf(stderr, "[factor] %s %2zu contract n_out %8d R %6d chunks %4d TJ %d nSh %d nVar %d nO %d  %9.3f ms  %.2f GFLOP\n", name, i,
-                  s.n_out, s.R, s.n_chunks, s.TJ, s.nSh, s.nVar, s.nO, ms[i], v[i].flops * 1e-9);
+          fprintf(stderr, "[factor] %s %2zu contract n_out %8d R %6d chunks %4d TJ %dx%d nSh %d nVar %d+%d nO %d  %9.3f ms  %.2f GFLOP\n", name, i,
+                  s.n_out, s.R, s.n_chunks, s.TJ, s.TK, s.nSh, s.nVar, s.nVar2, s.nO, ms[i], v[i].flops * 1e-9);
+        if (v[i].kind == FI_CONTRACT && ms[i] > 1.0) fprintf(stderr, "          %s\n", v[i].note.c_str());
         else
           fprintf(stderr, "[factor] %s %2zu kind %d n %d  %9.3f ms\n", name, i, v[i].kind, v[i].n, ms[i]);
       }

@@ -51,6 +51,7 @@ struct FacOpDev {
   int kind, inv, col;
   int olo, ohi, roff;      // positions of its index tables in the int pool
   int tstride;             // step along the tile variable (0: the operand does not hold it)
+  int tstride2;            // step along the second tile variable of a 2-D register tile
 };
 
 constexpr int kFacMaxOps = 8;
@@ -65,7 +66,8 @@ struct FacStepDev {
   int cpc, othr;           // results of few threads: a CTA covers `cpc` consecutive chunks, `othr` threads each
   int n_out;               // entries of the result tensor
   int nSh, nVar, nO;       // in-loop operands shared by the tile / varying along it; epilogue operands
-  FacOpDev opR[kFacMaxOps], opO[kFacMaxOps];   // opR: shared ones first
+  int TK, nVar2;           // 2-D tile: TK results along a second variable, in-loop operands varying along it only
+  FacOpDev opR[kFacMaxOps], opO[kFacMaxOps];   // opR: shared ones first, then the first tile variable's, then the second's
   FacOpDev out;
 };
 
@@ -81,6 +83,7 @@ struct FacInstr {
   bool only_t0 = false;    // FI_COUNT of a previous-slice variable: first slices only
   bool needs_history = false;  // FI_CONTRACT / FI_BETA_NORM of the message to slice t-1: t > 0 only
   double flops = 0;
+  std::string note;        // NIPGPU_FACTOR_TRACE: result and operand variables
 };
 
 struct FacProgram {

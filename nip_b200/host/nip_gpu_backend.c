@@ -120,6 +120,14 @@ static int configured_devices(int* dev) {
   return n;
 }
 
+/* NIP_GPU_ENGINE=1|2|3 asks for one engine of the device library (NIPGPU_ENGINE_*: generic
+ * join tree, chain, factor by factor); default: the library chooses */
+static int configured_engine(void) {
+  const char* s = getenv("NIP_GPU_ENGINE");
+  const int v = s ? atoi(s) : 0;
+  return v >= 1 && v <= 3 ? v : NIPGPU_ENGINE_AUTO;
+}
+
 static int parameters_differ(nip_model model, const backend_entry* e) {
   const nipgpu_model_desc* d = e->desc;
   int i, j;
@@ -186,7 +194,7 @@ static backend_entry* backend_for(nip_model model, int refresh) {
     fresh.model = model;
     fresh.n_dev = 1;
     configured_devices(fresh.dev);
-    if (nipgpu_model_create(fresh.desc, fresh.dev[0], NIPGPU_ENGINE_AUTO, &fresh.gm[0]) != NIPGPU_OK) {
+    if (nipgpu_model_create(fresh.desc, fresh.dev[0], configured_engine(), &fresh.gm[0]) != NIPGPU_OK) {
       report_device_error();
       nipgpu_desc_free(fresh.desc);
       return NULL;
@@ -228,7 +236,7 @@ static int ensure_group(backend_entry* e) {
   if (n <= 1 || e->group) return e->n_dev;
   for (k = 1; k < n; k++) {
     e->dev[k] = dev[k];
-    if (nipgpu_model_create(e->desc, dev[k], NIPGPU_ENGINE_AUTO, &e->gm[k]) != NIPGPU_OK ||
+    if (nipgpu_model_create(e->desc, dev[k], configured_engine(), &e->gm[k]) != NIPGPU_OK ||
         nipgpu_model_set_parameters(e->gm[k], e->tables, e->prior) != NIPGPU_OK) {
       report_device_error();
       while (k >= 1) { nipgpu_model_destroy(e->gm[k]); e->gm[k--] = NULL; }

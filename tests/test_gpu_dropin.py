@@ -502,3 +502,52 @@ def test_generate_set_dropin(libs, tmp_path):
         assert np.all(np.isclose(post.max(axis=1), 1.0)) and np.isfinite(ll)
     gpu.nip_gpu_forget_set(out)
     gpu.nip_gpu_release(model.h)
+
+
+def test_dropin_on_the_factor_engine(libs, tmp_path, monkeypatch):
+    """NIP_GPU_ENGINE=3: the reference's entry points on the engine that evaluates the join tree
+    factor by factor (what a model with huge cliques gets by itself), on a general tree with
+    in_clique != out_clique: smoothing, filtering, and em_learn's learning curve + trained CPTs"""
+    ref, gpu = libs
+    monkeypatch.setenv("NIP_GPU_ENGINE", "3")
+    p = tmp_path / "d.net"
+    p.write_text(_demo1_like_net())
+    rng = np.random.default_rng(8)
+    series = [np.stack([rng.integers(0, 2, size=n), rng.integers(0, 3, size=n)], axis=1).astype(np.int32)
+              for n in (7, 12, 3, 9)]
+    for s in series:
+        s[rng.random(s.shape) < 0.15] = -1
+        s[0] = np.abs(s[0])
+    model = ref.parse(p)
+    obs, query = [0, 2], [1, 3, 4]          # D1, B1 observed; C1, A1, A0 queried
+    row = 3 + 4 + 4
+    for s in series:
+        ts = model.timeseries(obs, s)
+        want, ll_want = model.infer(ts, query)
+        ll = f64()
+        got = _flat(ref, gpu.forward_backward_inference(ts, _vars(ref, model, query), 3, C.byref(ll)), row)
+        assert_close(got, want, "factor engine: forward_backward_inference posteriors")
+        assert_close(ll.value, ll_want, "factor engine: loglikelihood")
+        want, ll_want = model.infer(ts, query, forward_only=True)
+        got = _flat(ref, gpu.forward_inference(ts, _vars(ref, model, query), 3, C.byref(ll)), row)
+        assert_close(got, want, "factor engine: forward_inference posteriors")
+    gpu.nip_gpu_release(model.h)
+    m_ref, m_gpu = ref.parse(p), ref.parse(p)
+    ts_ref = [m_ref.timeseries(obs, s) for s in series]
+    ts_gpu = [m_gpu.timeseries(obs, s) for s in series]
+    st_ref, curve_ref = m_ref.em_learn(ts_ref, 1e-3, 7)
+    ref.L.refh_seed(7)
+    lc = ref.L.refh_new_double_list()
+    arr = (vp * len(ts_gpu))(*ts_gpu)
+    st_gpu = gpu.em_learn(arr, len(ts_gpu), 1e-3, lc)
+    curve = np.zeros(256)
+    n = ref.L.refh_double_list_to_array(lc, curve.ctypes.data_as(vp), 256)
+    ref.L.refh_free_double_list(lc)
+    assert st_gpu == st_ref
+    assert n == len(curve_ref)
+    assert_close(curve[:n], curve_ref, "factor engine: learning curve")
+    t_ref, p_ref = m_ref.parameters()
+    t_gpu, p_gpu = m_gpu.parameters()
+    assert_close(t_gpu, t_ref, "factor engine: trained original_p", rtol=1e-8)
+    assert_close(p_gpu, p_ref, "factor engine: trained priors", rtol=1e-8)
+    gpu.nip_gpu_release(m_gpu.h)
