@@ -237,8 +237,21 @@ void fill_fac_args(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence
   a->d_status = b->d_status; a->d_R1 = m->d_R1; a->d_m10 = m->d_m10;
 }
 
+// NIPGPU_CHUNKED_COPY_MIN_MB: smallest posterior set that is copied in chunks (default 256 MB)
+static size_t chunked_copy_min_bytes() {
+  static const size_t v = [] {
+    const char* p = getenv("NIPGPU_CHUNKED_COPY_MIN_MB");
+    return (size_t)(p && atoi(p) > 0 ? atoi(p) : 256) << 20;
+  }();
+  return v;
+}
+
+// host_post != nullptr: the caller wants the posterior rows in host memory; when the batch allows it
+// (see below) they are copied chunk by chunk while later chunks are still being computed, and
+// *copied is set
 int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, int nq,
-               const int32_t* query, int forward_only, int want_ll, bool want_post) {
+               const int32_t* query, int forward_only, int want_ll, bool want_post,
+               double* host_post = nullptr, bool* copied = nullptr) {
   if (!m || !b || b->m != m) return fail(NIPGPU_EINVAL, "model/batch mismatch");
   const HostModel& hm = m->hm;
   DQuery Q{};
@@ -276,6 +289,46 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
     a.d_post = project ? b->d_joint : post; a.post_stride = project ? SPc : Q.row; a.post_off = 0;
     a.d_ll = b->d_ll; a.d_status = b->d_status;
     NIPGPU_CUDA(cudaEventRecord(m->ev_mid, m->stream));   // re-recorded between the two kernels of the warp-resident path
+    // Host-buffered smoothing of a large set is a PCIe transfer with some kernels in front
+    // (C2: 2.9 ms of kernels, 40 ms of device-to-host copy).  When the series are stored in
+    // length-sorted order (equal lengths: always) a range of sorted positions is a contiguous
+    // block of output rows, so the set runs in chunks and chunk k's rows travel on a second
+    // stream while chunk k+1 is computed.
+    int n_chunks = 1;
+    if (host_post && copied && !project && post && !forward_only && m->chain.NT > 1 && !m->chain.dense &&
+        b->n_series >= 2048 && (size_t)b->rows * Q.row * sizeof(double) >= chunked_copy_min_bytes()) {
+      bool identity = true;
+      for (int i = 0; i < b->n_series && identity; i++) identity = b->chain.order[i] == i;
+      static const bool off = [] { const char* p = getenv("NIPGPU_CHUNKED_COPY"); return p && p[0] == '0'; }();
+      if (identity && !off) n_chunks = 4;
+    }
+    if (n_chunks > 1) {
+      if (!m->copy_stream) {
+        NIPGPU_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 4; k++) NIPGPU_CUDA(cudaEventCreateWithFlags(&m->chunk_ev[k], cudaEventDisableTiming));
+      }
+      const int per = ((b->n_series + n_chunks - 1) / n_chunks + 31) / 32 * 32;
+      cudaEvent_t first_ev = m->ev0;
+      for (int k = 0; k < n_chunks; k++) {
+        a.p0 = std::min(k * per, b->n_series);
+        a.p1 = std::min(a.p0 + per, b->n_series);
+        if (a.p1 <= a.p0) break;
+        if (int ce = chain_infer(hm, m->chain, b->chain, plan, a, m->stream, first_ev, m->ev1)) return ce;
+        first_ev = nullptr;
+        NIPGPU_CUDA(cudaEventRecord(m->chunk_ev[k], m->stream));
+        NIPGPU_CUDA(cudaStreamWaitEvent(m->copy_stream, m->chunk_ev[k], 0));
+        const long long r0 = b->row_off[a.p0];
+        const long long r1 = a.p1 < b->n_series ? b->row_off[a.p1] : b->rows;
+        NIPGPU_CUDA(cudaMemcpyAsync(host_post + r0 * Q.row, post + r0 * Q.row, (size_t)(r1 - r0) * Q.row * sizeof(double),
+                                    cudaMemcpyDeviceToHost, m->copy_stream));
+      }
+      NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+      NIPGPU_CUDA(cudaStreamSynchronize(m->copy_stream));
+      *copied = true;
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 2 * n_chunks; }
+      return NIPGPU_OK;
+    }
     g_chain_mid_event = m->ev_mid;
     const int ce = chain_infer(hm, m->chain, b->chain, plan, a, m->stream, m->ev0, m->ev1);
     g_chain_mid_event = nullptr;
@@ -492,6 +545,8 @@ void nipgpu_model_destroy(nipgpu_model* m) {
   if (m->h_prop) cudaFreeHost(m->h_prop);
   chain_free(m->chain);
   fac_free(m->fac);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  for (int k = 0; k < 4; k++) if (m->chunk_ev[k]) cudaEventDestroy(m->chunk_ev[k]);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->ev_mid) cudaEventDestroy(m->ev_mid);
@@ -581,6 +636,7 @@ int nipgpu_batch_update(nipgpu_batch* b, const int32_t* data) {
   cudaStream_t st = b->m->stream;
   NIPGPU_CUDA(cudaMemcpyAsync(b->d_obs, data, (size_t)b->rows * b->n_obs * sizeof(int), cudaMemcpyHostToDevice, st));
   b->chain.plan_key.clear();  // cached per-row evidence configuration is stale
+  b->chain.cfgT_key.clear();  // ... and its time-major copy
   // range check on the device (an index >= the cardinality would address past the evidence
   // tables; the reference would index out of bounds, src/nip.c:994)
   if (!b->d_check) {
@@ -623,8 +679,10 @@ int nipgpu_infer(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, 
                  const int32_t* query_vars, int forward_only, double* post, double* loglik) {
   if (!m) return fail(NIPGPU_EINVAL, "null model");
   NIPGPU_CUDA(cudaSetDevice(m->device));
-  if (int e = infer_impl(m, b, use_evidence, n_query, query_vars, forward_only, loglik != nullptr, post != nullptr)) return e;
-  if (post && n_query > 0) {
+  bool copied = false;
+  if (int e = infer_impl(m, b, use_evidence, n_query, query_vars, forward_only, loglik != nullptr, post != nullptr,
+                         post, &copied)) return e;
+  if (post && n_query > 0 && !copied) {
     size_t row = 0;
     for (int i = 0; i < n_query; i++) row += m->hm.card[query_vars[i]];
     NIPGPU_CUDA(cudaMemcpyAsync(post, b->d_post, (size_t)b->rows * row * sizeof(double), cudaMemcpyDeviceToHost, m->stream));

@@ -17,6 +17,8 @@ struct nipgpu_model {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+  cudaStream_t copy_stream = nullptr;      // chunked device-to-host copies of large posterior sets
+  cudaEvent_t chunk_ev[4] = {};
   double last_kernel_ms = 0, last_forward_ms = 0;
   int last_kernel_n = 0;
 

@@ -1514,6 +1514,8 @@ int chain_infer(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   if (int e = chain_prepare_evidence(cm, cb, plan, a, st)) return e;
   ChainBatchDev B;
   B.n_series = a.n_series; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
+  const bool ranged = a.p1 >= 0 && !cm.dense && cm.NT > 1;   // a range of the length-sorted sequences
+  if (ranged) { B.n_series = a.p1 - a.p0; B.order = cb.d_order + a.p0; B.len_sorted = cb.d_len_sorted + a.p0; }
   B.cfg = cb.d_cfg; B.row_off = a.d_row_off;
   B.fexp = cb.d_fexp; B.zc = cb.d_zc; B.zf = cb.d_zf; B.rn_out = cb.d_rn;
   ChainDev C;

@@ -125,6 +125,7 @@ struct ChainInferArgs {
   int post_stride, post_off;
   double* d_ll;                // [n_series] or nullptr
   int* d_status;               // [n_series] or nullptr
+  int p0 = 0, p1 = -1;         // sorted positions [p0, p1) to process (p1 < 0: all) — chunked host copies
 };
 
 // returns false when the plan cannot be served by the chain engine

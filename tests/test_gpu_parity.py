@@ -689,3 +689,45 @@ def test_thread_per_sequence_kernels_large_batch_matches_dmma_kernels(gpu_lib):
             assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
             outs.append(np.load(f))
     assert_close(outs[0], outs[1], "thread-per-sequence vs DMMA kernels", rtol=1e-12)
+
+
+def test_chunked_host_copy_matches_single_pass(gpu_lib, oracle_lib):
+    """host-buffered smoothing of a large equal-length set runs in four chunks of sequences whose
+    rows are copied to the host while the next chunk is computed: same posteriors and
+    log-likelihoods as the single pass (NIPGPU_CHUNKED_COPY=0), and the oracle's on the first and
+    last series (the threshold is lowered to 1 MB so that a 2148-series set qualifies)"""
+    import subprocess
+    import sys
+    import tempfile
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import nip_b200.api as api\n"
+        "from nip_b200.synth import HmmSpec\n"
+        "h = HmmSpec(16, 4, seed=5); data = h.sample(2148, 24, seed=6, missing=0.1)\n"
+        "m = api.Model(h.flat()); b = m.batch(h.obs_vars, [d for d in data])\n"
+        "post, ll = b.infer(h.hidden_query)\n"
+        "b.update(np.ascontiguousarray(data.reshape(-1, 1))); post2, ll2 = b.infer(h.hidden_query)\n"
+        "assert np.array_equal(post, post2) and np.array_equal(ll, ll2)\n"
+        "print('launches', api.launch_count())\n"
+        "np.save(sys.argv[1], np.concatenate([post.ravel(), ll.ravel()]))\n" % ROOT)
+    outs, launches = [], []
+    with tempfile.TemporaryDirectory() as d:
+        for flag in ("1", "0"):
+            env = dict(os.environ, NIPGPU_CHUNKED_COPY=flag, NIPGPU_CHUNKED_COPY_MIN_MB="1")
+            f = os.path.join(d, "o%s.npy" % flag)
+            r = subprocess.run([sys.executable, "-c", code, f], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            launches.append(int(r.stdout.split("launches")[1].split()[0]))
+            outs.append(np.load(f))
+    assert launches[0] > launches[1]            # the chunked run really launched per chunk
+    assert_close(outs[0], outs[1], "chunked vs single pass", rtol=1e-13)
+    from nip_b200.synth import HmmSpec
+    h = HmmSpec(16, 4, seed=5)
+    data = h.sample(2148, 24, seed=6, missing=0.1)
+    om = oracle_lib.model(h.flat())
+    post = outs[0][:2148 * 24 * 16].reshape(2148, 24, 16)
+    ll = outs[0][2148 * 24 * 16:]
+    for i in (0, 2147):
+        want, llw = om.infer(h.obs_vars, data[i], h.hidden_query)
+        assert_close(post[i], want, "chunked copy: series %d" % i)
+        assert_close(ll[i], llw, "chunked copy: loglik %d" % i, atol=1e-12)
