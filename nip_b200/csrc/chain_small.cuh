@@ -87,7 +87,7 @@ struct SmallDev {
 // shared memory: A [S*S] | lam_comb [n_lam][S] (when it fits: n_lam = n_comb, else 0) | toff [n_toff]
 // (the time-major offsets, when they fit: otherwise every slice's address waits for a global load)
 template <int S, bool FILT, bool WLL>
-__global__ void __launch_bounds__(128, S <= 4 ? (WLL ? 6 : 8) : 4) k_chain_small_forward(SmallDev C, int n_lam, int store_alpha,
+__global__ void __launch_bounds__(128) k_chain_small_forward(SmallDev C, int n_lam, int store_alpha,
                                                              double* __restrict__ alphaT,
                                                              double* __restrict__ post, int post_stride,
                                                              int post_off, int post_wide, double* ll_out,
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128, S <= 4 ? (WLL ? 6 : 8) : 4) k_chain_small
 }
 
 template <int S>
-__global__ void __launch_bounds__(128, S <= 4 ? 7 : 4) k_chain_small_backward(SmallDev C, int n_lam, const double* __restrict__ alphaT,
+__global__ void __launch_bounds__(128) k_chain_small_backward(SmallDev C, int n_lam, const double* __restrict__ alphaT,
                                                               double* __restrict__ post, int post_stride,
                                                               int post_off, int post_wide) {
   constexpr int AS = SmallGeom<S>::AS;
