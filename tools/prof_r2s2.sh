@@ -1,3 +1,5 @@
+# ncu evidence of the second half of round 2 (run under gpurun): the thread-per-sequence chain
+# kernels at 1 M x 50 and engine 3's contractions on C3; summaries as text, reports deleted
 cd $GRAFT_REPO_ROOT
 O=gpurun_out
 cap() {  # name, kernel regex, skip, count, command...
@@ -7,5 +9,5 @@ cap() {  # name, kernel regex, skip, count, command...
   rm -f $O/$name.ncu-rep
 }
 cap r02_c1_small "k_chain_small_(forward|backward)" 2 2 python tools/prof_configs.py C1
-cap r02_c3_factor "k_fac_contract" 0 110 env N=32 T=2 python tools/prof_c3.py
+cap r02_c3_factor "k_fac_contract" 0 75 env N=16 T=2 python tools/prof_c3.py
 ls -la $O | tail -5
