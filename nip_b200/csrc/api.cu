@@ -356,12 +356,17 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
     a.n_query = nq; a.query = query; a.post_row = Q.row; a.d_post = post;
     a.want_ll = want_ll; a.forward_only = forward_only;
     NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
-    if (int e = fac_run(hm, m->fac, a, m->stream)) return e;
-    NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
-    NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 0; }
-    return NIPGPU_OK;
+    const int fe = fac_run(hm, m->fac, a, m->stream);
+    if (fe == NIPGPU_EUNSUPPORTED && m->fac_auto) {
+      m->engine = NIPGPU_ENGINE_JTREE;   // a contraction beyond the planner's limits: engine 1 from now on
+    } else {
+      if (fe) return fe;
+      NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+      NIPGPU_CUDA(cudaStreamSynchronize(m->stream));
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) { m->last_kernel_ms = ms; m->last_kernel_n = 0; }
+      return NIPGPU_OK;
+    }
   }
 
   // ---- generic join-tree engine ----
@@ -509,7 +514,7 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
     const bool auto_fac = engine == NIPGPU_ENGINE_AUTO && !m->chain.ok && in_hbm && !(fenv && fenv[0] == '0');
     if (engine == NIPGPU_ENGINE_FACTOR || auto_fac) {
       fac_build(hm, m->fac);
-      if (m->fac.ok) m->engine = NIPGPU_ENGINE_FACTOR;
+      if (m->fac.ok) { m->engine = NIPGPU_ENGINE_FACTOR; m->fac_auto = engine == NIPGPU_ENGINE_AUTO; }
       else if (engine == NIPGPU_ENGINE_FACTOR) {
         const std::string why = m->fac.why;
         nipgpu_model_destroy(m);
@@ -749,12 +754,17 @@ int estep_enqueue(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence,
     fill_fac_args(m, b, use_evidence, &a);
     a.want_ll = 1; a.forward_only = 0; a.d_acc = m->d_acc; a.acc_stride = n; a.acc_slots = slots;
     NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
-    if (int e = fac_run(hm, m->fac, a, m->stream)) return e;
-    NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
-    if (int e = finish_estep(m->d_acc, slots, n, n, add_pseudocount ? 1.0 : 0.0, b->d_ll, b->d_status,
-                             b->n_series, m->d_counts, m->stream)) return e;
-    m->last_kernel_n = 0;
-    return NIPGPU_OK;
+    const int fe = fac_run(hm, m->fac, a, m->stream);
+    if (fe == NIPGPU_EUNSUPPORTED && m->fac_auto) {
+      m->engine = NIPGPU_ENGINE_JTREE;   // see infer_impl
+    } else {
+      if (fe) return fe;
+      NIPGPU_CUDA(cudaEventRecord(m->ev1, m->stream));
+      if (int e = finish_estep(m->d_acc, slots, n, n, add_pseudocount ? 1.0 : 0.0, b->d_ll, b->d_status,
+                               b->n_series, m->d_counts, m->stream)) return e;
+      m->last_kernel_n = 0;
+      return NIPGPU_OK;
+    }
   }
   const int* obs_proj = nullptr;
   if (int e = upload_obs_proj(m, b, use_evidence, true, 0, &obs_proj)) return e;

@@ -48,6 +48,7 @@ struct nipgpu_model {
 
   nipgpu::ChainModel chain;  // engine 2 (valid when hm.chain_ok)
   nipgpu::FacEngine fac;     // engine 3 (valid when fac.ok)
+  bool fac_auto = false;     // engine 3 was the library's own choice: a request it cannot plan goes to engine 1
 
   // ---- single-slice state (stateful API) ----
   std::vector<std::vector<double>> lik;  // host mirror of variable->likelihood

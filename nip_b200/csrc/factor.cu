@@ -663,6 +663,13 @@ struct Compiler {
   long long partial_max = 0;
   bool failed = false;
   bool saving = false;      // tensors created now go to the per-slice saved region
+  // in-loop operands a contraction may have (NIPGPU_FACTOR_MAX_OPS lowers it: the tests use that to
+  // exercise the fallback to engine 1)
+  int max_ops = [] {
+    const char* p = getenv("NIPGPU_FACTOR_MAX_OPS");
+    const int v = p ? atoi(p) : 0;
+    return v >= 1 && v < kFacMaxOps ? v : kFacMaxOps;
+  }();
   std::map<std::vector<int>, int> relayouts;   // (tensor, first variable) -> permuted copy, valid in the current section
 
   Compiler(const HostModel& h, const FacEngine& f) : hm(h), fe(f), T(f.tensors.begin(), f.tensors.begin() + f.n_model_tensors) {}
@@ -875,7 +882,7 @@ struct Compiler {
         (d.tstride != 0 ? varying : d.tstride2 != 0 ? varying2 : shared).push_back(d);
       }
     }
-    if ((int)(shared.size() + varying.size() + varying2.size()) > kFacMaxOps || (int)varying.size() > kFacMaxVar) { failed = true; return out; }
+    if ((int)(shared.size() + varying.size() + varying2.size()) > max_ops || (int)varying.size() > kFacMaxVar) { failed = true; return out; }
     if (TJ > 1 && TK == 1 && (int)shared.size() > 4) { failed = true; return out; }
     for (const FacOpDev& d : shared) s.opR[s.nSh++] = d;
     for (const FacOpDev& d : varying) s.opR[s.nSh + s.nVar++] = d;

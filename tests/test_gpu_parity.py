@@ -731,3 +731,33 @@ def test_chunked_host_copy_matches_single_pass(gpu_lib, oracle_lib):
         want, llw = om.infer(h.obs_vars, data[i], h.hidden_query)
         assert_close(post[i], want, "chunked copy: series %d" % i)
         assert_close(ll[i], llw, "chunked copy: loglik %d" % i, atol=1e-12)
+
+
+def test_factor_engine_falls_back_when_it_cannot_plan(gpu_lib, oracle_lib, monkeypatch):
+    """engine 3 chosen by the library itself (tables too large for shared memory) hands a request
+    it cannot plan — here: the operand limit lowered to 1 — to engine 1 instead of failing; asked
+    for explicitly it reports NIPGPU_EUNSUPPORTED"""
+    from nip_b200.synth import FactorialSpec
+    sp = FactorialSpec(6, 3, seed=4)
+    fm = sp.flat()
+    data = sp.sample(2, 3, seed=5)
+    series = [data[0], data[1][:2]]
+    monkeypatch.setenv("NIPGPU_FACTOR_MAX_OPS", "1")
+    m = gpu_lib.Model(fm, engine=0)
+    assert m.engine == 3
+    b = m.batch(sp.obs_vars, series)
+    post, ll = b.infer([4, 9])
+    assert m.engine == 1
+    om = oracle_lib.model(fm)
+    for i, got in enumerate(b.split(post)):
+        want, llw = om.infer(sp.obs_vars, series[i], [4, 9])
+        assert_close(got, want, "fallback posterior, series %d" % i)
+        assert_close(ll[i], llw, "fallback loglik, series %d" % i)
+    b.close()
+    m.close()
+    m = gpu_lib.Model(fm, engine=3)
+    b = m.batch(sp.obs_vars, series)
+    with pytest.raises(gpu_lib.NipGpuError):
+        b.infer([4, 9])
+    b.close()
+    m.close()
