@@ -133,9 +133,9 @@ class HmmConfig:
         self.f_alg = 4.0 * S * S           # two S x S contractions per slice-step
         self.b_alg = 16.0 * S + 8.0 * S + 8.0   # alpha write + read, posterior, evidence twice
         self.bound = "tensor"
-        self.kernel = ("k_chain_forward<8> + k_chain_backward<8> (one launch each per pass)" if S <= 64 else
+        self.kernel = ("k_chain_forward_team<8,2> + k_chain_backward_team<8,2> (one launch each per pass, + k_chain_final)" if S <= 64 else
                        "k_dense_gemm (one per slice and direction) + settle kernels")
-        self.engine = ("chain (DMMA m8n8k4, warp-resident recursion)" if S <= 64 else
+        self.engine = ("chain (DMMA m8n8k4, recursion resident in the registers of two-warp teams)" if S <= 64 else
                        "dense (per-slice DGEMM on DMMA, 128x128x16 tiles)")
 
     def build(self, seed_data):
@@ -276,8 +276,8 @@ class SmallModelConfig:
             self.metric, self.unit = "slice-steps/sec (forward-backward)", "slice-steps/s"
             self.workload = "%s: examples/model.net, %d series x %d slices, forward-backward smoothing + loglik" % (name, n_series, T)
             self.b_alg = 16.0 * 4 + 8.0 * 4 + 8.0   # 104 B per slice-step
-            self.kernel = "k_chain_forward<1> + k_chain_backward<1>"
-            self.engine = "chain (DMMA m8n8k4, one 8-state tile)"
+            self.kernel = "k_chain_forward<1> + k_chain_backward<1> (365 series); k_chain_small_forward/backward<4> at 1 M series"
+            self.engine = "chain (one 8-state DMMA tile below 2048 series, one thread per sequence above)"
 
     def build(self, seed_data):
         from cases import Case
@@ -369,7 +369,7 @@ class FactorialConfig:
         self.bound = "fp64"
         self.f_alg = 2 * 1.3e8  # 4 stages x 2 x 16^6 flops per direction, factored evaluation
         self.b_alg = 1.0e6      # 16 |I| bytes of forward rows per slice-step
-        self.kernel = "k_fac_contract (multi-operand contractions, ~12 of 16^6 terms per slice-step)"
+        self.kernel = "k_fac_contract / k_fac_contract2 (multi-operand contractions, ~12 of 16^6 terms per slice-step)"
         self.engine = "engine 3: join tree factor by factor (clique tables never materialised)"
 
     def build(self, seed_data):
