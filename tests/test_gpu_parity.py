@@ -761,3 +761,56 @@ def test_factor_engine_falls_back_when_it_cannot_plan(gpu_lib, oracle_lib, monke
         b.infer([4, 9])
     b.close()
     m.close()
+
+
+def test_factor_engine_follows_parameter_changes(gpu_lib, oracle_lib):
+    """engine 3 works on factors extracted from the clique tables: nipgpu_model_set_parameters
+    (new tables from the host: extraction + verification again) and nipgpu_em_mstep (factors =
+    the normalised counts, on the device) must both be followed; tables that are NOT products of
+    their families' CPTs are still served (the model drops to engine 1)"""
+    from nip_b200.synth import FactorialSpec
+    sp1, sp2 = FactorialSpec(6, 3, seed=4), FactorialSpec(6, 3, seed=9)
+    fm1, fm2 = sp1.flat(), sp2.flat()
+    data = sp1.sample(3, 3, seed=5, missing=0.2)
+    data[:, 0, :] = np.abs(data[:, 0, :])
+    series = [data[0], data[1][:2], data[2][:1]]
+    query = [5, 10, 1]
+    m = gpu_lib.Model(fm1, engine=0)
+    assert m.engine == 3
+    b = m.batch(sp1.obs_vars, series)
+
+    def check(fm, what):
+        om = oracle_lib.model(fm)
+        post, ll = b.infer(query)
+        for i, got in enumerate(b.split(post)):
+            want, llw = om.infer(sp1.obs_vars, series[i], query)
+            assert_close(got, want, "%s: posterior %d" % (what, i))
+            assert_close(ll[i], llw, "%s: loglik %d" % (what, i))
+        counts, L, st = b.estep()
+        want, Lw, stw = om.estep(sp1.obs_vars, series)
+        assert st == stw == 0
+        assert_close(counts, want, what + ": expected counts")
+        return counts
+
+    check(fm1, "as created")
+    m.set_parameters(fm2.clique_tables, fm2.var_prior)
+    assert m.engine == 3
+    counts = check(fm2, "after set_parameters")
+    m.mstep(counts)                                 # factors <- normalised counts, on the device
+    t, p = m.parameters()
+    fm3 = sp2.flat()
+    fm3.clique_tables[:] = t
+    fm3.var_prior[:] = p
+    check(fm3, "after an M-step")
+    # a table that is no product of CPTs: multiply one entry of a big clique
+    t2 = t.copy()
+    big = int(np.argmax(np.diff(fm3.clique_tab_off)))
+    t2[int(fm3.clique_tab_off[big]) + 7] *= 1.5
+    m.set_parameters(t2, p)
+    assert m.engine == 1
+    fm4 = sp2.flat()
+    fm4.clique_tables[:] = t2
+    fm4.var_prior[:] = p
+    check(fm4, "tables that do not factor (engine 1)")
+    b.close()
+    m.close()
