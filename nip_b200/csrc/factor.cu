@@ -259,7 +259,9 @@ __device__ __forceinline__ double fac_inv(double x) { return x != 0 ? 1.0 / x : 
 // result(o) [chunk] = prod_{epilogue operands}(o) * sum_{r in chunk} prod_k operand_k(o, r)
 // for the TJ results of a thread at once: `NSH` in-loop operands do not depend on the tile
 // variable (one load per term of the tile), `NV` do (TJ loads).
-template <int NSH, int NV, int TJ>
+// EV: some in-loop operand is an evidence vector (a compare instead of a load); the kernels
+// without such operands do not carry the test through their inner loop.
+template <int NSH, int NV, int TJ, bool EV>
 __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
   constexpr int NR = NSH + NV;
   extern __shared__ int s_roff[];   // [NR][cpc * Rc]
@@ -299,7 +301,8 @@ __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
   for (int j = 0; j < TJ; j++) acc[j] = NR == 0 ? 1.0 : 0.0;
   if (NR > 0) {
     auto value = [&](int k, int off) -> double {
-      return ptr[k] ? ptr[k][off] : ((ev[k] == INT_MIN || off == ev[k]) ? 1.0 : 0.0);
+      if constexpr (EV) return ptr[k] ? ptr[k][off] : ((ev[k] == INT_MIN || off == ev[k]) ? 1.0 : 0.0);
+      else return ptr[k][off];
     };
 #pragma unroll 4
     for (int r = 0; r < nr; r++) {
@@ -387,9 +390,7 @@ __global__ void __launch_bounds__(128) k_fac_contract2(FacStepDev s, SlotCtx X) 
       ptr[k] = (op.kind == FT_MODEL ? X.fac : area + (op.kind == FT_SAVED ? X.saved_off : 0)) + op.off + ob;
     }
   }
-  auto value = [&](int k, int off) -> double {
-    return ptr[k] ? ptr[k][off] : ((ev[k] == INT_MIN || off == ev[k]) ? 1.0 : 0.0);
-  };
+  auto value = [&](int k, int off) -> double { return ptr[k][off]; };   // the planner keeps evidence operands out
   double acc[TJ][TK];
 #pragma unroll
   for (int j = 0; j < TJ; j++)
@@ -814,7 +815,9 @@ struct Compiler {
     // ---- a second tile variable: no in-loop operand may hold both (outer product of two slices) ----
     int vt2 = -1, TK = 1;
     static const bool no_2d = [] { const char* p = getenv("NIPGPU_FACTOR_TILE2"); return p && p[0] == '0'; }();
-    if (vt >= 0 && !no_2d) {
+    bool evid_in_loop = false;
+    for (const FacOpRef& o : ops) evid_in_loop = evid_in_loop || (T[o.tensor].kind == FT_EVID && depends(T[o.tensor]));
+    if (vt >= 0 && !no_2d && !evid_in_loop) {
       int n1 = 0, nsh = 0;
       for (const FacOpRef& o : ops) {
         const FacTensor& t = T[o.tensor];
@@ -1141,7 +1144,10 @@ template <int NSH, int NV, int TJ>
 void launch_contract_n(const FacStepDev& s, const SlotCtx& X, int alive, cudaStream_t st) {
   const dim3 grid(s.cpc > 1 ? 1 : (s.n_thr + 127) / 128, (s.n_chunks + s.cpc - 1) / s.cpc, alive);
   const size_t smem = (size_t)std::max(NSH + NV, 1) * s.cpc * s.Rc * sizeof(int);
-  k_fac_contract<NSH, NV, TJ><<<grid, 128, smem, st>>>(s, X);
+  bool ev = false;
+  for (int k = 0; k < s.nSh + s.nVar; k++) ev = ev || s.opR[k].kind == FT_EVID;
+  if (ev) k_fac_contract<NSH, NV, TJ, true><<<grid, 128, smem, st>>>(s, X);
+  else k_fac_contract<NSH, NV, TJ, false><<<grid, 128, smem, st>>>(s, X);
 }
 
 template <int NSH, int TJ>
