@@ -93,7 +93,13 @@ int nipgpu_device_check(int device);
 /* Compile a model: index maps / projections, message schedule, device upload
  * of original_p and priors.  Replaces the per-call nip_mapper()+malloc of
  * nip_message_pass (src/nipjointree.c:676-709) and the per-entry
- * nip_inverse_mapping loops (src/nippotential.c:251-264). */
+ * nip_inverse_mapping loops (src/nippotential.c:251-264).
+ * engine: NIPGPU_ENGINE_AUTO lets the library choose (chain-structured model ->
+ * CHAIN; clique tables that fit shared memory -> JTREE; larger ones -> FACTOR
+ * when every table verifiably is the product of its families' CPTs, which is
+ * what parse_model / m_step build, src/nip.c:2044-2067; else JTREE streaming
+ * them).  Asking for CHAIN or FACTOR on a model they cannot serve fails with
+ * NIPGPU_EUNSUPPORTED. */
 int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine,
                         nipgpu_model** out);
 void nipgpu_model_destroy(nipgpu_model* m);
