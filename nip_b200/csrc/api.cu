@@ -907,7 +907,8 @@ int nipgpu_likelihood(nipgpu_model* m, nipgpu_batch* b, const uint8_t* evidence_
     S.n_series = nc; S.n_obs = b->n_obs; S.len = d_len; S.row_off = d_off; S.obs = d_obs; S.obs_proj = nullptr;
     NIPGPU_CUDA(cudaEventRecord(m->ev0, m->stream));
     if ((e = jt_likelihood(m->prog, S, p_off, p_on, jt_fit(m->launch, nc), d_table, m->stream)) ||
-        (e = jt_like_gather(b->d_obs, b->n_obs, b->rows, b->d_first, d_cs, d_cc, d_table, b->d_like, m->sm_count, m->stream))) {
+        (e = jt_like_gather(b->d_obs, b->n_obs, b->rows, b->d_first, d_cs, d_cc, d_table, b->d_like, m->sm_count, m->stream,
+                            col_stride[0], col_card[0]))) {
       cleanup();
       return e;
     }

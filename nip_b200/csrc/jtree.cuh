@@ -104,8 +104,11 @@ int jt_likelihood(const DProgram& p, const DBatch& b, const int* proj_off, const
 // memoised likelihood loop: flags of the rows that open a series; per-record gather from the
 // per-configuration table ([n_cfg][2 kinds][m1, m2])
 int jt_first_rows(const long long* row_off, int n_series, long long rows, unsigned char* first, cudaStream_t st);
+// host_stride0 / host_card0: the first column's stride and cardinality as the host knows them (a set
+// with one data column takes a vectorised kernel)
 int jt_like_gather(const int* obs, int n_obs, long long rows, const unsigned char* first, const int* col_stride,
-                   const int* col_card, const double* table, double* out, int sm_count, cudaStream_t st);
+                   const int* col_card, const double* table, double* out, int sm_count, cudaStream_t st,
+                   int host_stride0 = 0, int host_card0 = 0);
 int jt_calibrate(const DProgram& p, const JtLaunch& l, double* R1, double* m1_0, cudaStream_t st);
 // single-slice propagation for the stateful API: tables <- base x lik, collect, distribute
 int jt_slice(const DProgram& p, const JtLaunch& l, const double* start_tables, double* out_tables,
