@@ -71,11 +71,13 @@ __global__ void k_chain_mats(const double* base0, const double* base1, const int
 }
 
 __global__ void k_chain_phi0(const double* base0, const int* ent_of, int S, double* phi0) {
-  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  // a warp per current state: the lanes share the sum over the previous states
+  const int ip = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ip >= S) return;
   double s = 0;
-  for (int im = 0; im < S; im++) s += base0[ent_of[im * S + ip]];
-  phi0[ip] = s;
+  for (int im = lane; im < S; im += 32) s += base0[ent_of[im * S + ip]];
+  s = warp_sum(s);
+  if (lane == 0) phi0[ip] = s;
 }
 
 // meta: [n_free, card[0..n_free), stride[0..n_free)] — Lambda[cfg][ip] = sum over the leaf's
@@ -795,24 +797,59 @@ __global__ void k_chain_first(const long long* row_off, int n_series, long long 
   if (s < n_series && row_off[s] < rows) first[row_off[s]] = 1;
 }
 
-// out[x] = sum_p part[p][x] in a fixed order
-__global__ void k_chain_sum_parts(const double* part, int parts, long long n, double* out) {
-  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
-       x += (long long)gridDim.x * blockDim.x) {
+// out[x] = sum_p part[p][x] in a fixed association: a CTA owns 32 outputs, warp g adds the parts
+// g, g+8, g+16, ... in order (two running sums: the loads of a thread do not wait for each other),
+// the eight group sums are added in order.  One thread per output walking all the parts was a
+// chain of `parts` dependent loads (37 us for 148 parts of a 64 x 64 table).
+__global__ void __launch_bounds__(256) k_chain_sum_parts(const double* __restrict__ part, int parts, long long n,
+                                                         double* __restrict__ out) {
+  __shared__ double red[8][33];
+  const int lx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const long long x = blockIdx.x * 32LL + lx;
+  double s0 = 0, s1 = 0;
+  if (x < n) {
+    int p = g;
+    for (; p + 8 < parts; p += 16) {
+      s0 += part[(long long)p * n + x];
+      s1 += part[(long long)(p + 8) * n + x];
+    }
+    if (p < parts) s0 += part[(long long)p * n + x];
+  }
+  red[g][lx] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && x < n) {
     double s = 0;
-    for (int p = 0; p < parts; p++) s += part[(long long)p * n + x];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += red[k][lx];
     out[x] = s;
   }
 }
 
-// g0[ip] = sum over series of r0[series][ip]   (one block per column, fixed reduction order)
-__global__ void k_chain_g0(const double* r0, int n_series, int SP, double* g0) {
-  __shared__ double red[40];
-  const int ip = blockIdx.x;
+// column sums of r0 [n_series][SP], first stage: CTA c adds the rows [c * per, (c + 1) * per) — whole
+// rows per warp-load, 256 / SP rows at a time — into part[c][SP] (fixed order); k_chain_sum_parts
+// adds the CTAs' rows.  (One block per column read one double per 512-byte row.)
+__global__ void __launch_bounds__(256) k_chain_g0_part(const double* __restrict__ r0, int n_series, int SP, int per,
+                                                       double* __restrict__ part) {
+  __shared__ double red[256];
+  const int b0 = blockIdx.x * per, b1 = min(n_series, b0 + per);
+  if (SP > 256 || 256 % SP != 0) {   // wide interfaces (dense engine): a thread per column, rows in order
+    for (int col = threadIdx.x; col < SP; col += 256) {
+      double s = 0;
+      for (int b = b0; b < b1; b++) s += r0[(long long)b * SP + col];
+      part[(long long)blockIdx.x * SP + col] = s;
+    }
+    return;
+  }
+  const int col = threadIdx.x % SP, grp = threadIdx.x / SP, groups = 256 / SP;
   double s = 0;
-  for (int b = threadIdx.x; b < n_series; b += blockDim.x) s += r0[(long long)b * SP + ip];
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) g0[ip] = s;
+  for (int b = b0 + grp; b < b1; b += groups) s += r0[(long long)b * SP + col];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (grp == 0) {
+    double t = 0;
+    for (int k = 0; k < groups; k++) t += red[k * SP + col];
+    part[(long long)blockIdx.x * SP + col] = t;
+  }
 }
 
 // expected table of the interface clique over all slices (E) and over first slices (E0)
@@ -839,7 +876,8 @@ struct LeafExpect {
 __global__ void k_chain_expect_leaf(const double* base1, const int* pbase, const int* poff,
                                     const int* ip_to_s, LeafExpect L, const double* Cc,
                                     const double* lam, double* E) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  // a warp per table entry: the lanes share the sum over the evidence configurations
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (x >= L.m * L.R) return;
   const int s = x / L.R, r = x - s * L.R;
   const int entry = pbase[s] + poff[r];
@@ -854,12 +892,13 @@ __global__ void k_chain_expect_leaf(const double* base1, const int* pbase, const
     for (int ip = 0; ip < L.S; ip++) {
       if (ip_to_s[ip] != s) continue;
       lam_s = lam[L.lam_off + (long long)cl * L.SP + ip];
-      for (int c = 0; c < L.n_comb; c++)
+      for (int c = lane; c < L.n_comb; c += 32)
         if (L.slot < 0 || (c / L.mult) % L.n_cfg == cl) mass += Cc[(long long)c * L.SP + ip];
     }
+    mass = warp_sum(mass);
     if (lam_s != 0) W += mass / lam_s;
   }
-  E[entry] = base1[entry] * W;
+  if (lane == 0) E[entry] = base1[entry] * W;
 }
 
 // counts[j] = pseudo + sum_r E[base[j] + off[r]]   (family table of one variable)
@@ -1255,10 +1294,10 @@ int chain_refresh(const HostModel& hm, ChainModel& cm, const double* d_base0, co
       NIPGPU_LAUNCHED();
     }
   }
-  k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base0 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_phi0);
+  k_chain_phi0<<<(S + 3) / 4, 128, 0, st>>>(d_base0 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_phi0);
   NIPGPU_LAUNCHED();
   NIPGPU_CUDA(cudaMemsetAsync(cm.d_colsum, 0, cm.SP * sizeof(double), st));
-  k_chain_phi0<<<(S + 127) / 128, 128, 0, st>>>(d_base1 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_colsum);
+  k_chain_phi0<<<(S + 3) / 4, 128, 0, st>>>(d_base1 + tab_off[cm.c0], cm.d_ent_of, S, cm.d_colsum);
   NIPGPU_LAUNCHED();
   for (int l = 0; l < cm.n_real; l++) {
     const ChainLeafHost& L = cm.leaves[l];
@@ -1933,11 +1972,12 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
       NIPGPU_LAUNCHED();
     }
   }
-  // scratch: part_G | G | g0 | part_C | Cc | E | E0
+  // scratch: part_G | G | g0 | part_C | Cc | E | E0 | work | part_g0
   const size_t n_partG = (size_t)parts * SP * SP, n_G = (size_t)SP * SP, n_partC = (size_t)partsC * tab;
   const size_t n_E = (size_t)hm.toff[hm.nc], n_E0 = (size_t)hm.csize[cm.c0];
   const size_t n_work = dense ? 2 * (size_t)rows : 0;   // dense_stats: N_k and pair weights
-  const size_t need = n_partG + n_G + SP + n_partC + tab + n_E + n_E0 + n_work;
+  const int g0_parts = std::max(1, std::min(64, (a.n_series + 63) / 64));
+  const size_t need = n_partG + n_G + SP + n_partC + tab + n_E + n_E0 + n_work + (size_t)g0_parts * SP;
   if (cb.em_scratch_cap < need) {
     cudaFree(cb.d_em_scratch);
     cb.d_em_scratch = nullptr;
@@ -1952,6 +1992,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   double* E = Cc + tab;
   double* E0 = E + n_E;
   double* work = E0 + n_E0;
+  double* part_g0 = work + n_work;
 
   ChainBatchDev B;
   B.n_series = a.n_series; B.order = cb.d_order; B.len_sorted = cb.d_len_sorted;
@@ -1990,11 +2031,13 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
   } else {
     NIPGPU_CUDA(cudaMemsetAsync(partG, 0, (n_partG + n_G + SP + n_partC) * sizeof(double), st));
   }
-  k_chain_sum_parts<<<(unsigned)((n_G + 255) / 256), 256, 0, st>>>(partG, parts, (long long)n_G, G);
+  k_chain_sum_parts<<<(unsigned)((n_G + 31) / 32), 256, 0, st>>>(partG, parts, (long long)n_G, G);
   NIPGPU_LAUNCHED();
-  k_chain_g0<<<SP, 256, 0, st>>>(cb.d_r0, a.n_series, SP, g0);
+  k_chain_g0_part<<<g0_parts, 256, 0, st>>>(cb.d_r0, a.n_series, SP, (a.n_series + g0_parts - 1) / g0_parts, part_g0);
   NIPGPU_LAUNCHED();
-  k_chain_sum_parts<<<(unsigned)((tab + 255) / 256), 256, 0, st>>>(partC, partsC, (long long)tab, Cc);
+  k_chain_sum_parts<<<(unsigned)((SP + 31) / 32), 256, 0, st>>>(part_g0, g0_parts, (long long)SP, g0);
+  NIPGPU_LAUNCHED();
+  k_chain_sum_parts<<<(unsigned)((tab + 31) / 32), 256, 0, st>>>(partC, partsC, (long long)tab, Cc);
   NIPGPU_LAUNCHED();
   if (ev1) NIPGPU_CUDA(cudaEventRecord(ev1, st));
   // ---- expected clique tables ----
@@ -2015,7 +2058,7 @@ int chain_estep(const HostModel& hm, const ChainModel& cm, ChainBatch& cb, const
     L.n_cfg = Lh.n_cfg; L.miss_cfg = Lh.miss_cfg;
     L.m = p.m; L.R = p.R; L.S = S; L.SP = SP; L.n_comb = plan.n_comb; L.lam_off = Lh.lam_off;
     const int n = p.m * p.R;
-    k_chain_expect_leaf<<<(n + 127) / 128, 128, 0, st>>>(x.d_base1 + (*x.tab_off)[Lh.clique], x.d_ipool + p.base_pos,
+    k_chain_expect_leaf<<<(n + 3) / 4, 128, 0, st>>>(x.d_base1 + (*x.tab_off)[Lh.clique], x.d_ipool + p.base_pos,
                                                          x.d_ipool + p.off_pos, cm.d_ip_to_s + (size_t)l * S, L, Cc,
                                                          cm.d_lam, E + (*x.tab_off)[Lh.clique]);
     NIPGPU_LAUNCHED();
