@@ -1088,10 +1088,32 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
       for (int k = 0; k < hm.clique_dim(c); k++)
         if (has_var(U[c], hm.clique_vars(c)[k])) uv.push_back(hm.clique_vars(c)[k]);
       belief = C.contract(P.bwd, uv, false, all);
-      for (const Target& t : targets) {
-        if (t.clique != c) continue;
-        int src = belief;
-        if (t.vars != C.T[belief].vars) src = C.contract(P.bwd, t.vars, true, {FacOpRef{belief, false}});
+      // every marginal comes from the smallest tensor already computed here that holds its
+      // variables (largest targets first: a 16-entry marginal is summed out of a 4096-entry
+      // family table, not out of the belief again)
+      std::vector<int> made{belief};
+      auto smallest_source = [&](const std::vector<int>& vars) {
+        int best = belief;
+        for (int t : made) {
+          bool holds = true;
+          for (int v : vars) holds = holds && has_var(C.T[t].vars, v);
+          if (holds && C.T[t].size < C.T[best].size) best = t;
+        }
+        return best;
+      };
+      std::vector<int> mine;
+      for (size_t ti = 0; ti < targets.size(); ti++)
+        if (targets[ti].clique == c) mine.push_back((int)ti);
+      std::stable_sort(mine.begin(), mine.end(), [&](int x, int y) {
+        return prod_card(hm, targets[x].vars) > prod_card(hm, targets[y].vars);
+      });
+      for (int ti : mine) {
+        const Target& t = targets[ti];
+        int src = smallest_source(t.vars);
+        if (t.vars != C.T[src].vars) {
+          src = C.contract(P.bwd, t.vars, true, {FacOpRef{src, false}});
+          made.push_back(src);
+        }
         FacInstr ins;
         ins.kind = t.kind;
         ins.src_off = C.T[src].off;
@@ -1102,7 +1124,8 @@ int compile(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, bool counts
         P.bwd.push_back(ins);
       }
       for (int d : leaf_kids)
-        down[d] = C.contract(P.bwd, sep_vars(fe.psep[d]), false, {FacOpRef{belief, false}, FacOpRef{up[d], true}});
+        down[d] = C.contract(P.bwd, sep_vars(fe.psep[d]), false,
+                             {FacOpRef{smallest_source(sep_vars(fe.psep[d])), false}, FacOpRef{up[d], true}});
     }
     for (int d : inner_kids) {
       std::vector<FacOpRef> ops;
