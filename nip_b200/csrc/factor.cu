@@ -729,6 +729,46 @@ struct Compiler {
     for (const FacOpRef& o : ops)
       for (int v : T[o.tensor].vars)
         if (!has_var(ovars_in, v) && !has_var(rvars, v)) rvars.push_back(v);
+    // A contraction that sums several variables over three or more operands: when one summed
+    // variable is held by only some of them, it is summed out of THOSE first (an intermediate over
+    // the variables they hold) — fewer operands per term in both halves, and halves with two
+    // in-loop operands take the 2-D register tile.
+    static const bool no_split = [] { const char* p = getenv("NIPGPU_FACTOR_SPLIT"); return p && p[0] == '0'; }();
+    if (rvars.size() >= 2 && !no_split) {
+      auto in_loop = [&](const FacTensor& t) {
+        for (int v : t.vars)
+          if (has_var(rvars, v)) return true;
+        return false;
+      };
+      int n_in = 0;
+      for (const FacOpRef& o : ops) n_in += in_loop(T[o.tensor]) ? 1 : 0;
+      int best_r = -1;
+      long long best_size = 0;
+      std::vector<int> best_vars;
+      if (n_in >= 3)
+        for (int r : rvars) {
+          std::vector<int> iv;
+          int n_r = 0;
+          for (const FacOpRef& o : ops) {
+            const FacTensor& t = T[o.tensor];
+            if (!has_var(t.vars, r)) continue;
+            n_r++;
+            for (int v : t.vars)
+              if (v != r && !has_var(iv, v)) iv.push_back(v);
+          }
+          if (n_r == 0 || n_r >= n_in) continue;
+          const long long size = prod_card(hm, iv);
+          if (size > (1 << 21)) continue;
+          if (best_r < 0 || size < best_size) { best_r = r; best_size = size; best_vars = iv; }
+        }
+      if (best_r >= 0) {
+        std::vector<FacOpRef> first, rest;
+        for (const FacOpRef& o : ops) (has_var(T[o.tensor].vars, best_r) ? first : rest).push_back(o);
+        const int mid = contract(prog, best_vars, false, first, needs_history, relayout);
+        rest.push_back(FacOpRef{mid, false});
+        return contract(prog, ovars_in, fixed, rest, needs_history, relayout);
+      }
+    }
     const long long R = prod_card(hm, rvars);
     auto depends = [&](const FacTensor& t) {
       for (int v : t.vars)
