@@ -1,5 +1,4 @@
-# ncu evidence of the second half of round 2 (run under gpurun): the thread-per-sequence chain
-# kernels at 1 M x 50 and engine 3's contractions on C3; summaries as text, reports deleted
+# ncu evidence of the final kernels (run under gpurun): likelihood gather (C5) and engine 3's contractions (C3)
 cd $GRAFT_REPO_ROOT
 O=gpurun_out
 cap() {  # name, kernel regex, skip, count, command...
@@ -8,6 +7,6 @@ cap() {  # name, kernel regex, skip, count, command...
   python tools/ncu_summary.py $O/$name.ncu-rep x > $O/${name}_ncu_full.txt 2>&1
   rm -f $O/$name.ncu-rep
 }
-cap r02_c1_small "k_chain_small_(forward|backward)" 2 2 python tools/prof_configs.py C1
-cap r02_c3_factor "k_fac_contract" 0 75 env N=16 T=2 python tools/prof_c3.py
-ls -la $O | tail -5
+cap r02_c5_final "k_jt_like" 2 2 python tools/prof_configs.py C5
+cap r02_c3_factor_final "k_fac_contract" 0 80 env N=8 T=2 python tools/prof_c3.py
+ls -la $O | tail -4
