@@ -105,6 +105,11 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine,
 void nipgpu_model_destroy(nipgpu_model* m);
 /* which engine the compiler picked (NIPGPU_ENGINE_*) */
 int nipgpu_model_engine(const nipgpu_model* m);
+/* Host-only check, no device needed: is every clique table of the description the
+ * product of the CPTs of the families it hosts (what parse_model and m_step build,
+ * src/nip.c:2044-2067), i.e. can NIPGPU_ENGINE_FACTOR serve the model?  1: yes;
+ * 0: no (the reason is in nipgpu_last_error()); < 0: malformed description. */
+int nipgpu_model_factorable(const nipgpu_model_desc* desc);
 
 /* Replace all clique tables / priors (same layout as in the description), e.g.
  * after the host changed original_p.  Replaces nothing in the reference: it is

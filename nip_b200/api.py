@@ -24,7 +24,7 @@ EBADLUCK = 8
 # every symbol include/nipgpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "nipgpu_last_error", "nipgpu_device_check", "nipgpu_model_create", "nipgpu_model_destroy",
-    "nipgpu_model_engine", "nipgpu_model_set_parameters", "nipgpu_model_get_parameters",
+    "nipgpu_model_engine", "nipgpu_model_factorable", "nipgpu_model_set_parameters", "nipgpu_model_get_parameters",
     "nipgpu_batch_create", "nipgpu_batch_destroy", "nipgpu_batch_update", "nipgpu_infer", "nipgpu_infer_device",
     "nipgpu_em_estep", "nipgpu_model_counts_size", "nipgpu_model_counts_offsets",
     "nipgpu_em_counts_device", "nipgpu_em_mstep", "nipgpu_likelihood", "nipgpu_slice_reset",
@@ -61,6 +61,7 @@ def load_library(path=LIB_PATH):
     L.nipgpu_model_destroy.argtypes = [_vp]
     L.nipgpu_model_destroy.restype = None
     L.nipgpu_model_engine.argtypes = [_vp]
+    L.nipgpu_model_factorable.argtypes = [_vp]
     L.nipgpu_model_set_parameters.argtypes = [_vp, _vp, _vp]
     L.nipgpu_model_get_parameters.argtypes = [_vp, _vp, _vp]
     L.nipgpu_batch_create.argtypes = [_vp, _i, _vp, _i, _vp, _vp, C.POINTER(_vp)]
@@ -130,6 +131,17 @@ def probe_peaks(device=0):
     a, b, c = _d(), _d(), _d()
     _check(load_library().nipgpu_probe_peaks(int(device), C.byref(a), C.byref(b), C.byref(c)))
     return a.value, b.value, c.value
+
+
+def factorable(fm: FlatModel):
+    """host-only: can engine 3 serve this model (every clique table = product of its families' CPTs)?
+    Returns (bool, reason)."""
+    L = load_library()
+    desc = fm.to_ctypes()
+    rc = int(L.nipgpu_model_factorable(C.byref(desc)))
+    if rc < 0:
+        raise NipGpuError(-rc, (L.nipgpu_last_error() or b"").decode())
+    return rc == 1, ("" if rc == 1 else (L.nipgpu_last_error() or b"").decode())
 
 
 def launch_count(reset=False):

@@ -560,6 +560,16 @@ void nipgpu_model_destroy(nipgpu_model* m) {
 }
 
 int nipgpu_model_engine(const nipgpu_model* m) { return m ? m->engine : 0; }
+
+int nipgpu_model_factorable(const nipgpu_model_desc* desc) {
+  HostModel hm;
+  const std::string err = hm.load(desc);
+  if (!err.empty()) return -fail(NIPGPU_EINVAL, "model description: " + err);
+  FacEngine fe;
+  fac_build(hm, fe);
+  if (!fe.ok) set_error("factor engine: " + fe.why);
+  return fe.ok ? 1 : 0;
+}
 void* nipgpu_model_stream(nipgpu_model* m) { return m ? (void*)m->stream : nullptr; }
 
 int nipgpu_model_set_parameters(nipgpu_model* m, const double* tables, const double* prior) {

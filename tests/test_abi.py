@@ -49,3 +49,31 @@ def test_missing_library_is_loud(tmp_path):
             api.load_library(str(tmp_path / "libnipgpu.so"))
     finally:
         api._lib = api_lib
+
+
+from cases import ALL_CASES
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_factor_extraction_on_the_host(name):
+    """engine 3's factor extraction and verification are host code (no device): every fixture the
+    reference generated — structural zeros, no interface, shared observations included — factors
+    into its families' CPTs"""
+    ok, why = api.factorable(Case(name).fm)
+    assert ok, why
+
+
+def test_factor_extraction_refuses_tables_that_do_not_factor():
+    """one entry of a 6-variable clique of the factorial model changed: the table is no longer a
+    product of 3-variable CPTs, the check says which clique, and a malformed description is an
+    error, not a 'no'"""
+    fm = Case("factorial4x3").fm
+    big = int(np.argmax(np.diff(fm.clique_tab_off)))
+    lo, hi = int(fm.clique_tab_off[big]), int(fm.clique_tab_off[big + 1])
+    fm.clique_tables[lo + int(np.argmax(fm.clique_tables[lo:hi]))] *= 1.25
+    ok, why = api.factorable(fm)
+    assert not ok and ("clique %d" % big) in why
+    bad = Case("hmm5").fm
+    bad.var_family[0] = 99
+    with pytest.raises(api.NipGpuError):
+        api.factorable(bad)
