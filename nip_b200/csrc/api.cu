@@ -350,7 +350,6 @@ int infer_impl(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence, in
 
   // ---- engine 3: factor by factor ----
   if (m->engine == NIPGPU_ENGINE_FACTOR && m->fac.ok) {
-    if (int e = ensure_alpha(m, b)) return e;
     FacRunArgs a{};
     fill_fac_args(m, b, use_evidence, &a);
     a.n_query = nq; a.query = query; a.post_row = Q.row; a.d_post = post;
@@ -750,7 +749,6 @@ int estep_enqueue(nipgpu_model* m, nipgpu_batch* b, const uint8_t* use_evidence,
     if (rc != NIPGPU_EUNSUPPORTED) return rc;
   }
   if (m->engine == NIPGPU_ENGINE_FACTOR && m->fac.ok) {
-    if (int e = ensure_alpha(m, b)) return e;
     const int slots = fac_slots(hm, m->fac, b->n_series);
     if (m->acc_groups < (size_t)slots) {
       cudaFree(m->d_acc);

@@ -475,14 +475,15 @@ __global__ void k_fac_reduce(SlotCtx X, long long part_off, long long out_off, i
 
 // start of a slice: alpha_in <- alpha_{t-1} (or the prior product on first slices); backward:
 // beta <- 1 on the last slice of a sequence
-__global__ void k_fac_prepare(SlotCtx X, const int* len_sorted, const double* alpha, int S, long long o_alpha_in,
-                              long long o_beta, long long a0_off, int set_beta /*0 no, 1 where last, 2 all*/,
-                              double* ll_run, int* bad_run, int reset_ll) {
+// (the forward rows live in a store of the wave, [slot][t_rows][S]: a sequence needs them from its
+// own forward pass to its own backward pass only, so HBM holds W x T of them, not one per data row)
+__global__ void k_fac_prepare(SlotCtx X, const int* len_sorted, const double* alpha, int t_rows, int S,
+                              long long o_alpha_in, long long o_beta, long long a0_off,
+                              int set_beta /*0 no, 1 where last, 2 all*/, double* ll_run, int* bad_run, int reset_ll) {
   const int slot = blockIdx.y;
   double* area = X.slots + (long long)slot * X.slot_stride;
   const int p = X.wave0 + slot;
-  const long long row0 = X.row_off[X.order[p]];
-  const double* src = X.t == 0 ? X.fac + a0_off : alpha + (row0 + X.t - 1) * S;
+  const double* src = X.t == 0 ? X.fac + a0_off : alpha + ((long long)slot * t_rows + X.t - 1) * S;
   const bool beta1 = set_beta == 2 || (set_beta == 1 && len_sorted[p] - 1 == X.t);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
     area[o_alpha_in + i] = src[i];
@@ -496,8 +497,8 @@ __global__ void k_fac_prepare(SlotCtx X, const int* len_sorted, const double* al
 __global__ void __launch_bounds__(1024) k_fac_settle_fwd(SlotCtx X, const int* len_sorted, const int* marked, int S,
                                                          long long o_alpha_in, long long o_alpha_new,
                                                          const double* R1, const double* m1_0, double* alpha,
-                                                         int want_ll, int nif, double* ll_run, int* bad_run,
-                                                         double* ll_out, int* status_out) {
+                                                         int t_rows, int want_ll, int nif, double* ll_run,
+                                                         int* bad_run, double* ll_out, int* status_out) {
   __shared__ double red[40];
   const int slot = blockIdx.x;
   double* area = X.slots + (long long)slot * X.slot_stride;
@@ -508,7 +509,8 @@ __global__ void __launch_bounds__(1024) k_fac_settle_fwd(SlotCtx X, const int* l
   for (int i = threadIdx.x; i < S; i += blockDim.x) s += an[i];
   double m2 = block_sum(s, red);
   const double inv = m2 != 0 ? 1.0 / m2 : 1.0;      // zero sum: untouched (nip_normalise_array)
-  for (int i = threadIdx.x; i < S; i += blockDim.x) alpha[(row0 + X.t) * S + i] = an[i] * inv;
+  double* arow = alpha + ((long long)slot * t_rows + X.t) * S;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) arow[i] = an[i] * inv;
   if (want_ll) {
     double m1;
     if (X.t == 0) m1 = *m1_0;
@@ -643,6 +645,7 @@ void fac_free(FacEngine& fe) {
   cudaFree(fe.d_slots);
   cudaFree(fe.d_ll_run);
   cudaFree(fe.d_bad_run);
+  cudaFree(fe.d_alpha_wave);
   for (auto& kv : fe.programs) {
     cudaFree(kv.second.d_pool);
     cudaFree(kv.second.d_marked);
@@ -1293,7 +1296,7 @@ struct RunCtx {
   const FacRunArgs* a;
   FacEngine* fe;
   const int* d_len_sorted;
-  int S, nif;
+  int S, nif, t_rows;
   bool no_beta_update;   // filtering: beta stays 1, no message to slice t-1
 };
 
@@ -1318,7 +1321,7 @@ int run_instr(const RunCtx& R, const FacInstr& ins, const SlotCtx& X, int alive,
     }
     case FI_SETTLE_FWD:
       k_fac_settle_fwd<<<alive, 1024, 0, st>>>(X, R.d_len_sorted, P.d_marked, R.S, P.o_alpha_in, P.o_alpha_new,
-                                               a.d_R1, a.d_m10, a.d_alpha, a.want_ll, R.nif, R.fe->d_ll_run,
+                                               a.d_R1, a.d_m10, R.fe->d_alpha_wave, R.t_rows, a.want_ll, R.nif, R.fe->d_ll_run,
                                                R.fe->d_bad_run, a.d_ll, a.d_status);
       NIPGPU_LAUNCHED();
       return NIPGPU_OK;
@@ -1396,13 +1399,24 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
   }
   const long long slot_doubles = P.slot_doubles + P.saved_doubles * (keep_ups ? t_longest : 1);
   const size_t slot_bytes = (size_t)slot_doubles * sizeof(double);
-  while (W > 1 && (size_t)W * slot_bytes > budget) W--;
+  const size_t row_bytes = (size_t)t_longest * std::max(hm.S, 1) * sizeof(double);   // its forward rows
+  while (W > 1 && (size_t)W * (slot_bytes + row_bytes) > budget) W--;
   if (fe.slots_cap < (size_t)W * slot_doubles) {
     cudaFree(fe.d_slots);
     fe.d_slots = nullptr;
     fe.slots_cap = 0;
     NIPGPU_CUDA(cudaMalloc((void**)&fe.d_slots, (size_t)W * slot_bytes));
     fe.slots_cap = (size_t)W * slot_doubles;
+  }
+  {   // forward rows of the sequences in flight
+    const size_t need = (size_t)W * t_longest * std::max(hm.S, 1);
+    if (fe.alpha_cap < need) {
+      cudaFree(fe.d_alpha_wave);
+      fe.d_alpha_wave = nullptr;
+      fe.alpha_cap = 0;
+      NIPGPU_CUDA(cudaMalloc((void**)&fe.d_alpha_wave, need * sizeof(double)));
+      fe.alpha_cap = need;
+    }
   }
   if (fe.max_slots < W) {
     cudaFree(fe.d_ll_run); cudaFree(fe.d_bad_run);
@@ -1420,7 +1434,7 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
     cudaFree(d_len_sorted);
     return rc;
   };
-  RunCtx R{&P, &a, &fe, d_len_sorted, hm.S, hm.nif, false};
+  RunCtx R{&P, &a, &fe, d_len_sorted, hm.S, hm.nif, t_longest, false};
   // NIPGPU_FACTOR_TRACE=1: device time of every instruction of the first wave's slices (stderr)
   static const bool trace = [] { const char* p = getenv("NIPGPU_FACTOR_TRACE"); return p && p[0] == '1'; }();
   std::vector<double> tr_f(P.fwd.size(), 0.0), tr_b(P.bwd.size(), 0.0);
@@ -1460,7 +1474,7 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
       if (alive == 0) break;
       X.t = t;
       X.saved_off = P.slot_doubles + (keep_ups ? (long long)t * P.saved_doubles : 0);
-      k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, a.d_alpha, hm.nif > 0 ? S : 0,
+      k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, fe.d_alpha_wave, t_longest, hm.nif > 0 ? S : 0,
                                                               P.o_alpha_in, P.o_beta, a0_off, filtered ? 2 : 0,
                                                               fe.d_ll_run, fe.d_bad_run, t == 0);
       NIPGPU_LAUNCHED();
@@ -1481,7 +1495,7 @@ int fac_run(const HostModel& hm, FacEngine& fe, const FacRunArgs& a, cudaStream_
         if (alive == 0) continue;
         X.t = t;
         X.saved_off = P.slot_doubles + (keep_ups ? (long long)t * P.saved_doubles : 0);
-        k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, a.d_alpha, S, P.o_alpha_in, P.o_beta,
+        k_fac_prepare<<<dim3(prep_blocks, alive), 256, 0, st>>>(X, d_len_sorted, fe.d_alpha_wave, t_longest, S, P.o_alpha_in, P.o_beta,
                                                                 a0_off, 1, fe.d_ll_run, fe.d_bad_run, 0);
         NIPGPU_LAUNCHED();
         for (size_t i = keep_ups ? P.n_ups : 0; i < P.bwd.size(); i++)

@@ -123,6 +123,8 @@ struct FacEngine {
   // run-time buffers
   double* d_slots = nullptr;
   size_t slots_cap = 0;
+  double* d_alpha_wave = nullptr;   // [slots][longest series][S] forward rows of the sequences in flight
+  size_t alpha_cap = 0;
   double* d_ll_run = nullptr;   // [max slots] running log-likelihood
   int* d_bad_run = nullptr;
   int max_slots = 0;
@@ -152,7 +154,7 @@ struct FacRunArgs {
   int post_row;                        // doubles per output row
   double* d_post;                      // or nullptr
   int want_ll, forward_only;
-  double* d_alpha;                     // [rows][S]
+  double* d_alpha;                     // unused (the engine keeps the forward rows of a wave itself)
   double* d_ll;
   int* d_status;
   const double* d_R1;

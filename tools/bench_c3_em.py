@@ -47,6 +47,7 @@ if rank == 0:
     s = out[-1]["seconds"]
     print(json.dumps({"config": "C3: factorial 4x16 ring-coupled, %d series x %d slices, EM" % (N, T), "n_gpus": world,
                       "iterations": out, "em_iterations_per_s": 1.0 / s, "slice_steps_per_s": N * T / s,
-                      "alpha_store_GB_per_gpu": per * T * 65536 * 8 / 1e9}))
+                      "forward_rows_GB_per_gpu": min(64, per) * T * 65536 * 8 / 1e9,
+                      "forward_rows_note": "engine 3 keeps the rows of the 64 sequences in flight only (a store per data row would be %.1f GB per GPU)" % (per * T * 65536 * 8 / 1e9)}))
 if world > 1:
     dist.destroy_process_group()
