@@ -281,12 +281,13 @@ __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
   double* area = X.slots + (long long)slot * X.slot_stride;
   const long long row = X.row_off[X.order[X.wave0 + slot]] + X.t;
   const double* ptr[NR > 0 ? NR : 1];
-  int ev[NR > 0 ? NR : 1], ts[NR > 0 ? NR : 1];
+  int ev[NR > 0 ? NR : 1], ts[NR > 0 ? NR : 1][TJ];
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     const FacOpDev& op = s.opR[k];
     const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
-    ts[k] = op.tstride;
+#pragma unroll
+    for (int j = 0; j < TJ; j++) ts[k][j] = op.toff[j];
     if (op.kind == FT_EVID) {
       const int obs = X.obs[row * X.n_obs + op.col];
       ev[k] = obs < 0 ? INT_MIN : obs - ob;   // the operand is 1 where its offset == ev (everywhere when missing)
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
         double term = sh;
 #pragma unroll
         for (int k = NSH; k < NR; k++) {
-          const double v = value(k, roff[k * span + r] + j * ts[k]);
+          const double v = value(k, roff[k * span + r] + ts[k][j]);
           term = (NSH == 0 && k == NSH) ? v : term * v;
         }
         acc[j] += term;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
     else q = (op.kind == FT_MODEL ? X.fac : area + (op.kind == FT_SAVED ? X.saved_off : 0)) + op.off;
 #pragma unroll
     for (int j = 0; j < TJ; j++) {
-      const int off = ob + j * op.tstride;
+      const int off = ob + op.toff[j];
       double v;
       if (op.kind == FT_EVID) v = (obs < 0 || obs == off) ? 1.0 : 0.0;
       else {
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(128) k_fac_contract(FacStepDev s, SlotCtx X) {
   double* dst = area + (s.out.kind == FT_SAVED ? X.saved_off : 0) + s.out.off +
                 (s.n_chunks > 1 ? (long long)chunk * s.n_out : 0);
 #pragma unroll
-  for (int j = 0; j < TJ; j++) dst[oo + j * s.out.tstride] = acc[j];
+  for (int j = 0; j < TJ; j++) dst[oo + s.out.toff[j]] = acc[j];
 }
 
 // The same contraction with a 2-D register tile: TJ x TK results per thread along two output
@@ -375,12 +376,13 @@ __global__ void __launch_bounds__(128) k_fac_contract2(FacStepDev s, SlotCtx X) 
   double* area = X.slots + (long long)slot * X.slot_stride;
   const long long row = X.row_off[X.order[X.wave0 + slot]] + X.t;
   const double* ptr[NR];
-  int ev[NR], ts[NR];
+  int ev[NR], ts[NR][4];
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     const FacOpDev& op = s.opR[k];
     const int ob = X.pool[op.ohi + oh] + X.pool[op.olo + ol];
-    ts[k] = k < NSH + NV ? op.tstride : op.tstride2;
+#pragma unroll
+    for (int j = 0; j < 4; j++) ts[k][j] = k < NSH + NV ? op.toff[j] : op.toff2[j];
     if (op.kind == FT_EVID) {
       const int obs = X.obs[row * X.n_obs + op.col];
       ev[k] = obs < 0 ? INT_MIN : obs - ob;
@@ -401,15 +403,15 @@ __global__ void __launch_bounds__(128) k_fac_contract2(FacStepDev s, SlotCtx X) 
     double a[TJ], b[TK];
 #pragma unroll
     for (int j = 0; j < TJ; j++) {
-      a[j] = value(NSH, roff[NSH * span + r] + j * ts[NSH]);
+      a[j] = value(NSH, roff[NSH * span + r] + ts[NSH][j]);
 #pragma unroll
-      for (int k = NSH + 1; k < NSH + NV; k++) a[j] *= value(k, roff[k * span + r] + j * ts[k]);
+      for (int k = NSH + 1; k < NSH + NV; k++) a[j] *= value(k, roff[k * span + r] + ts[k][j]);
     }
 #pragma unroll
     for (int q = 0; q < TK; q++) {
-      b[q] = value(NSH + NV, roff[(NSH + NV) * span + r] + q * ts[NSH + NV]);
+      b[q] = value(NSH + NV, roff[(NSH + NV) * span + r] + ts[NSH + NV][q]);
 #pragma unroll
-      for (int k = NSH + NV + 1; k < NR; k++) b[q] *= value(k, roff[k * span + r] + q * ts[k]);
+      for (int k = NSH + NV + 1; k < NR; k++) b[q] *= value(k, roff[k * span + r] + ts[k][q]);
     }
     if (NSH > 0) {
       double sh = value(0, roff[r]);
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(128) k_fac_contract2(FacStepDev s, SlotCtx X) 
     for (int j = 0; j < TJ; j++)
 #pragma unroll
       for (int q = 0; q < TK; q++) {
-        const int off = ob + j * op.tstride + q * op.tstride2;
+        const int off = ob + op.toff[j] + op.toff2[q];
         double v;
         if (op.kind == FT_EVID) v = (obs < 0 || obs == off) ? 1.0 : 0.0;
         else {
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(128) k_fac_contract2(FacStepDev s, SlotCtx X) 
 #pragma unroll
   for (int j = 0; j < TJ; j++)
 #pragma unroll
-    for (int q = 0; q < TK; q++) dst[oo + j * s.out.tstride + q * s.out.tstride2] = acc[j][q];
+    for (int q = 0; q < TK; q++) dst[oo + s.out.toff[j] + s.out.toff2[q]] = acc[j][q];
 }
 
 // out[o] = sum over chunks of partial[chunk][o], fixed order
@@ -835,65 +837,106 @@ struct Compiler {
         if (v != v0) ovars.push_back(v);
     }
     const int out = slot_tensor(ovars);
-    // ---- the tile variable: the output variable the in-loop operands depend on least ----
-    int vt = -1, TJ = 1;
+    // ---- register tiles.  A tile holds four results: along one output variable whose cardinality
+    // is a multiple of 4, or over 2 x 2 states of two variables of even cardinality (binary
+    // variables).  First tile: the one the in-loop operands depend on least (they are loaded once
+    // per term of the tile when they do not hold its variables).
+    typedef std::vector<std::pair<int, int>> Tile;   // (variable, states per thread)
+    auto holds = [&](const FacTensor& t, const Tile& tl) {
+      for (const auto& e : tl)
+        if (has_var(t.vars, e.first)) return true;
+      return false;
+    };
+    std::vector<Tile> candidates;
+    for (int v : ovars) {
+      if (v == v0 && ovars.size() > 1) continue;
+      if (hm.card[v] % 4 == 0) candidates.push_back(Tile{{v, 4}});
+    }
+    for (size_t a = 0; a < ovars.size(); a++)
+      for (size_t b = a + 1; b < ovars.size(); b++) {
+        const int va = ovars[a], vb = ovars[b];
+        if (va == v0 || vb == v0) continue;
+        if (hm.card[va] % 2 != 0 || hm.card[vb] % 2 != 0) continue;
+        if (hm.card[va] % 4 == 0 && hm.card[vb] % 4 == 0) continue;   // each of them can carry a tile alone
+        candidates.push_back(Tile{{va, 2}, {vb, 2}});
+      }
+    Tile tile1, tile2;
+    int TJ = 1, TK = 1;
     if (R > 1) {
       double best = -1;
-      for (int v : ovars) {
-        if (v == v0 && ovars.size() > 1) continue;
-        if (hm.card[v] % 4 != 0) continue;
+      for (const Tile& tl : candidates) {
         double sc = 0;
         int nvar = 0;
         for (const FacOpRef& o : ops) {
           const FacTensor& t = T[o.tensor];
-          if (!depends(t) || !has_var(t.vars, v)) continue;
+          if (!depends(t) || !holds(t, tl)) continue;
           sc += (double)t.size;
           nvar++;
         }
         if (nvar > kFacMaxVar) continue;
-        if (best < 0 || sc < best) { best = sc; vt = v; }
+        if (best < 0 || sc < best) { best = sc; tile1 = tl; }
       }
-      if (vt >= 0) TJ = 4;
+      if (!tile1.empty()) TJ = 4;
     }
-    // ---- a second tile variable: no in-loop operand may hold both (outer product of two slices) ----
-    int vt2 = -1, TK = 1;
+    // ---- a second tile: no in-loop operand may hold variables of both (outer product of two slices) ----
     static const bool no_2d = [] { const char* p = getenv("NIPGPU_FACTOR_TILE2"); return p && p[0] == '0'; }();
     bool evid_in_loop = false;
     for (const FacOpRef& o : ops) evid_in_loop = evid_in_loop || (T[o.tensor].kind == FT_EVID && depends(T[o.tensor]));
-    if (vt >= 0 && !no_2d && !evid_in_loop) {
+    if (!tile1.empty() && !no_2d && !evid_in_loop) {
       int n1 = 0, nsh = 0;
       for (const FacOpRef& o : ops) {
         const FacTensor& t = T[o.tensor];
         if (!depends(t)) continue;
-        (has_var(t.vars, vt) ? n1 : nsh)++;
+        (holds(t, tile1) ? n1 : nsh)++;
       }
       double best = -1;
-      for (int v : ovars) {
-        if (v == v0 || v == vt || hm.card[v] % 4 != 0) continue;
+      for (const Tile& tl : candidates) {
+        bool overlap = false;
+        for (const auto& e : tl)
+          for (const auto& f : tile1) overlap = overlap || e.first == f.first;
+        if (overlap) continue;
         double sc = 0;
         int n2 = 0;
         bool both = false;
         for (const FacOpRef& o : ops) {
           const FacTensor& t = T[o.tensor];
-          if (!depends(t) || !has_var(t.vars, v)) continue;
-          if (has_var(t.vars, vt)) both = true;
+          if (!depends(t) || !holds(t, tl)) continue;
+          if (holds(t, tile1)) both = true;
           sc += (double)t.size;
           n2++;
         }
-        // templates exist for 1..2 operands per tile variable and up to 2 shared ones
+        // templates exist for 1..2 operands per tile and up to 2 shared ones
         if (both || n2 < 1 || n2 > 2 || n1 < 1 || n1 > 2 || nsh - n2 > 2 || nsh - n2 < 0) continue;
-        if (best < 0 || sc < best) { best = sc; vt2 = v; }
+        if (best < 0 || sc < best) { best = sc; tile2 = tl; }
       }
-      if (vt2 >= 0) TK = 4;
+      if (!tile2.empty()) TK = 4;
     }
+    auto in_tile = [&](int v) {
+      for (const auto& e : tile1) if (e.first == v) return e.second;
+      for (const auto& e : tile2) if (e.first == v) return e.second;
+      return 0;
+    };
     // thread space: v0 first, then the blocks of the tile variables (threads that share the heavy
     // operands' entries sit next to each other: one trip to HBM, the rest L1/L2 hits), then the rest
     std::vector<int> tv, tmult;
-    if (v0 >= 0 && v0 != vt) { tv.push_back(v0); tmult.push_back(1); }
-    if (vt >= 0) { tv.push_back(vt); tmult.push_back(TJ); }
-    if (vt2 >= 0) { tv.push_back(vt2); tmult.push_back(TK); }
+    if (v0 >= 0 && !in_tile(v0)) { tv.push_back(v0); tmult.push_back(1); }
+    for (const auto& e : tile1) { tv.push_back(e.first); tmult.push_back(e.second); }
+    for (const auto& e : tile2) { tv.push_back(e.first); tmult.push_back(e.second); }
     for (int v : ovars)
-      if (v != vt && v != v0 && v != vt2) { tv.push_back(v); tmult.push_back(1); }
+      if (v != v0 && !in_tile(v)) { tv.push_back(v); tmult.push_back(1); }
+    // offsets of a tile's four elements inside a tensor (element j: first tile variable fastest)
+    auto tile_offsets = [&](const FacTensor& t, const Tile& tl, int* out4) {
+      for (int j = 0; j < 4; j++) {
+        int rem = j;
+        long long o = 0;
+        for (const auto& e : tl) {
+          o += (rem % e.second) * stride_in(hm, t.vars, e.first);
+          rem /= e.second;
+        }
+        out4[j] = tl.empty() ? 0 : (int)o;
+      }
+    };
+    const int vt = tile1.empty() ? -1 : tile1[0].first, vt2 = tile2.empty() ? -1 : tile2[0].first;   // (trace only)
     const long long n_out = T[out].size, n_thr = n_out / (TJ * TK);
     FacInstr ins;
     ins.kind = FI_CONTRACT;
@@ -910,8 +953,8 @@ struct Compiler {
     auto dev = [&](const FacTensor& t, bool inv, bool dep) {
       FacOpDev d{};
       d.off = t.off; d.kind = t.kind; d.inv = inv ? 1 : 0; d.col = t.col;
-      d.tstride = vt >= 0 ? (int)stride_in(hm, t.vars, vt) : 0;
-      d.tstride2 = vt2 >= 0 ? (int)stride_in(hm, t.vars, vt2) : 0;
+      tile_offsets(t, tile1, d.toff);
+      tile_offsets(t, tile2, d.toff2);
       tables(t, tv, tmult, F, n_thr, rvars, dep ? R : 0, d);
       return d;
     };
@@ -925,7 +968,7 @@ struct Compiler {
         s.opO[s.nO++] = d;
       } else {
         if (o.inv) { failed = true; return out; }
-        (d.tstride != 0 ? varying : d.tstride2 != 0 ? varying2 : shared).push_back(d);
+        (holds(t, tile1) ? varying : holds(t, tile2) ? varying2 : shared).push_back(d);
       }
     }
     if ((int)(shared.size() + varying.size() + varying2.size()) > max_ops || (int)varying.size() > kFacMaxVar) { failed = true; return out; }

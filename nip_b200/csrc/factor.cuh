@@ -50,8 +50,10 @@ struct FacOpDev {
   long long off;           // offset of the tensor (MODEL: in d_fac, SLOT: in the slot area)
   int kind, inv, col;
   int olo, ohi, roff;      // positions of its index tables in the int pool
-  int tstride;             // step along the tile variable (0: the operand does not hold it)
-  int tstride2;            // step along the second tile variable of a 2-D register tile
+  int toff[4];             // offsets of the register tile's four elements (all 0: the operand does not
+                           // hold the tile's variables); a tile runs along one variable whose cardinality
+                           // is a multiple of 4, or over 2 x 2 states of two even-cardinality variables
+  int toff2[4];            // the same for the second tile of a 2-D register tile
 };
 
 constexpr int kFacMaxOps = 8;

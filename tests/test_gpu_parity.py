@@ -316,7 +316,8 @@ def test_launches_are_counted(gpu_lib):
 
 # ---- factorial DBN (config C3): cliques too large for shared memory ------------------------
 @pytest.mark.parametrize("coupled", [True, False])
-@pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None), (8, "grid"), (6, "factor"), (8, "factor")])
+@pytest.mark.parametrize("ns,mode", [(6, "hbm"), (6, "grid"), (8, None), (8, "grid"), (6, "factor"), (8, "factor"),
+                                     (2, "factor"), (10, "factor")])   # 2 x 2 tiles over pairs of even-cardinality variables
 def test_factorial_vs_oracle(gpu_lib, oracle_lib, ns, mode, coupled, monkeypatch):
     """4 ring-coupled chains (C3's topology) with cliques too large for shared memory, in the
     per-CTA HBM workspace and with the whole grid streaming one sequence: smoothing, filtering
