@@ -409,6 +409,17 @@ int nipgpu_device_check(int device) {
   return NIPGPU_OK;
 }
 
+// inside nipgpu_model_create: a CUDA failure releases the half-built model (stream, events, device memory)
+#define CREATE_CUDA(call)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                       \
+      nipgpu_model_destroy(m);                                                              \
+      return NIPGPU_ECUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
 int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, nipgpu_model** out) {
   if (!out) return fail(NIPGPU_EINVAL, "null out pointer");
   *out = nullptr;
@@ -428,12 +439,12 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
                   ? engine
                   : (m->chain.ok ? NIPGPU_ENGINE_CHAIN : NIPGPU_ENGINE_JTREE);
   cudaDeviceProp prop;
-  NIPGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+  CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
   m->sm_count = prop.multiProcessorCount;
-  NIPGPU_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  NIPGPU_CUDA(cudaEventCreate(&m->ev0));
-  NIPGPU_CUDA(cudaEventCreate(&m->ev1));
-  NIPGPU_CUDA(cudaEventCreate(&m->ev_mid));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaEventCreate(&m->ev0));
+  CREATE_CUDA(cudaEventCreate(&m->ev1));
+  CREATE_CUDA(cudaEventCreate(&m->ev_mid));
   cudaStream_t st = m->stream;
 
   // ---- table offsets (int: the reference indexes tables with int too) ----
@@ -476,17 +487,17 @@ int nipgpu_model_create(const nipgpu_model_desc* desc, int device, int engine, n
     nipgpu_model_destroy(m);
     return e;
   }
-  NIPGPU_CUDA(cudaStreamSynchronize(st));  // the temporaries above die here
+  CREATE_CUDA(cudaStreamSynchronize(st));  // the temporaries above die here
   const size_t T = (size_t)m->tab_off[hm.nc];
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_prior_flags, std::max<size_t>(hm.prior_vars.size(), 1) * sizeof(int)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_base0, T * sizeof(double)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_base1, T * sizeof(double)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_R1, (size_t)hm.S * sizeof(double)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_m10, sizeof(double)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_counts, (size_t)(hm.coff[hm.nv] + 2) * sizeof(double)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_slice_start, T * sizeof(double)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_slice_tab, T * sizeof(double)));
-  NIPGPU_CUDA(cudaMalloc((void**)&m->d_slice_msg, (size_t)std::max(hm.msg_total, 1) * sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_prior_flags, std::max<size_t>(hm.prior_vars.size(), 1) * sizeof(int)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_base0, T * sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_base1, T * sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_R1, (size_t)hm.S * sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_m10, sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_counts, (size_t)(hm.coff[hm.nv] + 2) * sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_slice_start, T * sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_slice_tab, T * sizeof(double)));
+  CREATE_CUDA(cudaMalloc((void**)&m->d_slice_msg, (size_t)std::max(hm.msg_total, 1) * sizeof(double)));
 
   DProgram& P = m->prog;
   P.tab_total = (int)T; P.msg_total = hm.msg_total; P.msg_max = hm.msg_max;
