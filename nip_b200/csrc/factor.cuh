@@ -59,10 +59,13 @@ struct FacOpDev {
 constexpr int kFacMaxOps = 8;
 constexpr int kFacMaxVar = 4;   // operands that vary along the register tile
 
-// One contraction.  A thread owns TJ results that differ in ONE output variable (the tile
-// variable, chosen so that the heavy operands do not hold it and are loaded once per term);
-// thread index -> (offset of every operand, offset of the result) through the olo/ohi tables,
-// consecutive threads run along the variable that is fastest in the heavy operands' memory.
+// One contraction.  A thread owns a register tile of TJ (x TK) results: TJ = 4 along one output
+// variable (or 2 x 2 states of two even-cardinality variables) chosen so that the heavy operands
+// do not hold it and are loaded once per term of the tile; TK = 4 along a second such tile when
+// no in-loop operand holds variables of both (the term is then the outer product of two
+// operand slices).  Thread index -> (offset of every operand, offset of the result) through the
+// olo/ohi tables; consecutive threads run along the variable that is fastest in the heavy
+// operands' memory.
 struct FacStepDev {
   int n_thr, F, R, Rc, n_chunks, TJ;
   int cpc, othr;           // results of few threads: a CTA covers `cpc` consecutive chunks, `othr` threads each
